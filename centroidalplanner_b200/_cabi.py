@@ -1,0 +1,105 @@
+"""ctypes binding of libcplb.so (the C ABI in include/cpl_batched.h).
+
+The library is the product; this module only declares its prototypes.  It fails loudly when
+the shared object is missing -- there is no Python/NumPy fallback for the evaluation path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcplb.so")
+
+OK, INVALID_ARGUMENT, OUT_OF_RANGE, RUNTIME_ERROR, CUDA_ERROR, NULL_POINTER = range(6)
+ENV_NONE, ENV_GROUND, ENV_SUPERQUADRIC = 0, 1, 2
+INSTANCE_MAJOR, COMPONENT_MAJOR = 0, 1
+BLOCK_COM, BLOCK_FORCE, BLOCK_POSITION, BLOCK_NORMAL = 0, 1, 2, 3
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+
+
+class EvalArgs(C.Structure):
+    _fields_ = [
+        ("num_instances", C.c_int64),
+        ("layout", C.c_int32),
+        ("reserved", C.c_int32),
+        ("ld", C.c_int64),
+        ("x", C.c_void_p),
+        ("g", C.c_void_p),
+        ("jac", C.c_void_p),
+        ("cost", C.c_void_p),
+        ("grad", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/cpl_batched.h declares
+PROTOTYPES = {
+    "cplb_create": (C.c_int, [C.c_int32, C.POINTER(C.c_char_p), C.c_int, C.c_double, C.c_int32, C.POINTER(C.c_void_p)]),
+    "cplb_destroy": (None, [C.c_void_p]),
+    "cplb_last_error": (C.c_char_p, []),
+    "cplb_abi_version": (C.c_int32, []),
+    "cplb_get_dims": (C.c_int, [C.c_void_p, ip, ip, ip]),
+    "cplb_get_jacobian_structure": (C.c_int, [C.c_void_p, ip, ip]),
+    "cplb_get_sorted_order": (C.c_int, [C.c_void_p, ip]),
+    "cplb_get_block_column": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, ip]),
+    "cplb_get_contact_row": (C.c_int, [C.c_void_p, C.c_char_p, ip]),
+    "cplb_get_variable_bounds": (C.c_int, [C.c_void_p, dp, dp]),
+    "cplb_get_constraint_bounds": (C.c_int, [C.c_void_p, dp, dp]),
+    "cplb_set_mass": (C.c_int, [C.c_void_p, C.c_double]),
+    "cplb_get_mass": (C.c_int, [C.c_void_p, dp]),
+    "cplb_set_manipulation_wrench": (C.c_int, [C.c_void_p, dp]),
+    "cplb_get_manipulation_wrench": (C.c_int, [C.c_void_p, dp]),
+    "cplb_set_mu": (C.c_int, [C.c_void_p, C.c_double]),
+    "cplb_get_mu": (C.c_int, [C.c_void_p, dp]),
+    "cplb_set_ground_z": (C.c_int, [C.c_void_p, C.c_double]),
+    "cplb_get_ground_z": (C.c_int, [C.c_void_p, dp]),
+    "cplb_set_superquadric": (C.c_int, [C.c_void_p, dp, dp, dp]),
+    "cplb_get_superquadric": (C.c_int, [C.c_void_p, dp, dp, dp]),
+    "cplb_set_force_threshold": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "cplb_get_force_threshold": (C.c_int, [C.c_void_p, C.c_char_p, dp]),
+    "cplb_set_bounds": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, dp, dp]),
+    "cplb_get_bounds": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, dp, dp]),
+    "cplb_set_pos_ref": (C.c_int, [C.c_void_p, C.c_char_p, dp]),
+    "cplb_get_pos_ref": (C.c_int, [C.c_void_p, C.c_char_p, dp]),
+    "cplb_set_force_ref": (C.c_int, [C.c_void_p, C.c_char_p, dp]),
+    "cplb_get_force_ref": (C.c_int, [C.c_void_p, C.c_char_p, dp]),
+    "cplb_set_com_ref": (C.c_int, [C.c_void_p, dp]),
+    "cplb_get_com_ref": (C.c_int, [C.c_void_p, dp]),
+    "cplb_set_com_weight": (C.c_int, [C.c_void_p, C.c_double]),
+    "cplb_get_com_weight": (C.c_int, [C.c_void_p, dp]),
+    "cplb_set_pos_weight": (C.c_int, [C.c_void_p, C.c_double]),
+    "cplb_set_force_weight": (C.c_int, [C.c_void_p, C.c_double]),
+    "cplb_set_contact_pos_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "cplb_get_contact_pos_weight": (C.c_int, [C.c_void_p, C.c_char_p, dp]),
+    "cplb_set_contact_force_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "cplb_get_contact_force_weight": (C.c_int, [C.c_void_p, C.c_char_p, dp]),
+    "cplb_eval_device": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs), C.c_void_p]),
+    "cplb_eval_host": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs)]),
+    "cplb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cplb_host_free": (C.c_int, [C.c_void_p]),
+    "cplb_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "cplb_timing_begin": (C.c_int, [C.c_void_p]),
+    "cplb_timing_end": (C.c_int, [C.c_void_p, dp, C.POINTER(C.c_int64)]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libcplb.so.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C centroidalplanner_b200/csrc`. The evaluator has no CPU fallback."
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

@@ -1,0 +1,785 @@
+// cplb_abi.cu -- implementation of the C ABI declared in include/cpl_batched.h.
+// Host-only code (parameter bookkeeping with the reference's validation predicates, layout, the
+// host<->device pipeline); the arithmetic lives in cplb_kernels.cu.  There is NO CPU evaluation
+// path in this library: without a CUDA device every evaluation fails with CPLB_CUDA_ERROR.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "cpl_batched.h"
+#include "cplb_kernels.h"
+#include "cplb_layout.hpp"
+#include "cplb_params.h"
+
+namespace {
+
+thread_local char g_last_error[512] = "";
+
+cplb_status fail(cplb_status st, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof g_last_error, fmt, ap);
+    va_end(ap);
+    return st;
+}
+
+cplb_status cuda_fail(cudaError_t e, const char* what)
+{
+    return fail(CPLB_CUDA_ERROR, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+#define CPLB_CUDA(call)                                      \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+#define CPLB_REQUIRE(ptr)                                                          \
+    do {                                                                           \
+        if ((ptr) == nullptr) return fail(CPLB_NULL_POINTER, "%s is NULL", #ptr); \
+    } while (0)
+
+constexpr int kHostStreams = 3;
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+struct cplb_problem {
+    std::vector<std::string> names;
+    cplb_env_kind env = CPLB_ENV_NONE;
+    int device = 0;
+    double mass = 100.0;
+    double sqC[3] = {0.0, 0.0, 10.0}, sqR[3] = {10.0, 10.0, 10.0}, sqP[3] = {10.0, 10.0, 10.0};
+    cplb::Layout layout;
+    CplbParams P{};
+    std::vector<double> x_lb, x_ub;
+    std::atomic<long long> launches{0};
+
+    // kernel timing (cplb_timing_begin/end)
+    std::mutex timing_mu;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+
+    // cplb_eval_host pipeline
+    std::mutex host_mu;
+    cudaStream_t streams[kHostStreams] = {};
+    double* stage[kHostStreams] = {};
+    size_t stage_bytes = 0;
+    bool streams_ready = false;
+
+    int find(const char* name) const
+    {
+        if (!name) return -1;
+        for (size_t k = 0; k < names.size(); k++)
+            if (names[k] == name) return (int)k;
+        return -1;
+    }
+
+    void refresh_derived()
+    {
+        // _m * _g with _g = (0, 0, -9.81) (CentroidalStatics.cpp:15,57): one multiply per component
+        const double g[3] = {0.0, 0.0, -9.81};
+        for (int i = 0; i < 3; i++) P.mg[i] = mass * g[i];
+        for (int q = 0; q < 3; q++) {
+            P.sqC[q] = sqC[q];
+            P.sqR[q] = sqR[q];
+            P.sqP[q] = sqP[q];
+            const double twoP = sqP[q] * 2.0;
+            P.sqPoverRP[q] = sqP[q] / std::pow(sqR[q], sqP[q]);
+            P.sqRmP[q] = std::pow(sqR[q], -sqP[q]);
+            P.sqRm2P[q] = std::pow(sqR[q], -twoP);
+            P.sqR2P[q] = std::pow(sqR[q], twoP);
+        }
+    }
+};
+
+extern "C" {
+
+const char* cplb_last_error(void) { return g_last_error; }
+int32_t cplb_abi_version(void) { return CPLB_ABI_VERSION; }
+
+cplb_status cplb_create(int32_t num_contacts, const char* const* contact_names, cplb_env_kind env, double robot_mass,
+                        int32_t device, cplb_problem** out)
+{
+    CPLB_REQUIRE(out);
+    *out = nullptr;
+    CPLB_REQUIRE(contact_names);
+    if (num_contacts < 1) return fail(CPLB_INVALID_ARGUMENT, "at least one contact is required");
+    if (num_contacts > CPLB_MAX_CONTACTS)
+        return fail(CPLB_INVALID_ARGUMENT, "at most %d contacts are supported (got %d)", CPLB_MAX_CONTACTS, num_contacts);
+    if (env != CPLB_ENV_NONE && env != CPLB_ENV_GROUND && env != CPLB_ENV_SUPERQUADRIC)
+        return fail(CPLB_INVALID_ARGUMENT, "unknown environment kind %d", (int)env);
+    if (!(robot_mass > 0.0)) return fail(CPLB_INVALID_ARGUMENT, "Invalid robot mass");  // CentroidalPlanner.cpp:12-15
+
+    if (device >= 0) {  // an explicit ordinal is validated now; -1 binds to the caller's current device at first evaluation
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            return fail(CPLB_CUDA_ERROR, "no usable CUDA device (%s); this library has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        if (device >= ndev) return fail(CPLB_INVALID_ARGUMENT, "device %d out of range (%d devices)", device, ndev);
+    }
+
+    cplb_problem* p = new (std::nothrow) cplb_problem();
+    if (!p) return fail(CPLB_RUNTIME_ERROR, "out of host memory");
+    for (int k = 0; k < num_contacts; k++) {
+        if (!contact_names[k]) {
+            delete p;
+            return fail(CPLB_NULL_POINTER, "contact_names[%d] is NULL", k);
+        }
+        if (p->find(contact_names[k]) >= 0) {
+            delete p;
+            return fail(CPLB_INVALID_ARGUMENT, "duplicate contact name '%s'", contact_names[k]);
+        }
+        p->names.emplace_back(contact_names[k]);
+    }
+    p->env = env;
+    p->device = device;
+    p->mass = robot_mass;
+    p->layout.build(p->names, env != CPLB_ENV_NONE);
+
+    CplbParams& P = p->P;
+    std::memset(&P, 0, sizeof P);
+    P.nc = num_contacts;
+    P.env = (int)env;
+    P.n = p->layout.n;
+    P.m = p->layout.m;
+    P.nnz = p->layout.nnz;
+    for (int j = 0; j < num_contacts; j++) P.perm[j] = p->layout.perm[j];
+    P.mu = 1.0;          // Environment.h:46
+    P.ground_z = 0.0;    // Ground.cpp:7
+    P.com_ref[2] = 1.0;  // MinimizeCentroidalVariables.cpp:11
+    P.W_com = 1.0;       // :13
+    for (int k = 0; k < num_contacts; k++) {
+        P.W_p[k] = 1.0;  // :24-25
+        P.W_F[k] = 1.0;
+    }
+    p->refresh_derived();
+    p->x_lb.assign(P.n, -1000.0);  // Variable3D.cpp:12-13
+    p->x_ub.assign(P.n, 1000.0);
+    *out = p;
+    return CPLB_OK;
+}
+
+void cplb_destroy(cplb_problem* p)
+{
+    if (!p) return;
+    if (p->device >= 0) {
+        DeviceGuard dg(p->device);
+        for (auto& ev : p->events) {
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
+        if (p->streams_ready) {
+            for (int s = 0; s < kHostStreams; s++) {
+                cudaStreamSynchronize(p->streams[s]);
+                cudaStreamDestroy(p->streams[s]);
+                if (p->stage[s]) cudaFree(p->stage[s]);
+            }
+        }
+    }
+    delete p;
+}
+
+// ---- layout ---------------------------------------------------------------------------------
+
+cplb_status cplb_get_dims(const cplb_problem* p, int32_t* n, int32_t* m, int32_t* nnz)
+{
+    CPLB_REQUIRE(p);
+    if (n) *n = p->layout.n;
+    if (m) *m = p->layout.m;
+    if (nnz) *nnz = p->layout.nnz;
+    return CPLB_OK;
+}
+
+cplb_status cplb_get_jacobian_structure(const cplb_problem* p, int32_t* iRow, int32_t* jCol)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(iRow);
+    CPLB_REQUIRE(jCol);
+    std::memcpy(iRow, p->layout.iRow.data(), sizeof(int32_t) * p->layout.nnz);
+    std::memcpy(jCol, p->layout.jCol.data(), sizeof(int32_t) * p->layout.nnz);
+    return CPLB_OK;
+}
+
+cplb_status cplb_get_sorted_order(const cplb_problem* p, int32_t* sorted_to_vector)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(sorted_to_vector);
+    for (int j = 0; j < p->layout.nc; j++) sorted_to_vector[j] = p->layout.perm[j];
+    return CPLB_OK;
+}
+
+static cplb_status block_column(const cplb_problem* p, cplb_block block, const char* name, int* col)
+{
+    if (block == CPLB_BLOCK_COM) {
+        *col = 0;
+        return CPLB_OK;
+    }
+    if (block != CPLB_BLOCK_FORCE && block != CPLB_BLOCK_POSITION && block != CPLB_BLOCK_NORMAL)
+        return fail(CPLB_INVALID_ARGUMENT, "unknown variable block %d", (int)block);
+    const int k = p->find(name);
+    if (k < 0) return fail(CPLB_OUT_OF_RANGE, "map::at: unknown contact '%s'", name ? name : "(null)");
+    *col = 3 + 9 * k + 3 * ((int)block - 1);
+    return CPLB_OK;
+}
+
+cplb_status cplb_get_block_column(const cplb_problem* p, cplb_block block, const char* contact_name, int32_t* col)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(col);
+    int c = 0;
+    cplb_status st = block_column(p, block, contact_name, &c);
+    if (st == CPLB_OK) *col = c;
+    return st;
+}
+
+cplb_status cplb_get_contact_row(const cplb_problem* p, const char* contact_name, int32_t* row)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(row);
+    const int k = p->find(contact_name);
+    if (k < 0) return fail(CPLB_OUT_OF_RANGE, "map::at: unknown contact '%s'", contact_name ? contact_name : "(null)");
+    *row = p->layout.contact_row(p->layout.rank[k]);
+    return CPLB_OK;
+}
+
+cplb_status cplb_get_variable_bounds(const cplb_problem* p, double* lower, double* upper)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(lower);
+    CPLB_REQUIRE(upper);
+    std::memcpy(lower, p->x_lb.data(), sizeof(double) * p->layout.n);
+    std::memcpy(upper, p->x_ub.data(), sizeof(double) * p->layout.n);
+    return CPLB_OK;
+}
+
+cplb_status cplb_get_constraint_bounds(const cplb_problem* p, double* lower, double* upper)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(lower);
+    CPLB_REQUIRE(upper);
+    const cplb::Layout& L = p->layout;
+    for (int r = 0; r < L.m; r++) {  // ifopt::Bounds(0,0) everywhere ...
+        lower[r] = 0.0;
+        upper[r] = 0.0;
+    }
+    for (int j = 0; j < L.nc; j++) {  // ... except the FrictionCone rows: ifopt::BoundSmallerZero = (-1e20, 0)
+        const int row = L.contact_row(j) + (L.has_env ? 4 : 0);
+        lower[row] = lower[row + 1] = -1.0e20;
+    }
+    return CPLB_OK;
+}
+
+// ---- parameters ---------------------------------------------------------------------------
+
+cplb_status cplb_set_mass(cplb_problem* p, double mass)
+{
+    CPLB_REQUIRE(p);
+    if (!(mass > 0.0)) return fail(CPLB_INVALID_ARGUMENT, "Invalid robot mass");
+    p->mass = mass;
+    p->refresh_derived();
+    return CPLB_OK;
+}
+cplb_status cplb_get_mass(const cplb_problem* p, double* mass)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(mass);
+    *mass = p->mass;
+    return CPLB_OK;
+}
+
+cplb_status cplb_set_manipulation_wrench(cplb_problem* p, const double wrench[6])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(wrench);
+    for (int i = 0; i < 6; i++) p->P.wrench[i] = wrench[i];
+    return CPLB_OK;
+}
+cplb_status cplb_get_manipulation_wrench(const cplb_problem* p, double wrench[6])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(wrench);
+    for (int i = 0; i < 6; i++) wrench[i] = p->P.wrench[i];
+    return CPLB_OK;
+}
+
+cplb_status cplb_set_mu(cplb_problem* p, double mu)
+{
+    CPLB_REQUIRE(p);
+    if (mu <= 0.0) return fail(CPLB_INVALID_ARGUMENT, "Invalid friction coefficient");  // Environment.h:21-22
+    p->P.mu = mu;
+    return CPLB_OK;
+}
+cplb_status cplb_get_mu(const cplb_problem* p, double* mu)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(mu);
+    *mu = p->P.mu;
+    return CPLB_OK;
+}
+
+cplb_status cplb_set_ground_z(cplb_problem* p, double ground_z)
+{
+    CPLB_REQUIRE(p);
+    if (p->env != CPLB_ENV_GROUND) return fail(CPLB_RUNTIME_ERROR, "the problem's environment is not a Ground");
+    p->P.ground_z = ground_z;
+    return CPLB_OK;
+}
+cplb_status cplb_get_ground_z(const cplb_problem* p, double* ground_z)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(ground_z);
+    if (p->env != CPLB_ENV_GROUND) return fail(CPLB_RUNTIME_ERROR, "the problem's environment is not a Ground");
+    *ground_z = p->P.ground_z;
+    return CPLB_OK;
+}
+
+cplb_status cplb_set_superquadric(cplb_problem* p, const double C[3], const double R[3], const double Pw[3])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(C);
+    CPLB_REQUIRE(R);
+    CPLB_REQUIRE(Pw);
+    if (p->env != CPLB_ENV_SUPERQUADRIC) return fail(CPLB_RUNTIME_ERROR, "the problem's environment is not a Superquadric");
+    if (R[0] <= 0.0 || R[1] <= 0.0 || R[2] <= 0.0)  // Superquadric.cpp:16-19
+        return fail(CPLB_INVALID_ARGUMENT, "Invalid superquadric axial radii");
+    if (Pw[0] < 2.0 || Pw[1] < 2.0 || Pw[2] < 2.0)  // :21-24
+        return fail(CPLB_INVALID_ARGUMENT, "Invalid superquadric axial curvatures: must be >= 2");
+    for (int q = 0; q < 3; q++) {
+        p->sqC[q] = C[q];
+        p->sqR[q] = R[q];
+        p->sqP[q] = Pw[q];
+    }
+    p->refresh_derived();
+    return CPLB_OK;
+}
+cplb_status cplb_get_superquadric(const cplb_problem* p, double C[3], double R[3], double Pw[3])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(C);
+    CPLB_REQUIRE(R);
+    CPLB_REQUIRE(Pw);
+    if (p->env != CPLB_ENV_SUPERQUADRIC) return fail(CPLB_RUNTIME_ERROR, "the problem's environment is not a Superquadric");
+    for (int q = 0; q < 3; q++) {
+        C[q] = p->sqC[q];
+        R[q] = p->sqR[q];
+        Pw[q] = p->sqP[q];
+    }
+    return CPLB_OK;
+}
+
+#define CPLB_CONTACT(k, p, name)                                                                        \
+    const int k = (p)->find(name);                                                                      \
+    if (k < 0) return fail(CPLB_OUT_OF_RANGE, "map::at: unknown contact '%s'", (name) ? (name) : "(null)")
+
+cplb_status cplb_set_force_threshold(cplb_problem* p, const char* contact_name, double F_thr)
+{
+    CPLB_REQUIRE(p);
+    CPLB_CONTACT(k, p, contact_name);
+    p->P.F_thr[k] = F_thr;
+    return CPLB_OK;
+}
+cplb_status cplb_get_force_threshold(const cplb_problem* p, const char* contact_name, double* F_thr)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(F_thr);
+    CPLB_CONTACT(k, p, contact_name);
+    *F_thr = p->P.F_thr[k];
+    return CPLB_OK;
+}
+
+cplb_status cplb_set_bounds(cplb_problem* p, cplb_block block, const char* contact_name, const double lower[3],
+                            const double upper[3])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(lower);
+    CPLB_REQUIRE(upper);
+    int col = 0;
+    cplb_status st = block_column(p, block, contact_name, &col);
+    if (st != CPLB_OK) return st;
+    bool bad = false;
+    for (int i = 0; i < 3; i++) {  // Variable3D::SetBounds stores first, then checks (Variable3D.cpp:31-38)
+        p->x_lb[col + i] = lower[i];
+        p->x_ub[col + i] = upper[i];
+        if (upper[i] - lower[i] < 0) bad = true;
+    }
+    if (bad) return fail(CPLB_INVALID_ARGUMENT, "Inconsistent bounds");
+    return CPLB_OK;
+}
+cplb_status cplb_get_bounds(const cplb_problem* p, cplb_block block, const char* contact_name, double lower[3], double upper[3])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(lower);
+    CPLB_REQUIRE(upper);
+    int col = 0;
+    cplb_status st = block_column(p, block, contact_name, &col);
+    if (st != CPLB_OK) return st;
+    for (int i = 0; i < 3; i++) {
+        lower[i] = p->x_lb[col + i];
+        upper[i] = p->x_ub[col + i];
+    }
+    return CPLB_OK;
+}
+
+cplb_status cplb_set_pos_ref(cplb_problem* p, const char* contact_name, const double ref[3])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(ref);
+    CPLB_CONTACT(k, p, contact_name);
+    for (int i = 0; i < 3; i++) p->P.p_ref[k][i] = ref[i];
+    return CPLB_OK;
+}
+cplb_status cplb_get_pos_ref(const cplb_problem* p, const char* contact_name, double ref[3])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(ref);
+    CPLB_CONTACT(k, p, contact_name);
+    for (int i = 0; i < 3; i++) ref[i] = p->P.p_ref[k][i];
+    return CPLB_OK;
+}
+cplb_status cplb_set_force_ref(cplb_problem* p, const char* contact_name, const double ref[3])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(ref);
+    CPLB_CONTACT(k, p, contact_name);
+    for (int i = 0; i < 3; i++) p->P.F_ref[k][i] = ref[i];
+    return CPLB_OK;
+}
+cplb_status cplb_get_force_ref(const cplb_problem* p, const char* contact_name, double ref[3])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(ref);
+    CPLB_CONTACT(k, p, contact_name);
+    for (int i = 0; i < 3; i++) ref[i] = p->P.F_ref[k][i];
+    return CPLB_OK;
+}
+cplb_status cplb_set_com_ref(cplb_problem* p, const double ref[3])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(ref);
+    for (int i = 0; i < 3; i++) p->P.com_ref[i] = ref[i];
+    return CPLB_OK;
+}
+cplb_status cplb_get_com_ref(const cplb_problem* p, double ref[3])
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(ref);
+    for (int i = 0; i < 3; i++) ref[i] = p->P.com_ref[i];
+    return CPLB_OK;
+}
+// Weight checks (< 0 -> std::invalid_argument "Invalid weight") are the planner facade's
+// (CentroidalPlanner.cpp:186-189, 203-206, 233-236, 256-259, 286-289); kept here so every binding gets them.
+cplb_status cplb_set_com_weight(cplb_problem* p, double W)
+{
+    CPLB_REQUIRE(p);
+    if (W < 0.0) return fail(CPLB_INVALID_ARGUMENT, "Invalid weight");
+    p->P.W_com = W;
+    return CPLB_OK;
+}
+cplb_status cplb_get_com_weight(const cplb_problem* p, double* W)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(W);
+    *W = p->P.W_com;
+    return CPLB_OK;
+}
+cplb_status cplb_set_pos_weight(cplb_problem* p, double W)
+{
+    CPLB_REQUIRE(p);
+    if (W < 0.0) return fail(CPLB_INVALID_ARGUMENT, "Invalid weight");
+    for (int k = 0; k < p->layout.nc; k++) p->P.W_p[k] = W;
+    return CPLB_OK;
+}
+cplb_status cplb_set_force_weight(cplb_problem* p, double W)
+{
+    CPLB_REQUIRE(p);
+    if (W < 0.0) return fail(CPLB_INVALID_ARGUMENT, "Invalid weight");
+    for (int k = 0; k < p->layout.nc; k++) p->P.W_F[k] = W;
+    return CPLB_OK;
+}
+cplb_status cplb_set_contact_pos_weight(cplb_problem* p, const char* contact_name, double W)
+{
+    CPLB_REQUIRE(p);
+    CPLB_CONTACT(k, p, contact_name);
+    if (W < 0.0) return fail(CPLB_INVALID_ARGUMENT, "Invalid weight");
+    p->P.W_p[k] = W;
+    return CPLB_OK;
+}
+cplb_status cplb_get_contact_pos_weight(const cplb_problem* p, const char* contact_name, double* W)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(W);
+    CPLB_CONTACT(k, p, contact_name);
+    *W = p->P.W_p[k];
+    return CPLB_OK;
+}
+cplb_status cplb_set_contact_force_weight(cplb_problem* p, const char* contact_name, double W)
+{
+    CPLB_REQUIRE(p);
+    CPLB_CONTACT(k, p, contact_name);
+    if (W < 0.0) return fail(CPLB_INVALID_ARGUMENT, "Invalid weight");
+    p->P.W_F[k] = W;
+    return CPLB_OK;
+}
+cplb_status cplb_get_contact_force_weight(const cplb_problem* p, const char* contact_name, double* W)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(W);
+    CPLB_CONTACT(k, p, contact_name);
+    *W = p->P.W_F[k];
+    return CPLB_OK;
+}
+
+// ---- evaluation -----------------------------------------------------------------------------
+
+// Binds a problem created with device = -1 to the calling thread's current device.  This is where a
+// machine without a GPU fails: loudly, with CPLB_CUDA_ERROR -- there is no CPU evaluation path.
+static cplb_status bind_device(cplb_problem* p)
+{
+    if (p->device >= 0) return CPLB_OK;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CPLB_CUDA_ERROR, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    int dev = 0;
+    CPLB_CUDA(cudaGetDevice(&dev));
+    p->device = dev;
+    return CPLB_OK;
+}
+
+static cplb_status check_args(const cplb_problem* p, const cplb_eval_args* a, unsigned* flags, long long* ld)
+{
+    if (a->num_instances < 0) return fail(CPLB_INVALID_ARGUMENT, "num_instances is negative");
+    if (a->layout != CPLB_INSTANCE_MAJOR && a->layout != CPLB_COMPONENT_MAJOR)
+        return fail(CPLB_INVALID_ARGUMENT, "unknown layout %d", a->layout);
+    if (a->num_instances > 0 && a->x == nullptr) return fail(CPLB_NULL_POINTER, "x is NULL");
+    unsigned f = 0;
+    if (a->g) f |= CPLB_WANT_G;
+    if (a->jac) f |= CPLB_WANT_J;
+    if (a->cost) f |= CPLB_WANT_COST;
+    if (a->grad) f |= CPLB_WANT_GRAD;
+    *flags = f;
+    long long pitch = a->ld == 0 ? a->num_instances : a->ld;
+    if (a->layout == CPLB_COMPONENT_MAJOR && pitch < a->num_instances)
+        return fail(CPLB_INVALID_ARGUMENT, "ld (%lld) is smaller than num_instances (%lld)", pitch, (long long)a->num_instances);
+    *ld = pitch;
+    (void)p;
+    return CPLB_OK;
+}
+
+static cplb_status launch(cplb_problem* p, const CplbIo& io, int layout, unsigned flags, cudaStream_t st)
+{
+    cudaError_t e = layout == CPLB_COMPONENT_MAJOR ? cplb::launch_component_major(p->P, io, flags, st)
+                                                   : cplb::launch_instance_major(p->P, io, flags, st);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    p->launches.fetch_add(1, std::memory_order_relaxed);
+    return CPLB_OK;
+}
+
+cplb_status cplb_eval_device(cplb_problem* p, const cplb_eval_args* args, void* cuda_stream)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(args);
+    unsigned flags = 0;
+    long long ld = 0;
+    cplb_status st = check_args(p, args, &flags, &ld);
+    if (st != CPLB_OK) return st;
+    if (args->num_instances == 0 || flags == 0) return CPLB_OK;
+    st = bind_device(p);
+    if (st != CPLB_OK) return st;
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(CPLB_CUDA_ERROR, "cudaSetDevice(%d) failed", p->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    CplbIo io{args->x, args->g, args->jac, args->cost, args->grad, ld, args->num_instances};
+
+    bool timed = false;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(p->timing_mu);
+        timed = p->timing;
+    }
+    if (timed) {
+        CPLB_CUDA(cudaEventCreate(&e0));
+        CPLB_CUDA(cudaEventCreate(&e1));
+        CPLB_CUDA(cudaEventRecord(e0, stream));
+    }
+    st = launch(p, io, args->layout, flags, stream);
+    if (timed) {
+        cudaEventRecord(e1, stream);
+        std::lock_guard<std::mutex> lk(p->timing_mu);
+        p->events.emplace_back(e0, e1);
+    }
+    return st;
+}
+
+static cplb_status ensure_host_pipeline(cplb_problem* p, size_t bytes_per_stream)
+{
+    if (!p->streams_ready) {
+        for (int s = 0; s < kHostStreams; s++) CPLB_CUDA(cudaStreamCreateWithFlags(&p->streams[s], cudaStreamNonBlocking));
+        p->streams_ready = true;
+    }
+    if (bytes_per_stream > p->stage_bytes) {
+        for (int s = 0; s < kHostStreams; s++) {
+            if (p->stage[s]) {
+                CPLB_CUDA(cudaStreamSynchronize(p->streams[s]));
+                CPLB_CUDA(cudaFree(p->stage[s]));
+                p->stage[s] = nullptr;
+            }
+        }
+        p->stage_bytes = 0;
+        for (int s = 0; s < kHostStreams; s++) CPLB_CUDA(cudaMalloc(&p->stage[s], bytes_per_stream));
+        p->stage_bytes = bytes_per_stream;
+    }
+    return CPLB_OK;
+}
+
+cplb_status cplb_eval_host(cplb_problem* p, const cplb_eval_args* args)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(args);
+    unsigned flags = 0;
+    long long ld = 0;
+    cplb_status st = check_args(p, args, &flags, &ld);
+    if (st != CPLB_OK) return st;
+    const long long N = args->num_instances;
+    if (N == 0 || flags == 0) return CPLB_OK;
+    st = bind_device(p);
+    if (st != CPLB_OK) return st;
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(CPLB_CUDA_ERROR, "cudaSetDevice(%d) failed", p->device);
+    std::lock_guard<std::mutex> lk(p->host_mu);
+
+    const int n = p->layout.n, m = p->layout.m, nnz = p->layout.nnz;
+    // chunk: big enough for efficient PCIe bursts (several MB per copy), small enough that three
+    // chunks in flight overlap H2D, kernel and D2H
+    long long chunk = 16384;
+    if (chunk > N) chunk = N;
+    chunk = (chunk + 31) & ~31LL;  // keeps every chunk's slices 16-byte aligned and tile-aligned
+    size_t per_inst = (size_t)n;
+    if (flags & CPLB_WANT_G) per_inst += m;
+    if (flags & CPLB_WANT_J) per_inst += nnz;
+    if (flags & CPLB_WANT_COST) per_inst += 1;
+    if (flags & CPLB_WANT_GRAD) per_inst += n;
+    st = ensure_host_pipeline(p, per_inst * (size_t)chunk * sizeof(double));
+    if (st != CPLB_OK) return st;
+
+    const bool cm = args->layout == CPLB_COMPONENT_MAJOR;
+    int s = 0;
+    for (long long i0 = 0; i0 < N; i0 += chunk, s = (s + 1) % kHostStreams) {
+        const long long cnt = (N - i0) < chunk ? (N - i0) : chunk;
+        cudaStream_t stream = p->streams[s];
+        double* d = p->stage[s];
+        double* dx = d;
+        d += (size_t)n * chunk;
+        double *dg_ = nullptr, *dj = nullptr, *dc = nullptr, *dgr = nullptr;
+        if (flags & CPLB_WANT_G) { dg_ = d; d += (size_t)m * chunk; }
+        if (flags & CPLB_WANT_J) { dj = d; d += (size_t)nnz * chunk; }
+        if (flags & CPLB_WANT_GRAD) { dgr = d; d += (size_t)n * chunk; }
+        if (flags & CPLB_WANT_COST) { dc = d; }
+        // device-side chunk buffers use pitch `chunk` (component-major) or are dense (instance-major)
+        if (cm) {
+            CPLB_CUDA(cudaMemcpy2DAsync(dx, chunk * sizeof(double), args->x + i0, ld * sizeof(double), cnt * sizeof(double), n,
+                                        cudaMemcpyHostToDevice, stream));
+        } else {
+            CPLB_CUDA(cudaMemcpyAsync(dx, args->x + i0 * n, (size_t)cnt * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        }
+        CplbIo io{dx, dg_, dj, dc, dgr, chunk, cnt};
+        st = launch(p, io, args->layout, flags, stream);
+        if (st != CPLB_OK) return st;
+        if (cm) {
+            if (dg_) CPLB_CUDA(cudaMemcpy2DAsync(args->g + i0, ld * sizeof(double), dg_, chunk * sizeof(double), cnt * sizeof(double), m, cudaMemcpyDeviceToHost, stream));
+            if (dj) CPLB_CUDA(cudaMemcpy2DAsync(args->jac + i0, ld * sizeof(double), dj, chunk * sizeof(double), cnt * sizeof(double), nnz, cudaMemcpyDeviceToHost, stream));
+            if (dgr) CPLB_CUDA(cudaMemcpy2DAsync(args->grad + i0, ld * sizeof(double), dgr, chunk * sizeof(double), cnt * sizeof(double), n, cudaMemcpyDeviceToHost, stream));
+        } else {
+            if (dg_) CPLB_CUDA(cudaMemcpyAsync(args->g + i0 * m, dg_, (size_t)cnt * m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            if (dj) CPLB_CUDA(cudaMemcpyAsync(args->jac + i0 * nnz, dj, (size_t)cnt * nnz * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            if (dgr) CPLB_CUDA(cudaMemcpyAsync(args->grad + i0 * n, dgr, (size_t)cnt * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        }
+        if (dc) CPLB_CUDA(cudaMemcpyAsync(args->cost + i0, dc, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    for (int t = 0; t < kHostStreams; t++) CPLB_CUDA(cudaStreamSynchronize(p->streams[t]));
+    return CPLB_OK;
+}
+
+cplb_status cplb_host_alloc(size_t bytes, void** out)
+{
+    CPLB_REQUIRE(out);
+    *out = nullptr;
+    CPLB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return CPLB_OK;
+}
+cplb_status cplb_host_free(void* ptr)
+{
+    if (ptr) CPLB_CUDA(cudaFreeHost(ptr));
+    return CPLB_OK;
+}
+
+cplb_status cplb_get_launch_count(const cplb_problem* p, int64_t* launches)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(launches);
+    *launches = p->launches.load(std::memory_order_relaxed);
+    return CPLB_OK;
+}
+
+cplb_status cplb_timing_begin(cplb_problem* p)
+{
+    CPLB_REQUIRE(p);
+    std::lock_guard<std::mutex> lk(p->timing_mu);
+    for (auto& ev : p->events) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    p->events.clear();
+    p->timing = true;
+    return CPLB_OK;
+}
+
+cplb_status cplb_timing_end(cplb_problem* p, double* avg_kernel_ms, int64_t* kernels)
+{
+    CPLB_REQUIRE(p);
+    DeviceGuard dg(p->device >= 0 ? p->device : 0);
+    std::lock_guard<std::mutex> lk(p->timing_mu);
+    p->timing = false;
+    double total = 0.0;
+    long long cnt = 0;
+    for (auto& ev : p->events) {
+        CPLB_CUDA(cudaEventSynchronize(ev.second));
+        float ms = 0.f;
+        CPLB_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        total += ms;
+        cnt++;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    p->events.clear();
+    if (avg_kernel_ms) *avg_kernel_ms = cnt ? total / (double)cnt : 0.0;
+    if (kernels) *kernels = cnt;
+    return CPLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,17 @@
+// cplb_kernels.h -- launchers of the evaluation kernels (cplb_kernels.cu).
+#ifndef CPLB_KERNELS_H
+#define CPLB_KERNELS_H
+
+#include <cuda_runtime.h>
+
+#include "cplb_params.h"
+
+namespace cplb {
+
+// buf[e*ld + i]: one thread per instance, fully coalesced.
+cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st);
+// buf[i*len + e]: warp tiles staged through shared memory with bulk async (TMA) copies.
+cudaError_t launch_instance_major(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st);
+
+}  // namespace cplb
+#endif

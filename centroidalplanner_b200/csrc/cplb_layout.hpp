@@ -1,0 +1,86 @@
+// cplb_layout.hpp -- host-side layout generator: the row/column/triplet contract that
+// cpl::solver::CplProblem::CplProblem fixes (src/CplProblem.cpp:6-82) and ifopt turns into the
+// (iRow, jCol) list IPOPT sees.  Closed-form in (names, env); runs once per problem.
+#ifndef CPLB_LAYOUT_HPP
+#define CPLB_LAYOUT_HPP
+
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace cplb {
+
+struct Layout {
+    int nc = 0;
+    bool has_env = false;
+    int n = 0, m = 0, nnz = 0;
+    std::vector<int32_t> perm;      // sorted-name rank -> index in the caller's vector
+    std::vector<int32_t> rank;      // index in the caller's vector -> sorted-name rank
+    std::vector<int32_t> iRow, jCol;
+
+    static int col_com() { return 0; }
+    static int col_F(int k) { return 3 + 9 * k; }  // AddVariableSet order: F_, p_, n_ per name (CplProblem.cpp:31-33)
+    static int col_p(int k) { return 3 + 9 * k + 3; }
+    static int col_n(int k) { return 3 + 9 * k + 6; }
+    int rows_per_contact() const { return has_env ? 6 : 2; }
+    int contact_row(int sorted_rank) const { return 6 + rows_per_contact() * sorted_rank; }
+
+    void build(const std::vector<std::string>& names, bool env_present)
+    {
+        nc = (int)names.size();
+        has_env = env_present;
+        n = 3 + 9 * nc;
+        m = 6 + rows_per_contact() * nc;
+        perm.resize(nc);
+        std::iota(perm.begin(), perm.end(), 0);
+        // iteration order of std::map<std::string, ContactVars> (CplProblem.cpp:29,42)
+        std::sort(perm.begin(), perm.end(), [&](int a, int b) { return names[a] < names[b]; });
+        rank.assign(nc, 0);
+        for (int j = 0; j < nc; j++) rank[perm[j]] = j;
+
+        iRow.clear();
+        jCol.clear();
+        auto put = [&](int r, int c) {
+            iRow.push_back(r);
+            jCol.push_back(c);
+        };
+        // CentroidalStatics rows 0..2: identity on every F block (CentroidalStatics.cpp:93-95)
+        for (int r = 0; r < 3; r++)
+            for (int k = 0; k < nc; k++) put(r, col_F(k) + r);
+        // rows 3..5: the two columns != q of CoM, F_k, p_k (:96-101, :108-113, :128-133)
+        for (int q = 0; q < 3; q++) {
+            const int c0 = (q == 0) ? 1 : 0, c1 = (q == 2) ? 1 : 2;
+            put(3 + q, col_com() + c0);
+            put(3 + q, col_com() + c1);
+            for (int k = 0; k < nc; k++) {
+                put(3 + q, col_F(k) + c0);
+                put(3 + q, col_F(k) + c1);
+                put(3 + q, col_p(k) + c0);
+                put(3 + q, col_p(k) + c1);
+            }
+        }
+        for (int j = 0; j < nc; j++) {
+            const int k = perm[j];
+            int row = contact_row(j);
+            if (has_env) {
+                for (int c = 0; c < 3; c++) put(row, col_p(k) + c);  // EnvironmentConstraint.cpp:56-58
+                row++;
+                for (int i = 0; i < 3; i++) {                        // EnvironmentNormal.cpp:66-68, :75-83
+                    for (int c = 0; c < 3; c++) put(row + i, col_p(k) + c);
+                    put(row + i, col_n(k) + i);
+                }
+                row += 3;
+            }
+            for (int i = 0; i < 2; i++) {                            // FrictionCone.cpp:82-87, :93-99
+                for (int c = 0; c < 3; c++) put(row + i, col_F(k) + c);
+                for (int c = 0; c < 3; c++) put(row + i, col_n(k) + c);
+            }
+        }
+        nnz = (int)iRow.size();
+    }
+};
+
+}  // namespace cplb
+#endif

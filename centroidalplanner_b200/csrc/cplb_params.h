@@ -1,0 +1,58 @@
+// cplb_params.h -- the read-only parameter block handed BY VALUE to every kernel launch
+// (__grid_constant__, lives in the constant bank: one broadcast read per warp, no HBM traffic,
+// no staleness between a setter and the next launch on any stream).
+//
+// It holds what the reference keeps scattered over its IFOPT objects: CentroidalStatics::_m/_g/
+// _wrench_manip (CentroidalStatics.cpp:12-15), FrictionCone::_F_thr (FrictionCone.cpp:14),
+// EnvironmentClass::_mu (Environment.h:46), Ground::_ground_z, Superquadric::_C/_R/_P, and the
+// refs/weights of MinimizeCentroidalVariables (MinimizeCentroidalVariables.cpp:11-26).
+#ifndef CPLB_PARAMS_H
+#define CPLB_PARAMS_H
+
+#include <stdint.h>
+
+#define CPLB_KMAX_CONTACTS 32
+
+#define CPLB_WANT_G 1u
+#define CPLB_WANT_J 2u
+#define CPLB_WANT_COST 4u
+#define CPLB_WANT_GRAD 8u
+
+struct CplbParams {
+    int32_t nc;
+    int32_t env;
+    int32_t n, m, nnz;
+    int32_t pad0;
+    int32_t perm[CPLB_KMAX_CONTACTS];  // sorted-name rank -> index in the caller's vector
+    double mg[3];                       // _m * _g, one IEEE multiply per component, done on the host
+    double wrench[6];
+    double mu;
+    double ground_z;
+    // Superquadric: raw parameters plus the constant-argument pow() results the reference
+    // recomputes on every call (host glibc pow on the same arguments gives the same bits).
+    double sqC[3], sqR[3], sqP[3];
+    double sqPoverRP[3];  // P / pow(R, P)          Superquadric.cpp:54-56
+    double sqRmP[3];      // pow(R, -P)             :98,109,...
+    double sqRm2P[3];     // pow(R, -(P*2.0))       :82,86,107,...
+    double sqR2P[3];      // pow(R,  P*2.0)         :95,96,149,150,203,204
+    double F_thr[CPLB_KMAX_CONTACTS];
+    double com_ref[3];
+    double W_com;
+    double p_ref[CPLB_KMAX_CONTACTS][3];
+    double F_ref[CPLB_KMAX_CONTACTS][3];
+    double W_p[CPLB_KMAX_CONTACTS];
+    double W_F[CPLB_KMAX_CONTACTS];
+};
+
+// Pointers of one evaluation (device memory), see cplb_eval_args in include/cpl_batched.h.
+struct CplbIo {
+    const double* x;
+    double* g;
+    double* jac;
+    double* cost;
+    double* grad;
+    long long ld;  // COMPONENT_MAJOR row pitch (elements)
+    long long N;
+};
+
+#endif

@@ -1,0 +1,415 @@
+"""Host-side mirror of the reference's problem interface over the C ABI.
+
+`BatchedCplProblem` plays the role of `cpl::solver::CplProblem` (include/CentroidalPlanner/Ifopt/
+CplProblem.h:19-115, src/CplProblem.cpp) for N instances at once: same constructor arguments,
+same setter/getter names, same error behaviour (std::invalid_argument -> ValueError,
+std::out_of_range -> IndexError, std::runtime_error -> RuntimeError, i.e. pybind11's mapping),
+and the four `ifopt::Problem` evaluation entry points IPOPT drives, batched.  `Ground` and
+`Superquadric` mirror cpl::env (Environment.h:13-48, Ground.h, Superquadric.h).
+
+Everything numeric happens in libcplb.so on the GPU; torch is used only to own device memory and
+streams.  NumPy / CPU-tensor inputs go through `cplb_eval_host` (host buffers, copies inside).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _cabi
+
+_EXC = {
+    _cabi.INVALID_ARGUMENT: ValueError,
+    _cabi.OUT_OF_RANGE: IndexError,
+    _cabi.RUNTIME_ERROR: RuntimeError,
+    _cabi.CUDA_ERROR: RuntimeError,
+    _cabi.NULL_POINTER: ValueError,
+}
+
+
+def _check(status):
+    if status != _cabi.OK:
+        msg = _cabi.load().cplb_last_error().decode(errors="replace")
+        raise _EXC.get(status, RuntimeError)(msg)
+
+
+def _v3(v, n=3):
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(n))
+    return a, a.ctypes.data_as(_cabi.dp)
+
+
+class EnvironmentClass:
+    """cpl::env::EnvironmentClass (Environment.h:13-48): friction coefficient, default 1.0."""
+
+    _kind = _cabi.ENV_NONE
+
+    def __init__(self):
+        self._mu = 1.0
+        self._problems = weakref.WeakSet()
+
+    def SetMu(self, mu):
+        if mu <= 0.0:
+            raise ValueError("Invalid friction coefficient")
+        self._mu = float(mu)
+        self._push()
+
+    def GetMu(self):
+        return self._mu
+
+    def _attach(self, problem):
+        self._problems.add(problem)
+        self._push_to(problem)
+
+    def _push(self):
+        for p in list(self._problems):
+            self._push_to(p)
+
+    def _push_to(self, problem):
+        _check(problem._lib.cplb_set_mu(problem._h, self._mu))
+
+
+class Ground(EnvironmentClass):
+    """cpl::env::Ground (Ground.h:13-40, src/Ground.cpp): the plane z = ground_z."""
+
+    _kind = _cabi.ENV_GROUND
+
+    def __init__(self):
+        super().__init__()
+        self._ground_z = 0.0
+
+    def SetGroundZ(self, ground_z):
+        self._ground_z = float(ground_z)
+        self._push()
+
+    def GetGroundZ(self):
+        return self._ground_z
+
+    def _push_to(self, problem):
+        super()._push_to(problem)
+        if problem._env_kind == _cabi.ENV_GROUND:
+            _check(problem._lib.cplb_set_ground_z(problem._h, self._ground_z))
+
+
+class Superquadric(EnvironmentClass):
+    """cpl::env::Superquadric (Superquadric.h:13-49, src/Superquadric.cpp:5-37)."""
+
+    _kind = _cabi.ENV_SUPERQUADRIC
+
+    def __init__(self):
+        super().__init__()
+        self._C = np.array([0.0, 0.0, 10.0])
+        self._R = np.array([10.0, 10.0, 10.0])
+        self._P = np.array([10.0, 10.0, 10.0])
+
+    def SetParameters(self, Cc, R, P):
+        Cc, R, P = (np.asarray(v, dtype=np.float64).reshape(3) for v in (Cc, R, P))
+        if (R <= 0.0).any():
+            raise ValueError("Invalid superquadric axial radii")
+        if (P < 2.0).any():
+            raise ValueError("Invalid superquadric axial curvatures: must be >= 2")
+        self._C, self._R, self._P = Cc.copy(), R.copy(), P.copy()
+        self._push()
+
+    def GetParameters(self):
+        return self._C.copy(), self._R.copy(), self._P.copy()
+
+    def _push_to(self, problem):
+        super()._push_to(problem)
+        _, c = _v3(self._C)
+        _, r = _v3(self._R)
+        _, p = _v3(self._P)
+        _check(problem._lib.cplb_set_superquadric(problem._h, c, r, p))
+
+
+def _is_torch(t):
+    return type(t).__module__.startswith("torch")
+
+
+class BatchedCplProblem:
+    """N instances of one CplProblem shape, evaluated on one B200.
+
+    contact_names / robot_mass / env as in CplProblem::CplProblem (src/CplProblem.cpp:6-11);
+    env=None selects the CoMPlanner variant (FrictionCone only, src/CplProblem.cpp:63-71).
+    """
+
+    def __init__(self, contact_names, robot_mass, env=None, device=None):
+        self._lib = _cabi.load()
+        self._names = [str(s) for s in contact_names]
+        self._env = env
+        self._env_kind = _cabi.ENV_NONE if env is None else env._kind
+        self._ground_fake = Ground() if env is None else None  # CplProblem.cpp:14
+        arr = (C.c_char_p * len(self._names))(*[s.encode() for s in self._names])
+        h = C.c_void_p()
+        dev = -1 if device is None else int(device)
+        _check(self._lib.cplb_create(len(self._names), arr, self._env_kind, float(robot_mass), dev, C.byref(h)))
+        self._h = h
+        n, m, nnz = C.c_int32(), C.c_int32(), C.c_int32()
+        _check(self._lib.cplb_get_dims(self._h, C.byref(n), C.byref(m), C.byref(nnz)))
+        self.n, self.m, self.nnz = n.value, m.value, nnz.value
+        (env if env is not None else self._ground_fake)._attach(self)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.cplb_destroy(h)
+            self._h = None
+
+    # ---- layout ------------------------------------------------------------------------------
+    @property
+    def contact_names(self):
+        return list(self._names)
+
+    def GetNumberOfOptimizationVariables(self):
+        return self.n
+
+    def GetNumberOfConstraints(self):
+        return self.m
+
+    def GetJacobianStructure(self):
+        """(iRow, jCol) exactly as IpoptAdapter::eval_jac_g(values=NULL) would fill them."""
+        r = np.zeros(self.nnz, dtype=np.int32)
+        c = np.zeros(self.nnz, dtype=np.int32)
+        _check(self._lib.cplb_get_jacobian_structure(self._h, r.ctypes.data_as(_cabi.ip), c.ctypes.data_as(_cabi.ip)))
+        return r, c
+
+    def GetSortedOrder(self):
+        p = np.zeros(len(self._names), dtype=np.int32)
+        _check(self._lib.cplb_get_sorted_order(self._h, p.ctypes.data_as(_cabi.ip)))
+        return p
+
+    def GetBlockColumn(self, block, contact_name=None):
+        col = C.c_int32()
+        name = None if contact_name is None else str(contact_name).encode()
+        _check(self._lib.cplb_get_block_column(self._h, int(block), name, C.byref(col)))
+        return col.value
+
+    def GetContactRow(self, contact_name):
+        row = C.c_int32()
+        _check(self._lib.cplb_get_contact_row(self._h, str(contact_name).encode(), C.byref(row)))
+        return row.value
+
+    def GetBoundsOnOptimizationVariables(self):
+        lb, ub = np.zeros(self.n), np.zeros(self.n)
+        _check(self._lib.cplb_get_variable_bounds(self._h, lb.ctypes.data_as(_cabi.dp), ub.ctypes.data_as(_cabi.dp)))
+        return lb, ub
+
+    def GetBoundsOnConstraints(self):
+        lb, ub = np.zeros(self.m), np.zeros(self.m)
+        _check(self._lib.cplb_get_constraint_bounds(self._h, lb.ctypes.data_as(_cabi.dp), ub.ctypes.data_as(_cabi.dp)))
+        return lb, ub
+
+    # ---- CplProblem forwarders (src/CplProblem.cpp:109-316) ----------------------------------
+    def _set_bounds(self, block, name, lb, ub):
+        _, l = _v3(lb)
+        _, u = _v3(ub)
+        _check(self._lib.cplb_set_bounds(self._h, block, None if name is None else str(name).encode(), l, u))
+
+    def _get_bounds(self, block, name):
+        lb, ub = np.zeros(3), np.zeros(3)
+        _check(self._lib.cplb_get_bounds(self._h, block, None if name is None else str(name).encode(),
+                                         lb.ctypes.data_as(_cabi.dp), ub.ctypes.data_as(_cabi.dp)))
+        return lb, ub
+
+    def SetForceBounds(self, contact_name, force_lb, force_ub):
+        self._set_bounds(_cabi.BLOCK_FORCE, contact_name, force_lb, force_ub)
+
+    def GetForceBounds(self, contact_name):
+        return self._get_bounds(_cabi.BLOCK_FORCE, contact_name)
+
+    def SetPosBounds(self, contact_name, pos_lb, pos_ub):
+        self._set_bounds(_cabi.BLOCK_POSITION, contact_name, pos_lb, pos_ub)
+
+    def GetPosBounds(self, contact_name):
+        return self._get_bounds(_cabi.BLOCK_POSITION, contact_name)
+
+    def SetNormalBounds(self, contact_name, normal_lb, normal_ub):
+        self._set_bounds(_cabi.BLOCK_NORMAL, contact_name, normal_lb, normal_ub)
+
+    def GetNormalBounds(self, contact_name):
+        return self._get_bounds(_cabi.BLOCK_NORMAL, contact_name)
+
+    def _set3(self, fn, name, v):
+        _, p = _v3(v)
+        _check(fn(self._h, str(name).encode(), p))
+
+    def _get3(self, fn, name):
+        out = np.zeros(3)
+        _check(fn(self._h, str(name).encode(), out.ctypes.data_as(_cabi.dp)))
+        return out
+
+    def _get1(self, fn, *args):
+        out = C.c_double()
+        _check(fn(self._h, *args, C.byref(out)))
+        return out.value
+
+    def SetPosRef(self, contact_name, pos_ref):
+        self._set3(self._lib.cplb_set_pos_ref, contact_name, pos_ref)
+
+    def GetPosRef(self, contact_name):
+        return self._get3(self._lib.cplb_get_pos_ref, contact_name)
+
+    def SetForceRef(self, contact_name, force_ref):
+        self._set3(self._lib.cplb_set_force_ref, contact_name, force_ref)
+
+    def GetForceRef(self, contact_name):
+        return self._get3(self._lib.cplb_get_force_ref, contact_name)
+
+    def SetCoMRef(self, com_ref):
+        _, p = _v3(com_ref)
+        _check(self._lib.cplb_set_com_ref(self._h, p))
+
+    def GetCoMRef(self):
+        out = np.zeros(3)
+        _check(self._lib.cplb_get_com_ref(self._h, out.ctypes.data_as(_cabi.dp)))
+        return out
+
+    def SetCoMWeight(self, W_CoM):
+        _check(self._lib.cplb_set_com_weight(self._h, float(W_CoM)))
+
+    def GetCoMWeight(self):
+        return self._get1(self._lib.cplb_get_com_weight)
+
+    def SetPosWeight(self, W_p):
+        _check(self._lib.cplb_set_pos_weight(self._h, float(W_p)))
+
+    def SetContactPosWeight(self, contact_name, W_p):
+        _check(self._lib.cplb_set_contact_pos_weight(self._h, str(contact_name).encode(), float(W_p)))
+
+    def GetContactPosWeight(self, contact_name):
+        return self._get1(self._lib.cplb_get_contact_pos_weight, str(contact_name).encode())
+
+    def SetForceWeight(self, W_F):
+        _check(self._lib.cplb_set_force_weight(self._h, float(W_F)))
+
+    def SetContactForceWeight(self, contact_name, W_F):
+        _check(self._lib.cplb_set_contact_force_weight(self._h, str(contact_name).encode(), float(W_F)))
+
+    def GetContactForceWeight(self, contact_name):
+        return self._get1(self._lib.cplb_get_contact_force_weight, str(contact_name).encode())
+
+    def SetManipulationWrench(self, wrench_manip):
+        _, p = _v3(wrench_manip, 6)
+        _check(self._lib.cplb_set_manipulation_wrench(self._h, p))
+
+    def GetManipulationWrench(self):
+        out = np.zeros(6)
+        _check(self._lib.cplb_get_manipulation_wrench(self._h, out.ctypes.data_as(_cabi.dp)))
+        return out
+
+    def SetMu(self, mu):
+        # CplProblem::SetMu (src/CplProblem.cpp:275-287): forwards to the env, or to _ground_fake
+        (self._env if self._env is not None else self._ground_fake).SetMu(mu)
+
+    def GetMu(self):
+        return (self._env if self._env is not None else self._ground_fake).GetMu()
+
+    def SetForceThreshold(self, contact_name, F_thr):
+        _check(self._lib.cplb_set_force_threshold(self._h, str(contact_name).encode(), float(F_thr)))
+
+    def GetForceThreshold(self, contact_name):
+        return self._get1(self._lib.cplb_get_force_threshold, str(contact_name).encode())
+
+    def SetMass(self, mass):
+        _check(self._lib.cplb_set_mass(self._h, float(mass)))
+
+    # ---- evaluation --------------------------------------------------------------------------
+    def _shape(self, length, N, layout):
+        return (N, length) if layout == _cabi.INSTANCE_MAJOR else (length, N)
+
+    def eval(self, x, g=True, jac=True, cost=False, grad=False, layout=_cabi.INSTANCE_MAJOR, out=None, stream=None):
+        """One batched evaluation.  x: (N, n) [instance-major] or (n, N) [component-major], fp64,
+        a torch CUDA tensor (device path, asynchronous on the current stream) or a NumPy array /
+        CPU tensor (host path through cplb_eval_host).  Returns a dict of outputs of the same kind."""
+        out = dict(out or {})
+        if _is_torch(x) and x.is_cuda:
+            return self._eval_device(x, g, jac, cost, grad, layout, out, stream)
+        return self._eval_host(x, g, jac, cost, grad, layout, out)
+
+    def _eval_device(self, x, g, jac, cost, grad, layout, out, stream):
+        import torch
+
+        assert x.dtype == torch.float64 and x.is_contiguous() and x.dim() == 2
+        N = x.shape[0] if layout == _cabi.INSTANCE_MAJOR else x.shape[1]
+        assert tuple(x.shape) == self._shape(self.n, N, layout), (tuple(x.shape), self.n)
+
+        def buf(key, want, length):
+            if not want:
+                return None
+            t = out.get(key)
+            if t is None:
+                shape = (N,) if length is None else self._shape(length, N, layout)
+                t = torch.empty(shape, dtype=torch.float64, device=x.device)
+            assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+            return t
+
+        res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self.nnz), "cost": buf("cost", cost, None),
+               "grad": buf("grad", grad, self.n)}
+        args = _cabi.EvalArgs(N, layout, 0, N, x.data_ptr(), *[None if res[k] is None else res[k].data_ptr()
+                                                              for k in ("g", "jac", "cost", "grad")])
+        s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
+        _check(self._lib.cplb_eval_device(self._h, C.byref(args), C.c_void_p(s)))
+        return res
+
+    def _eval_host(self, x, g, jac, cost, grad, layout, out):
+        is_t = _is_torch(x)
+        xa = x.numpy() if is_t else np.asarray(x, dtype=np.float64)
+        xa = np.ascontiguousarray(xa)
+        N = xa.shape[0] if layout == _cabi.INSTANCE_MAJOR else xa.shape[1]
+        assert xa.shape == self._shape(self.n, N, layout), (xa.shape, self.n)
+
+        def buf(key, want, length):
+            if not want:
+                return None
+            t = out.get(key)
+            if t is None:
+                return np.empty((N,) if length is None else self._shape(length, N, layout))
+            t = t.numpy() if _is_torch(t) else t
+            assert t.dtype == np.float64 and t.flags.c_contiguous
+            return t
+
+        res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self.nnz), "cost": buf("cost", cost, None),
+               "grad": buf("grad", grad, self.n)}
+        args = _cabi.EvalArgs(N, layout, 0, N, xa.ctypes.data, *[None if res[k] is None else res[k].ctypes.data
+                                                                for k in ("g", "jac", "cost", "grad")])
+        _check(self._lib.cplb_eval_host(self._h, C.byref(args)))
+        return res
+
+    # the four ifopt::Problem entry points IpoptAdapter calls, batched
+    def EvaluateConstraints(self, x, **kw):
+        return self.eval(x, g=True, jac=False, **kw)["g"]
+
+    def EvalNonzerosOfJacobian(self, x, **kw):
+        return self.eval(x, g=False, jac=True, **kw)["jac"]
+
+    def EvaluateCostFunction(self, x, **kw):
+        return self.eval(x, g=False, jac=False, cost=True, **kw)["cost"]
+
+    def EvaluateCostFunctionGradient(self, x, **kw):
+        return self.eval(x, g=False, jac=False, grad=True, **kw)["grad"]
+
+    def GetSolution(self, x_i):
+        """CplProblem::GetSolution (src/CplProblem.cpp:85-106) for one instance's x[n]:
+        {'com_sol': (3,), 'contact_values_map': {name: {'force_value','position_value','normal_value'}}}
+        with the map in sorted-name order like std::map."""
+        x_i = np.asarray(x_i, dtype=np.float64).reshape(self.n)
+        cv = {}
+        for k in self.GetSortedOrder():
+            b = 3 + 9 * int(k)
+            cv[self._names[k]] = {"force_value": x_i[b:b + 3].copy(), "position_value": x_i[b + 3:b + 6].copy(),
+                                  "normal_value": x_i[b + 6:b + 9].copy()}
+        return {"com_sol": x_i[0:3].copy(), "contact_values_map": cv}
+
+    # ---- measurement helpers -----------------------------------------------------------------
+    def launch_count(self):
+        v = C.c_int64()
+        _check(self._lib.cplb_get_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    def timing_begin(self):
+        _check(self._lib.cplb_timing_begin(self._h))
+
+    def timing_end(self):
+        ms, k = C.c_double(), C.c_int64()
+        _check(self._lib.cplb_timing_end(self._h, C.byref(ms), C.byref(k)))
+        return ms.value, k.value

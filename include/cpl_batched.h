@@ -1,0 +1,216 @@
+/*
+ * cpl_batched.h -- C ABI of the B200 batched evaluator for CentroidalPlanner's IFOPT problem.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no exceptions.
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * ADVRHumanoids/CentroidalPlanner tree).  One `cplb_problem` describes ONE problem *shape*
+ * (contact names, environment, parameters) -- what the reference holds in one
+ * `cpl::solver::CplProblem` -- and evaluates it for N independent instances (N different x)
+ * per call on one GPU.
+ *
+ * Layout contract (identical to the reference + ifopt):
+ *   columns  CoM -> 0..2; contact k (index in the CALLER'S name vector): F_k -> 3+9k+{0,1,2},
+ *            p_k -> 3+9k+{3,4,5}, n_k -> 3+9k+{6,7,8}                 (src/CplProblem.cpp:17-34)
+ *   rows     0..5 CentroidalStatics; contact of sorted-name rank j (std::map order):
+ *            6+6j EnvironmentConstraint, 6+6j+{1,2,3} EnvironmentNormal, 6+6j+{4,5}
+ *            FrictionCone; without environment 6+2j+{0,1} FrictionCone    (src/CplProblem.cpp:37-75)
+ *   Jacobian values in the order ifopt's IpoptAdapter::eval_jac_g emits (iRow, jCol): row-major,
+ *            column ascending, every coeffRef'd slot present even when its value is 0.0.
+ *
+ * Error convention: every function returns a cplb_status; on failure a message is kept in a
+ * thread-local buffer (cplb_last_error).  The status says which C++ exception the reference
+ * would have thrown at the same place.  Non-finite outputs are data, not errors (the reference
+ * divides by the tangential force norm without a guard, src/Constraints/FrictionCone.cpp:85-87).
+ *
+ * Threading: setters must not run concurrently with evaluation on the same problem.  Evaluation
+ * calls take x as an argument (not problem state, unlike Variable3D::SetVariables,
+ * src/Variable3D.cpp:18-25) so several host threads may evaluate disjoint instance ranges of the
+ * same problem on different streams at once.
+ */
+#ifndef CPL_BATCHED_H
+#define CPL_BATCHED_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPLB_ABI_VERSION 1
+#define CPLB_MAX_CONTACTS 32
+
+typedef enum cplb_status {
+    CPLB_OK = 0,
+    CPLB_INVALID_ARGUMENT = 1, /* reference throws std::invalid_argument */
+    CPLB_OUT_OF_RANGE = 2,     /* reference throws std::out_of_range (std::map::at on an unknown contact) */
+    CPLB_RUNTIME_ERROR = 3,    /* reference throws std::runtime_error */
+    CPLB_CUDA_ERROR = 4,       /* CUDA runtime failure (no device, launch failure, out of memory) */
+    CPLB_NULL_POINTER = 5      /* a required pointer argument was NULL */
+} cplb_status;
+
+/* cpl::env::EnvironmentClass::Ptr passed to CplProblem (src/CplProblem.cpp:8,44,63):
+ * nullptr / Ground / Superquadric */
+typedef enum cplb_env_kind {
+    CPLB_ENV_NONE = 0,
+    CPLB_ENV_GROUND = 1,
+    CPLB_ENV_SUPERQUADRIC = 2
+} cplb_env_kind;
+
+/* How the N instances are laid out in the batched buffers.
+ *  INSTANCE_MAJOR : buf[i*len + e]   -- instance i owns a contiguous slice; this is what one
+ *                   IPOPT thread hands to / receives from eval_g / eval_jac_g (x[n], g[m], values[nnz]).
+ *  COMPONENT_MAJOR: buf[e*ld + i]    -- struct-of-arrays, ld >= N is the row pitch in elements. */
+typedef enum cplb_layout {
+    CPLB_INSTANCE_MAJOR = 0,
+    CPLB_COMPONENT_MAJOR = 1
+} cplb_layout;
+
+/* Which variable block a bound refers to (Variable3D objects of src/CplProblem.cpp:17-33). */
+typedef enum cplb_block {
+    CPLB_BLOCK_COM = 0,
+    CPLB_BLOCK_FORCE = 1,
+    CPLB_BLOCK_POSITION = 2,
+    CPLB_BLOCK_NORMAL = 3
+} cplb_block;
+
+typedef struct cplb_problem cplb_problem; /* opaque */
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+
+/* Replaces cpl::solver::CplProblem::CplProblem(contact_names, robot_mass, env)
+ * (src/CplProblem.cpp:6-82) together with the robot_mass check of
+ * cpl::CentroidalPlanner::CentroidalPlanner (src/CentroidalPlanner.cpp:12-15: mass <= 0 ->
+ * CPLB_INVALID_ARGUMENT).  Parameters start at the reference's defaults (mass-g (0,0,-9.81),
+ * zero wrench, mu 1, F_thr 0, ground z 0, superquadric C=(0,0,10) R=P=(10,10,10), CoM ref (0,0,1),
+ * all weights 1, refs 0, variable bounds +-1000).  Duplicate or empty name lists are rejected
+ * (CPLB_INVALID_ARGUMENT): the reference's std::map would silently merge them.
+ * device: CUDA ordinal (validated now: CPLB_CUDA_ERROR when no CUDA device is usable), or -1 to bind to
+ * the calling thread's current device at the first evaluation.  Creation, layout queries and the
+ * parameter setters are host-only; evaluation on a machine without a GPU fails with
+ * CPLB_CUDA_ERROR -- there is no CPU fallback. */
+cplb_status cplb_create(int32_t num_contacts, const char *const *contact_names, cplb_env_kind env,
+                        double robot_mass, int32_t device, cplb_problem **out);
+void cplb_destroy(cplb_problem *p);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char *cplb_last_error(void);
+int32_t cplb_abi_version(void);
+
+/* ---- layout: what ifopt::Problem / IpoptAdapter report ------------------------------------- */
+
+/* n = GetNumberOfOptimizationVariables, m = GetNumberOfConstraints,
+ * nnz = GetJacobianOfConstraints().nonZeros() [ifopt; call sites src/CplProblem.cpp:19-80] */
+cplb_status cplb_get_dims(const cplb_problem *p, int32_t *n, int32_t *m, int32_t *nnz);
+/* IpoptAdapter::eval_jac_g(values == NULL): C-style (iRow, jCol), nnz entries each. */
+cplb_status cplb_get_jacobian_structure(const cplb_problem *p, int32_t *iRow, int32_t *jCol);
+/* sorted_to_vector[j] = index in the caller's name vector of the contact with sorted rank j
+ * (iteration order of _contact_vars_map, src/CplProblem.cpp:42). */
+cplb_status cplb_get_sorted_order(const cplb_problem *p, int32_t *sorted_to_vector);
+/* First column of a block / first row of a contact's constraint rows (-1 rows for statics = 0). */
+cplb_status cplb_get_block_column(const cplb_problem *p, cplb_block block, const char *contact_name, int32_t *col);
+cplb_status cplb_get_contact_row(const cplb_problem *p, const char *contact_name, int32_t *row);
+/* Problem::GetBoundsOnOptimizationVariables / GetBoundsOnConstraints
+ * (Variable3D::GetBounds src/Variable3D.cpp:54-65; CentroidalStatics.cpp:64-73, FrictionCone.cpp:48-58,
+ * EnvironmentConstraint.cpp:31-40, EnvironmentNormal.cpp:36-50; ifopt inf = 1e20). */
+cplb_status cplb_get_variable_bounds(const cplb_problem *p, double *lower, double *upper);
+cplb_status cplb_get_constraint_bounds(const cplb_problem *p, double *lower, double *upper);
+
+/* ---- parameters: the CplProblem forwarders (src/CplProblem.cpp:109-316) --------------------- */
+
+/* CentroidalStatics::SetMass (src/Constraints/CentroidalStatics.cpp:20-23); mass <= 0 rejected like the planner ctor. */
+cplb_status cplb_set_mass(cplb_problem *p, double mass);
+cplb_status cplb_get_mass(const cplb_problem *p, double *mass);
+/* CplProblem::Set/GetManipulationWrench (src/CplProblem.cpp:263-272) */
+cplb_status cplb_set_manipulation_wrench(cplb_problem *p, const double wrench[6]);
+cplb_status cplb_get_manipulation_wrench(const cplb_problem *p, double wrench[6]);
+/* CplProblem::SetMu/GetMu (src/CplProblem.cpp:275-303) -> EnvironmentClass::SetMu
+ * (include/CentroidalPlanner/Environment/Environment.h:19-26): mu <= 0 -> CPLB_INVALID_ARGUMENT */
+cplb_status cplb_set_mu(cplb_problem *p, double mu);
+cplb_status cplb_get_mu(const cplb_problem *p, double *mu);
+/* Ground::SetGroundZ/GetGroundZ (src/Ground.cpp:11-20); CPLB_RUNTIME_ERROR if env is not GROUND */
+cplb_status cplb_set_ground_z(cplb_problem *p, double ground_z);
+cplb_status cplb_get_ground_z(const cplb_problem *p, double *ground_z);
+/* Superquadric::SetParameters/GetParameters (src/Superquadric.cpp:12-37): any R <= 0 or any P < 2 ->
+ * CPLB_INVALID_ARGUMENT; CPLB_RUNTIME_ERROR if env is not SUPERQUADRIC */
+cplb_status cplb_set_superquadric(cplb_problem *p, const double C[3], const double R[3], const double P[3]);
+cplb_status cplb_get_superquadric(const cplb_problem *p, double C[3], double R[3], double P[3]);
+/* CplProblem::Set/GetForceThreshold (src/CplProblem.cpp:306-316) -> FrictionCone::SetForceThreshold
+ * (src/Constraints/FrictionCone.cpp:18-27); unknown contact -> CPLB_OUT_OF_RANGE (map::at) */
+cplb_status cplb_set_force_threshold(cplb_problem *p, const char *contact_name, double F_thr);
+cplb_status cplb_get_force_threshold(const cplb_problem *p, const char *contact_name, double *F_thr);
+/* CplProblem::Set*Bounds / Get*Bounds (src/CplProblem.cpp:109-172) -> Variable3D::SetBounds
+ * (src/Variable3D.cpp:28-40): any upper < lower -> CPLB_INVALID_ARGUMENT ("Inconsistent bounds"; like the
+ * reference the new bounds are stored BEFORE the check fires). contact_name ignored for CPLB_BLOCK_COM. */
+cplb_status cplb_set_bounds(cplb_problem *p, cplb_block block, const char *contact_name, const double lower[3],
+                            const double upper[3]);
+cplb_status cplb_get_bounds(const cplb_problem *p, cplb_block block, const char *contact_name, double lower[3],
+                            double upper[3]);
+/* MinimizeCentroidalVariables setters/getters (src/MinimizeCentroidalVariables.cpp:30-121) */
+cplb_status cplb_set_pos_ref(cplb_problem *p, const char *contact_name, const double ref[3]);
+cplb_status cplb_get_pos_ref(const cplb_problem *p, const char *contact_name, double ref[3]);
+cplb_status cplb_set_force_ref(cplb_problem *p, const char *contact_name, const double ref[3]);
+cplb_status cplb_get_force_ref(const cplb_problem *p, const char *contact_name, double ref[3]);
+cplb_status cplb_set_com_ref(cplb_problem *p, const double ref[3]);
+cplb_status cplb_get_com_ref(const cplb_problem *p, double ref[3]);
+cplb_status cplb_set_com_weight(cplb_problem *p, double W_CoM);
+cplb_status cplb_get_com_weight(const cplb_problem *p, double *W_CoM);
+cplb_status cplb_set_pos_weight(cplb_problem *p, double W_p);   /* all contacts (:80-86) */
+cplb_status cplb_set_force_weight(cplb_problem *p, double W_F); /* all contacts (:102-108) */
+cplb_status cplb_set_contact_pos_weight(cplb_problem *p, const char *contact_name, double W_p);
+cplb_status cplb_get_contact_pos_weight(const cplb_problem *p, const char *contact_name, double *W_p);
+cplb_status cplb_set_contact_force_weight(cplb_problem *p, const char *contact_name, double W_F);
+cplb_status cplb_get_contact_force_weight(const cplb_problem *p, const char *contact_name, double *W_F);
+
+/* ---- evaluation: the hot path -------------------------------------------------------------- */
+
+/* One batched evaluation.  Replaces, for N instances at once, what ifopt does per instance on behalf
+ * of IpoptAdapter (SetVariables(x) + ...):
+ *   g        Problem::EvaluateConstraints       -> each ConstraintSet::GetValues
+ *            (CentroidalStatics.cpp:37-61, FrictionCone.cpp:30-45, EnvironmentConstraint.cpp:16-28,
+ *             EnvironmentNormal.cpp:16-33, Ground.cpp:23-43, Superquadric.cpp:40-69)
+ *   jac      Problem::EvalNonzerosOfJacobian    -> each ConstraintSet::FillJacobianBlock
+ *            (CentroidalStatics.cpp:75-138, FrictionCone.cpp:60-103, EnvironmentConstraint.cpp:42-62,
+ *             EnvironmentNormal.cpp:52-87, Ground.cpp:30-50, Superquadric.cpp:51-210)
+ *   cost     Problem::EvaluateCostFunction      -> MinimizeCentroidalVariables::GetCost (:124-148)
+ *   grad     Problem::EvaluateCostFunctionGradient -> MinimizeCentroidalVariables::FillJacobianBlock (:151-193)
+ * Any of g / jac / cost / grad may be NULL: that output is not computed and not written.
+ * Element counts per instance: x n, g m, jac nnz, cost 1, grad n.  `layout`/`ld` apply to every buffer
+ * (cost is always cost[i]); ld is ignored for INSTANCE_MAJOR and may be 0 (= num_instances) otherwise. */
+typedef struct cplb_eval_args {
+    int64_t num_instances;
+    int32_t layout; /* cplb_layout */
+    int32_t reserved;
+    int64_t ld;
+    const double *x;
+    double *g;
+    double *jac;
+    double *cost;
+    double *grad;
+} cplb_eval_args;
+
+/* All pointers are DEVICE pointers on the problem's device; the kernel is enqueued on `cuda_stream`
+ * (a cudaStream_t, NULL = default stream) and the call returns without synchronising. */
+cplb_status cplb_eval_device(cplb_problem *p, const cplb_eval_args *args, void *cuda_stream);
+
+/* All pointers are HOST pointers (pinned memory makes the copies asynchronous and faster, pageable
+ * works).  Instances are cut into chunks; each chunk's host->device copy, kernel and device->host copy
+ * run on one of several internal streams so that both copy directions overlap the kernels.  Returns
+ * after every output has landed in the host buffers. */
+cplb_status cplb_eval_host(cplb_problem *p, const cplb_eval_args *args);
+
+/* Pinned host memory for cplb_eval_host buffers (cudaHostAlloc / cudaFreeHost). */
+cplb_status cplb_host_alloc(size_t bytes, void **out);
+cplb_status cplb_host_free(void *ptr);
+
+/* Number of kernels this problem has launched so far (bench.py's gpu_launches). */
+cplb_status cplb_get_launch_count(const cplb_problem *p, int64_t *launches);
+/* Average device time (ms, CUDA events on the launch stream) of the kernels launched by
+ * cplb_eval_device between cplb_timing_begin and cplb_timing_end; used by bench.py for the roofline. */
+cplb_status cplb_timing_begin(cplb_problem *p);
+cplb_status cplb_timing_end(cplb_problem *p, double *avg_kernel_ms, int64_t *kernels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPL_BATCHED_H */

@@ -1,0 +1,146 @@
+"""Shared test plumbing: the named configurations, product/oracle pairs with identical parameters,
+and the parity comparison (bit-exact where no pow() is upstream, <= 1e-12 relative elsewhere)."""
+from __future__ import annotations
+
+import numpy as np
+
+import centroidalplanner_b200 as cpl
+from centroidalplanner_b200 import synthetic
+from oracle import cpl_oracle_py as orc
+
+RTOL = 1e-12  # north_star: "within 1e-12 relative (fp64)"
+
+NAMES_PERMUTED = ["r_foot", "l_foot", "r_hand", "l_hand"]  # vector order != sorted order
+
+CASES = {
+    # name: (contact names, env kind, batch generator)
+    "ground4": (synthetic.NAMES4, "ground", lambda N: synthetic.ground_batch(N, 4, 1002)),
+    "superquadric4": (synthetic.NAMES4, "superquadric", lambda N: synthetic.superquadric_batch(N, 4, 1003)),
+    "ground8": (synthetic.NAMES8, "ground", lambda N: synthetic.ground_batch(N, 8, 1004)),
+    "noenv4": (NAMES_PERMUTED, "none", lambda N: synthetic.ground_batch(N, 4, 77)),
+    "ground1": (["contact1"], "ground", lambda N: synthetic.ground_batch(N, 1, 5)),
+    "superquadric3": (["c", "a", "b"], "superquadric", lambda N: synthetic.superquadric_batch(N, 3, 9)),
+    "ground5": (["e", "d", "c", "b", "a"], "ground", lambda N: synthetic.ground_batch(N, 5, 11)),
+    "noenv8": (synthetic.NAMES8, "none", lambda N: synthetic.ground_batch(N, 8, 13)),
+    "superquadric8": (synthetic.NAMES8, "superquadric", lambda N: synthetic.superquadric_batch(N, 8, 15)),
+    "ground12": (["k%02d" % (11 - i) for i in range(12)], "ground", lambda N: synthetic.ground_batch(N, 12, 17)),
+}
+
+
+class OracleProblem:
+    """Gives the oracle the same setter names as BatchedCplProblem so one routine configures both."""
+
+    def __init__(self, names, env_name, mass):
+        kind = {"none": orc.ENV_NONE, "ground": orc.ENV_GROUND, "superquadric": orc.ENV_SUPERQUADRIC}[env_name]
+        self.o = orc.Oracle(names, kind, mass)
+        self.names = list(names)
+
+    def SetGroundZ(self, z): self.o.set_ground_z(z)
+    def SetParameters(self, C, R, P): self.o.set_superquadric(C, R, P)
+    def SetMu(self, mu): self.o.set_mu(mu)
+    def SetManipulationWrench(self, w): self.o.set_wrench(w)
+    def SetForceThreshold(self, nm, t): self.o.set_force_threshold(nm, t)
+    def SetCoMRef(self, r): self.o.set_com_ref(r)
+    def SetCoMWeight(self, w): self.o.set_com_weight(w)
+    def SetPosRef(self, nm, r): self.o.set_pos_ref(nm, r)
+    def SetForceRef(self, nm, r): self.o.set_force_ref(nm, r)
+    def SetPosWeight(self, w): self.o.set_pos_weight(w)
+    def SetForceWeight(self, w): self.o.set_force_weight(w)
+    def SetContactPosWeight(self, nm, w): self.o.set_contact_pos_weight(nm, w)
+    def SetContactForceWeight(self, nm, w): self.o.set_contact_force_weight(nm, w)
+    def SetPosBounds(self, nm, lb, ub): self.o.set_var_bounds(orc.BLOCK_P, nm, lb, ub)
+    def SetForceBounds(self, nm, lb, ub): self.o.set_var_bounds(orc.BLOCK_F, nm, lb, ub)
+    def SetNormalBounds(self, nm, lb, ub): self.o.set_var_bounds(orc.BLOCK_N, nm, lb, ub)
+
+
+def configure(problem, env, names, env_name, rich=True):
+    """Same non-default parameters on either side.  `env` is the cpl.Ground/Superquadric object for the
+    product, or the OracleProblem itself for the oracle."""
+    if env_name == "ground":
+        env.SetGroundZ(synthetic.TESTBASIC["ground_z"])
+    elif env_name == "superquadric":
+        sq = synthetic.SUPERQUADRIC
+        env.SetParameters(sq["C"], sq["R"], sq["P"])
+    (env if env is not None else problem).SetMu(0.5)
+    problem.SetManipulationWrench(synthetic.TESTBASIC["wrench"])
+    problem.SetCoMWeight(2.0)
+    if rich:  # exercise every per-contact parameter with distinct values
+        problem.SetCoMRef([0.05, -0.02, 0.9])
+        for k, nm in enumerate(names):
+            problem.SetForceThreshold(nm, 10.0 + 3.0 * k)
+            problem.SetPosRef(nm, [0.1 * k, -0.05 * k, 0.02 * k])
+            problem.SetForceRef(nm, [1.0 + k, 2.0 - k, 100.0 + 10.0 * k])
+            problem.SetContactPosWeight(nm, 0.5 + 0.25 * k)
+            problem.SetContactForceWeight(nm, 0.001 * (k + 1))
+
+
+def make_pair(case, mass=100.0, rich=True):
+    names, env_name, gen = CASES[case]
+    env = {"none": None, "ground": cpl.Ground, "superquadric": cpl.Superquadric}[env_name]
+    env = env() if env is not None else None
+    prob = cpl.BatchedCplProblem(names, mass, env)
+    configure(prob, env, names, env_name, rich)
+    op = OracleProblem(names, env_name, mass)
+    configure(op, op if env_name != "none" else None, names, env_name, rich)
+    return prob, op.o, gen
+
+
+def pow_downstream_masks(o):
+    """Boolean masks (over g rows / jac slots) of the outputs that have a pow() upstream: only the
+    EnvironmentConstraint / EnvironmentNormal rows of a Superquadric problem."""
+    gm = np.zeros(o.m, dtype=bool)
+    jm = np.zeros(o.nnz, dtype=bool)
+    if o.env_kind == orc.ENV_SUPERQUADRIC:
+        iRow, jCol = o.structure()
+        for j in range(o.nc):
+            rows = 6 + 6 * j + np.arange(4)
+            gm[rows] = True
+            jm |= np.isin(iRow, rows)
+        # the identity entries of EnvironmentNormal's n-block are constants
+        perm = o.sorted_order()
+        for j in range(o.nc):
+            ncol = 3 + 9 * int(perm[j]) + 6
+            jm &= ~(np.isin(iRow, 6 + 6 * j + 1 + np.arange(3)) & (jCol >= ncol) & (jCol < ncol + 3))
+    return gm, jm
+
+
+def same_bits(a, b):
+    """Bit-identical, with NaNs matched by position (payload bits ignored)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    na, nb = np.isnan(a), np.isnan(b)
+    if not (na == nb).all():
+        return False
+    return bool((a.view(np.int64)[~na] == b.view(np.int64)[~nb]).all())
+
+
+def assert_parity(got, want, o, what, x=None):
+    """got/want: dicts with instance-major arrays g (N,m), jac (N,nnz), cost (N,), grad (N,n)."""
+    gm, jm = pow_downstream_masks(o)
+    for key in ("g", "jac", "cost", "grad"):
+        if want.get(key) is None or got.get(key) is None:
+            continue
+        a, b = np.asarray(got[key]), np.asarray(want[key])
+        assert a.shape == b.shape, (what, key, a.shape, b.shape)
+        mask = {"g": gm, "jac": jm}.get(key)
+        if mask is None or not mask.any():
+            assert same_bits(a, b), f"{what}: {key} is not bit-identical to the oracle"
+            continue
+        assert same_bits(a[:, ~mask], b[:, ~mask]), f"{what}: pow-free part of {key} is not bit-identical"
+        aa, bb = a[:, mask], b[:, mask]
+        assert (np.isnan(aa) == np.isnan(bb)).all(), f"{what}: NaN positions differ in {key}"
+        assert (np.isinf(aa) == np.isinf(bb)).all() and (aa[np.isinf(aa)] == bb[np.isinf(bb)]).all()
+        fin = np.isfinite(bb)
+        scale = np.abs(bb)
+        if key == "g":
+            # EnvironmentConstraint value is a sum of O(>=1) terms minus 1; the normal rows are n - n_env with
+            # |n_env| <= 1: relative-to-result is meaningless under cancellation, so the floor is the term scale
+            scale = np.maximum(scale, 1.0)
+        err = np.abs(aa - bb)[fin] / scale[fin]
+        worst = float(err.max()) if err.size else 0.0
+        assert worst <= RTOL, f"{what}: {key} differs from the oracle by {worst:.3e} relative (> {RTOL})"
+
+
+def to_instance_major(arr, layout):
+    a = np.asarray(arr)
+    return a.T if (layout == cpl.COMPONENT_MAJOR and a.ndim == 2) else a

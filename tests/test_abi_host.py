@@ -1,0 +1,156 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared
+symbol, the layout generator agrees with the oracle's discovered structure, the setters keep the
+reference's validation / error behaviour, and evaluation FAILS LOUDLY without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import centroidalplanner_b200 as cpl
+from centroidalplanner_b200 import _cabi, synthetic
+from oracle import cpl_oracle_py as orc
+
+from helpers import CASES, make_pair
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    hdr = open(os.path.join(ROOT, "include", "cpl_batched.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(cplb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    lib = C.CDLL(cpl.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libcplb.so does not export {name}"
+    assert declared == set(_cabi.PROTOTYPES), declared ^ set(_cabi.PROTOTYPES)
+    assert _cabi.load().cplb_abi_version() == 1
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "centroidalplanner_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", "Makefile")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                # no import / include / dlopen of anything under oracle/ (prose mentions are fine)
+                assert not re.search(r"cpl_oracle|import\s+oracle|from\s+oracle|libcpl_ref|#include\s*[<\"].*oracle", src), \
+                    os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_layout_matches_oracle_structure(case):
+    prob, o, _ = make_pair(case)
+    assert (prob.n, prob.m, prob.nnz) == (o.n, o.m, o.nnz)
+    r, c = prob.GetJacobianStructure()
+    ro, co = o.structure()
+    assert np.array_equal(r, ro) and np.array_equal(c, co)  # identical triplet order
+    assert np.array_equal(prob.GetSortedOrder(), o.sorted_order())
+    lb, ub = prob.GetBoundsOnConstraints()
+    lbo, ubo = o.con_bounds()
+    assert np.array_equal(lb, lbo) and np.array_equal(ub, ubo)
+    lb, ub = prob.GetBoundsOnOptimizationVariables()
+    lbo, ubo = o.var_bounds()
+    assert np.array_equal(lb, lbo) and np.array_equal(ub, ubo)
+
+
+def test_block_columns_and_contact_rows():
+    prob = cpl.BatchedCplProblem(["r_foot", "l_foot", "r_hand", "l_hand"], 100.0, cpl.Ground())
+    assert prob.GetBlockColumn(cpl.BLOCK_COM) == 0
+    assert prob.GetBlockColumn(cpl.BLOCK_FORCE, "l_foot") == 12
+    assert prob.GetBlockColumn(cpl.BLOCK_POSITION, "l_foot") == 15
+    assert prob.GetBlockColumn(cpl.BLOCK_NORMAL, "r_foot") == 9
+    assert prob.GetContactRow("l_foot") == 6 and prob.GetContactRow("r_hand") == 24
+    with pytest.raises(IndexError):
+        prob.GetContactRow("nose")
+
+
+def test_defaults_are_the_references():
+    prob = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, cpl.Ground())
+    assert prob.GetMu() == 1.0                                    # Environment.h:46
+    assert list(prob.GetCoMRef()) == [0.0, 0.0, 1.0]              # MinimizeCentroidalVariables.cpp:11
+    assert prob.GetCoMWeight() == 1.0
+    assert list(prob.GetManipulationWrench()) == [0.0] * 6        # CentroidalStatics.cpp:12
+    for nm in synthetic.NAMES4:
+        assert prob.GetForceThreshold(nm) == 0.0                  # FrictionCone.cpp:14
+        assert prob.GetContactPosWeight(nm) == 1.0 and prob.GetContactForceWeight(nm) == 1.0
+        assert list(prob.GetPosRef(nm)) == [0, 0, 0] and list(prob.GetForceRef(nm)) == [0, 0, 0]
+        lb, ub = prob.GetForceBounds(nm)
+        assert list(lb) == [-1000.0] * 3 and list(ub) == [1000.0] * 3  # Variable3D.cpp:12-13
+    sq = cpl.Superquadric()
+    Cc, R, P = sq.GetParameters()
+    assert list(Cc) == [0, 0, 10] and list(R) == [10, 10, 10] and list(P) == [10, 10, 10]  # Superquadric.cpp:7-9
+
+
+def test_validation_mirrors_the_reference_exceptions():
+    with pytest.raises(ValueError, match="Invalid robot mass"):      # CentroidalPlanner.cpp:12-15
+        cpl.BatchedCplProblem(synthetic.NAMES4, 0.0, cpl.Ground())
+    with pytest.raises(ValueError):
+        cpl.BatchedCplProblem(["a", "a"], 1.0, cpl.Ground())
+    with pytest.raises(ValueError):
+        cpl.BatchedCplProblem([], 1.0, cpl.Ground())
+    g = cpl.Ground()
+    with pytest.raises(ValueError, match="Invalid friction coefficient"):  # Environment.h:21-22
+        g.SetMu(0.0)
+    sq = cpl.Superquadric()
+    with pytest.raises(ValueError, match="axial radii"):             # Superquadric.cpp:16-19
+        sq.SetParameters([0, 0, 1], [0.3, 0.0, 10], [10, 10, 10])
+    with pytest.raises(ValueError, match="curvatures"):              # Superquadric.cpp:21-24
+        sq.SetParameters([0, 0, 1], [0.3, 0.3, 10], [10, 1.9, 10])
+    prob = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, g)
+    with pytest.raises(IndexError):                                  # std::map::at, CplProblem.cpp:113
+        prob.SetForceBounds("nose", [0, 0, 0], [1, 1, 1])
+    with pytest.raises(IndexError):                                  # MinimizeCentroidalVariables.cpp:33
+        prob.SetPosRef("nose", [0, 0, 0])
+    with pytest.raises(ValueError, match="Inconsistent bounds"):     # Variable3D.cpp:35-38
+        prob.SetPosBounds("contact1", [0, 0, 1], [1, 1, 0])
+    lb, ub = prob.GetPosBounds("contact1")                           # ... stored before the throw (:31-32)
+    assert list(lb) == [0, 0, 1] and list(ub) == [1, 1, 0]
+    with pytest.raises(ValueError, match="Invalid weight"):          # CentroidalPlanner.cpp:186-189
+        prob.SetCoMWeight(-1.0)
+    with pytest.raises(ValueError, match="Invalid weight"):
+        prob.SetContactForceWeight("contact2", -0.5)
+    lib = _cabi.load()                                               # the C level, directly
+    assert lib.cplb_set_mu(prob._h, -1.0) == _cabi.INVALID_ARGUMENT
+    assert b"friction" in lib.cplb_last_error()
+    assert lib.cplb_set_superquadric(prob._h, *(np.ones(3).ctypes.data_as(_cabi.dp),) * 3) == _cabi.RUNTIME_ERROR
+    assert lib.cplb_get_dims(None, None, None, None) == _cabi.NULL_POINTER
+
+
+def test_environment_object_is_shared_like_the_reference():
+    """The reference's sets alias one env object (CplProblem.cpp:47-59): a later SetMu is seen."""
+    g = cpl.Ground()
+    a = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, g)
+    b = cpl.BatchedCplProblem(["x", "y"], 50.0, g)
+    g.SetMu(0.25)
+    g.SetGroundZ(0.4)
+    lib = _cabi.load()
+    for prob in (a, b):
+        mu, z = C.c_double(), C.c_double()
+        assert lib.cplb_get_mu(prob._h, C.byref(mu)) == 0 and mu.value == 0.25
+        assert lib.cplb_get_ground_z(prob._h, C.byref(z)) == 0 and z.value == 0.4
+    c = cpl.BatchedCplProblem(["x", "y"], 50.0, None)   # CoMPlanner variant: _ground_fake holds mu (CplProblem.cpp:282-285)
+    c.SetMu(0.3)
+    assert c.GetMu() == 0.3 and (c.m, c.nnz) == (10, 60)
+
+
+def test_get_solution_unpacks_in_sorted_order():
+    prob = cpl.BatchedCplProblem(["r_foot", "l_foot"], 100.0, cpl.Ground())
+    x = np.arange(21, dtype=np.float64)
+    sol = prob.GetSolution(x)
+    assert list(sol["com_sol"]) == [0, 1, 2]
+    assert list(sol["contact_values_map"]) == ["l_foot", "r_foot"]     # std::map order (CplProblem.cpp:90)
+    assert list(sol["contact_values_map"]["l_foot"]["force_value"]) == [12, 13, 14]
+    assert list(sol["contact_values_map"]["r_foot"]["normal_value"]) == [9, 10, 11]
+
+
+def test_evaluation_without_a_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the loud-failure path is for CPU-only machines")
+    prob, _, gen = make_pair("ground4")
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        prob.eval(gen(8))

@@ -1,0 +1,151 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Bit-exact wherever no pow() is upstream; <= 1e-12 relative elsewhere (north_star)."""
+import numpy as np
+import pytest
+
+import centroidalplanner_b200 as cpl
+from centroidalplanner_b200 import synthetic
+
+from helpers import CASES, assert_parity, make_pair, same_bits, to_instance_major
+
+pytestmark = pytest.mark.gpu
+
+LAYOUTS = [cpl.INSTANCE_MAJOR, cpl.COMPONENT_MAJOR]
+
+
+def run_device(prob, x_np, layout, device, **want):
+    import torch
+
+    xd = torch.from_numpy(np.ascontiguousarray(x_np)).to(device)
+    if layout == cpl.COMPONENT_MAJOR:
+        xd = xd.t().contiguous()
+    out = prob.eval(xd, layout=layout, **want)
+    torch.cuda.synchronize()
+    return {k: (None if v is None else to_instance_major(v.cpu().numpy(), layout)) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_all_outputs_match_oracle(case, layout, cuda_device):
+    prob, o, gen = make_pair(case)
+    x = gen(1000)
+    want = o.eval_batch(x, nthreads=4)
+    got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
+    assert_parity(got, want, o, f"{case}/layout{layout}")
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("N", [1, 2, 7, 31, 33, 129, 4097])
+def test_ragged_batch_sizes(N, layout, cuda_device):
+    for case in ("ground4", "superquadric3", "noenv8"):
+        prob, o, gen = make_pair(case)
+        x = gen(N)
+        want = o.eval_batch(x)
+        got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
+        assert_parity(got, want, o, f"{case}/N{N}/layout{layout}")
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("want", [dict(g=True, jac=False), dict(g=False, jac=True), dict(g=False, jac=False, cost=True),
+                                  dict(g=False, jac=False, grad=True), dict(g=True, jac=True, cost=True, grad=False)])
+def test_output_subsets_do_not_touch_other_buffers(want, layout, cuda_device):
+    prob, o, gen = make_pair("superquadric4")
+    x = gen(513)
+    ref = o.eval_batch(x)
+    got = run_device(prob, x, layout, cuda_device, **want)
+    for k in ("g", "jac", "cost", "grad"):
+        if not want.get(k, False):
+            assert got[k] is None
+            ref[k] = None
+    assert_parity(got, ref, o, f"subset{want}/layout{layout}")
+
+
+def test_default_start_point_nan_pattern(cuda_device):
+    """x = 0 (Variable3D.cpp:8-10): NaN exactly where the reference produces NaN."""
+    for case in ("ground4", "noenv4", "superquadric4"):
+        prob, o, _ = make_pair(case)
+        x = np.zeros((40, o.n))
+        want = o.eval_batch(x)
+        assert np.isnan(want["jac"]).any()
+        for layout in LAYOUTS:
+            got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
+            assert_parity(got, want, o, f"{case}/zeros/layout{layout}")
+
+
+def test_equilibrium_point_and_special_values(cuda_device):
+    from test_oracle import equilibrium_x
+
+    prob, o, _ = make_pair("ground4", rich=False)
+    x = np.tile(equilibrium_x(), (64, 1))
+    x[1, 3:6] = [0.0, 0.0, -0.0]
+    x[2, 0:3] = [1e300, -1e300, 1e-300]      # overflow / underflow are values, not errors
+    x[3, 9:12] = [np.inf, 0.0, 1.0]
+    x[4, 5] = np.nan
+    want = o.eval_batch(x)
+    assert np.abs(want["g"][0, :6]).max() <= 1e-12
+    for layout in LAYOUTS:
+        got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
+        assert_parity(got, want, o, f"special/layout{layout}")
+
+
+def test_parameter_updates_are_seen_by_the_next_launch(cuda_device):
+    prob, o, gen = make_pair("ground4")
+    x = gen(256)
+    prob.SetManipulationWrench([1, 2, 3, 4, 5, 6])
+    o.set_wrench([1, 2, 3, 4, 5, 6])
+    prob.SetMass(73.5)
+    o.set_mass(73.5)
+    prob.SetMu(0.9)
+    o.set_mu(0.9)
+    prob.SetForceThreshold("contact3", 42.0)
+    o.set_force_threshold("contact3", 42.0)
+    got = run_device(prob, x, cpl.INSTANCE_MAJOR, cuda_device, g=True, jac=True, cost=True, grad=True)
+    assert_parity(got, o.eval_batch(x), o, "updated parameters")
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_host_buffer_path_matches_device_path(layout, cuda_device):
+    """cplb_eval_host (H2D, kernel, D2H in chunks on several streams) == cplb_eval_device, bit for bit."""
+    prob, o, gen = make_pair("ground8")
+    N = 40000  # > one chunk, ragged last chunk
+    x = gen(N)
+    xin = x if layout == cpl.INSTANCE_MAJOR else np.ascontiguousarray(x.T)
+    host = prob.eval(xin, g=True, jac=True, cost=True, grad=True, layout=layout)
+    host = {k: to_instance_major(v, layout) for k, v in host.items()}
+    dev = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
+    for k in ("g", "jac", "cost", "grad"):
+        assert same_bits(host[k], dev[k]), k
+    sub = np.arange(0, N, 37)
+    want = o.eval_batch(x[sub])
+    assert_parity({k: host[k][sub] for k in host}, want, o, "host path")
+
+
+@pytest.mark.parametrize("case,N", [("ground4", 65536), ("superquadric4", 65536), ("ground8", 1 << 20)])
+def test_full_size_configs(case, N, cuda_device):
+    """BASELINE.json configs 2-4 at full size.  The oracle checks a strided sample; the two kernels (different
+    code paths: thread-per-instance vs warp tiles + bulk copies) must agree bit for bit on every instance;
+    and the statics rows obey their closed-form identities for all N."""
+    import torch
+
+    prob, o, gen = make_pair(case, rich=False)
+    x = gen(N)
+    xd = torch.from_numpy(x).to(cuda_device)
+    a = prob.eval(xd, g=True, jac=True, layout=cpl.INSTANCE_MAJOR)
+    b = prob.eval(xd.t().contiguous(), g=True, jac=True, layout=cpl.COMPONENT_MAJOR)
+    torch.cuda.synchronize()
+    for k in ("g", "jac"):
+        assert torch.equal(a[k].view(torch.int64), b[k].t().contiguous().view(torch.int64)), f"{case}: {k} differs between kernels"
+    sub = np.arange(0, N, max(1, N // 2048))
+    want = o.eval_batch(x[sub], want=("g", "jac"), nthreads=4)
+    got = {"g": a["g"][torch.from_numpy(sub).to(cuda_device)].cpu().numpy(),
+           "jac": a["jac"][torch.from_numpy(sub).to(cuda_device)].cpu().numpy()}
+    assert_parity(got, want, o, f"{case}/full")
+    # size-independent property: the force-balance Jacobian rows are all 1.0 and row r of g equals
+    # Sigma_k F_k[r] - w[r] + m g[r] up to summation-order rounding
+    nc = o.nc
+    jac = a["jac"]
+    assert bool((jac[:, : 3 * nc] == 1.0).all())
+    F = xd[:, 3:].reshape(N, nc, 9)[:, :, 0:3].sum(dim=1)
+    w = torch.tensor(synthetic.TESTBASIC["wrench"][:3], device=cuda_device, dtype=torch.float64)
+    mg = torch.tensor([0.0, 0.0, -981.0], device=cuda_device, dtype=torch.float64)
+    assert float((a["g"][:, :3] - (F - w + mg)).abs().max()) <= 1e-9
