@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- constraint+Jacobian evaluations per second of the batched evaluator.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one batched evaluation (constraint values g and Jacobian values, fused in one kernel
+launch) of BASELINE.json configs[1]: 65,536 synthetic 4-contact flat-ground instances per GPU.
+Instances shard by index across ranks with no collective on the data path (weak scaling: every
+rank evaluates its own 65,536-instance shard).  Prints ONE JSON line (rank 0).
+
+  value     instances/s, inputs resident in HBM, K back-to-back launches bracketed by CUDA events
+            on the launch stream; successive steps rotate through buffer sets whose total size
+            is >> L2, so every step reads and writes HBM, not L2.
+  e2e       the same metric through cplb_eval_host: HOST (pinned) buffers in, host buffers out,
+            H2D and D2H copies inside the timed region.
+  roofline  algorithmic bytes per launch (8*(n+m+nnz) per instance) / average launch
+            duration over the timed region, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline  the CPU oracle (port of the reference's evaluation) timed on this box's host cores.
+
+--impl reference times the reference's own CPU evaluation (oracle/_ref when it was built from the
+reference sources, else the oracle port) on all host cores, same config/metric.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_PER_GPU = 65536
+NC = 4
+WORKLOAD = "configs[1]: 65,536 synthetic 4-contact flat-ground instances per GPU, fused g+Jacobian eval"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def algorithmic_bytes_per_instance(n, m, nnz):
+    return 8 * (n + m + nnz)  # read x[n], write g[m] and jac[nnz], fp64
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed regions run (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(rank):
+    from centroidalplanner_b200 import synthetic
+
+    return synthetic.ground_batch(N_PER_GPU, NC, seed=1002 + 7919 * rank)
+
+
+def configure(problem_like, env_like):
+    from centroidalplanner_b200 import synthetic
+
+    tb = synthetic.TESTBASIC
+    env_like.SetGroundZ(tb["ground_z"])
+    env_like.SetMu(tb["mu"])
+    synthetic.configure_testbasic(problem_like, synthetic.NAMES4)
+
+
+def oracle_problem():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import OracleProblem  # the oracle with the product's setter names
+
+    op = OracleProblem(__import__("centroidalplanner_b200").synthetic.NAMES4, "ground", 100.0)
+    configure(op, op)
+    return op.o
+
+
+def time_cpu(o, x, threads, budget_s=10.0, want=("g", "jac")):
+    """Bounded CPU sample: repeat the 65,536-instance batch until ~budget_s of wall time is spent."""
+    out = {"g": np.empty((x.shape[0], o.m)), "jac": np.empty((x.shape[0], o.nnz))}
+    o.eval_batch(x[:4096], want=want, nthreads=threads)  # warm-up
+    t0 = time.perf_counter()
+    o.eval_batch(x, want=want, nthreads=threads, out=out)
+    one = time.perf_counter() - t0
+    reps = max(1, min(50, int(budget_s / max(one, 1e-6))))
+    best = one
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        o.eval_batch(x, want=want, nthreads=threads, out=out)
+        best = min(best, time.perf_counter() - t0)
+    return x.shape[0] / best, reps + 1
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU evaluation on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    x = make_inputs(0)
+    kind, sample = "port", ""
+    ref_lib = os.path.join(ROOT, "oracle", "_ref", "libcpl_ref.so")
+    per_step = []
+    if os.path.exists(ref_lib):
+        from oracle import cpl_ref_py
+
+        r = cpl_ref_py.RefProblem(__import__("centroidalplanner_b200").synthetic.NAMES4, "ground", 100.0)
+        configure(r, r)
+        kind = "reference"
+        n_s = min(N_PER_GPU, 8192)
+        fn = lambda: r.eval_batch(x[:n_s], nthreads=cores)  # noqa: E731
+        sample = (f"{n_s} of the 65,536 instances per step through the reference's own ifopt components "
+                  f"(oracle/_ref: reference sources compiled against stand-in Eigen/ifopt headers), {cores} threads")
+    else:
+        o = oracle_problem()
+        n_s = N_PER_GPU
+        buf = {"g": np.empty((n_s, o.m)), "jac": np.empty((n_s, o.nnz))}
+        fn = lambda: o.eval_batch(x, want=("g", "jac"), nthreads=cores, out=buf)  # noqa: E731
+        sample = f"all 65,536 instances per step through the C oracle port, {cores} threads"
+    for _ in range(max(1, min(args.warmup, 3))):
+        fn()
+    steps = max(1, min(args.steps, 20))
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fn()
+        per_step.append(time.perf_counter() - t0)
+    total = time.perf_counter() - t_all
+    value = n_s * steps / total
+    line = {"impl": "reference", "metric": "constraint+Jacobian evals/sec (instances/s)", "value": value, "unit": "instances/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * total / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "num_contacts": NC, "env": "Ground"},
+            "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def pinned_array(lib, shape):
+    nbytes = int(np.prod(shape)) * 8
+    ptr = C.c_void_p()
+    st = lib.cplb_host_alloc(nbytes, C.byref(ptr))
+    if st != 0:
+        raise RuntimeError(lib.cplb_last_error().decode())
+    arr = np.ctypeslib.as_array((C.c_double * (nbytes // 8)).from_address(ptr.value)).reshape(shape)
+    return arr, ptr
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import centroidalplanner_b200 as cpl
+    from centroidalplanner_b200 import _cabi, synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the evaluator has no CPU fallback (use --impl reference for the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    env = cpl.Ground()
+    prob = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, env, device=local)
+    configure(prob, env)
+    n, m, nnz = prob.n, prob.m, prob.nnz
+    N = N_PER_GPU
+    bytes_per_launch = algorithmic_bytes_per_instance(n, m, nnz) * N
+    layout = cpl.INSTANCE_MAJOR if args.layout == "instance" else cpl.COMPONENT_MAJOR
+
+    x_host = make_inputs(rank)
+    # buffer sets: total footprint >> L2 so no step finds its lines in L2
+    sets = max(4, int(np.ceil(8 * L2_BYTES / bytes_per_launch)))
+    xs, gs, js = [], [], []
+    shape = (lambda length: (N, length)) if layout == cpl.INSTANCE_MAJOR else (lambda length: (length, N))
+    base = torch.from_numpy(x_host if layout == cpl.INSTANCE_MAJOR else np.ascontiguousarray(x_host.T)).to(dev)
+    for s in range(sets):
+        xs.append(base.clone())
+        gs.append(torch.empty(shape(m), dtype=torch.float64, device=dev))
+        js.append(torch.empty(shape(nnz), dtype=torch.float64, device=dev))
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        s = i % sets
+        prob.eval(xs[s], g=True, jac=True, layout=layout, out={"g": gs[s], "jac": js[s]})
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    W, K = max(3, args.warmup), args.steps
+    for i in range(W):
+        step(i)
+    barrier()
+    launches0 = prob.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        step(W + i)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = prob.launch_count() - launches0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    value = world * N / (ms_per_step * 1e-3)
+
+    # per-launch device time with an event pair around every launch (same stream), second pass
+    prob.timing_begin()
+    for i in range(min(K, 200)):
+        step(W + K + i)
+    torch.cuda.synchronize(dev)
+    ev_ms, ev_k = prob.timing_end()
+
+    # ---- e2e: host buffers through cplb_eval_host -------------------------------------------
+    lib = _cabi.load()
+    hx, px = pinned_array(lib, shape(n))
+    hg, pg = pinned_array(lib, shape(m))
+    hj, pj = pinned_array(lib, shape(nnz))
+    hx[...] = x_host if layout == cpl.INSTANCE_MAJOR else x_host.T
+    e2e_steps = max(3, min(K, 20))
+    for _ in range(2):
+        prob.eval(hx, g=True, jac=True, layout=layout, out={"g": hg, "jac": hj})
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        prob.eval(hx, g=True, jac=True, layout=layout, out={"g": hg, "jac": hj})  # synchronous: outputs landed
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_check = float(np.abs(hg).sum())  # touch the result on the host
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": "constraint+Jacobian evals/sec (instances/s)", "value": value, "unit": "instances/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "num_contacts": NC, "env": "Ground", "instances_per_gpu": N,
+                       "layout": "instance-major" if layout == cpl.INSTANCE_MAJOR else "component-major",
+                       "outputs": "g+jac", "params": "shared",
+                       "l2": f"inputs larger than L2: steps rotate through {sets} buffer sets, {sets * bytes_per_launch / 2**20:.0f} MiB total vs 126 MiB L2"},
+            "e2e": {"value": world * N / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": 8 * n * N,
+                    "d2h_bytes_per_step": 8 * (m + nnz) * N, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s,
+                    "api": "cplb_eval_host (pinned host buffers; chunked H2D/kernel/D2H on 3 streams)", "checksum": e2e_check},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
+                         "kernel": "eval_instance_major" if layout == cpl.INSTANCE_MAJOR else "eval_component_major",
+                         "avg_launch_ms": ms_per_step, "avg_launch_ms_event_pairs": ev_ms, "event_pair_launches": ev_k},
+            "clocks": clocks,
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                line["roofline"]["traffic"] = json.load(open(traffic_file)).get(line["roofline"]["kernel"])
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu:
+            from oracle import cpl_oracle_py  # noqa: F401  (cpu_baseline leg: the oracle as the timed CPU port)
+
+            o = oracle_problem()
+            o.set_call_all_pairs(0)
+            cores = host_cores()
+            v, reps = time_cpu(o, x_host, cores, budget_s=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": "instances/s", "cores": cores, "kind": "port",
+                                    "sample": f"{reps} passes over the same 65,536 instances, best pass; C oracle (-O2), "
+                                              f"{cores} threads, pairs that produce no Jacobian entry skipped (conservative: "
+                                              "faster than the reference's own ifopt assembly)"}
+        print(json.dumps(line), flush=True)
+
+    for p in (px, pg, pj):
+        lib.cplb_host_free(p)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layout", default="instance", choices=["instance", "component"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,100 +18,125 @@
 namespace cplb {
 
 // ================================================================================================
-// component-major (SoA): one thread per instance
+// component-major (SoA)
 // ================================================================================================
 
+// Addressing: element (e, i) lives at base + e*ld + i.  With the row pitch in BYTES held in 32 bits
+// (ld < 2^29) every address is one IMAD.WIDE.U32 (e * pitch + pointer): the kernel issues ~250
+// loads/stores per instance, so the address arithmetic is as hot as the fp64 arithmetic.
 struct SoaEmitter {
-    double* gp;
-    double* jp;
-    double* gradp;
-    long long ld;
-    long long i;
+    char* gp;  // already offset to this thread's instance column
+    char* jp;
+    char* gradp;
+    unsigned pitch;  // ld * sizeof(double)
     // streaming stores: every output element is written once and never re-read by this kernel
-    __device__ __forceinline__ void put(double* base, int e, double v) const { __stcs(base + (long long)e * ld + i, v); }
+    __device__ __forceinline__ void put(char* base, int e, double v) const
+    {
+        __stcs(reinterpret_cast<double*>(base + (unsigned long long)(unsigned)e * pitch), v);
+    }
     __device__ __forceinline__ void g(int row, double v) const { put(gp, row, v); }
     __device__ __forceinline__ void j(int slot, double v) const { put(jp, slot, v); }
     __device__ __forceinline__ void grad(int col, double v) const { put(gradp, col, v); }
 };
 
-template <int ENV, int NC>
-__global__ void __launch_bounds__(128) eval_component_major(const __grid_constant__ CplbParams P, const CplbIo io,
-                                                             const unsigned flags)
+__device__ __forceinline__ double ld_stream(const char* base, int e, unsigned pitch)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= io.N) return;
-    const int nc = NC > 0 ? NC : P.nc;
-    const long long ld = io.ld;
-    const double* __restrict__ x = io.x + i;
-    SoaEmitter em{io.g, io.jac, io.grad, ld, i};
+    return __ldcs(reinterpret_cast<const double*>(base + (unsigned long long)(unsigned)e * pitch));
+}
 
-    double c[3];
-#pragma unroll
-    for (int q = 0; q < 3; q++) c[q] = __ldcs(x + q * ld);
-
-    // CentroidalStatics::GetValues accumulators (CentroidalStatics.cpp:39-54) and the CoM block of
-    // FillJacobianBlock (:121-135), all summed over contacts in sorted-name order.
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, v4 = 0.0, v5 = 0.0;
-    double a31 = 0.0, a32 = 0.0, a40 = 0.0, a42 = 0.0, a50 = 0.0, a51 = 0.0;
-    double cost = 0.0;
+// One thread per (instance, contact): warp w of a CTA owns the contact of sorted rank w for 32
+// consecutive instances, so a CTA is nc warps and every global access of a warp is one contiguous
+// 256-byte segment.  Compared with one thread per instance this puts nc times more warps in
+// flight and cuts each thread's dependent instruction stream by nc -- what matters at 65,536
+// instances, where the whole batch is less than one wave of threads and latency, not bandwidth,
+// is the limit.  The only cross-contact quantities are the six CentroidalStatics sums; each warp
+// leaves its contact's force and moment term in shared memory and, after one barrier, warp r adds
+// row r's terms in sorted-name order (CentroidalStatics.cpp:44-54), the order that fixes rounding.
+template <int ENV, unsigned FLAGS, int MAX_WARPS>
+__global__ void __launch_bounds__(MAX_WARPS * 32) eval_component_major_split(const __grid_constant__ CplbParams P, const CplbIo io,
+                                                                   const unsigned flags_rt)
+{
+    extern __shared__ double sh[];  // [nc][6][32]
+    const unsigned flags = FLAGS ? FLAGS : flags_rt;
+    const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const int nc = P.nc;
+    const long long i_raw = (long long)blockIdx.x * 32 + lane;
+    const bool active = i_raw < io.N;
+    const long long i = active ? i_raw : io.N - 1;  // inactive lanes recompute the last instance, store nothing
+    const unsigned pitch = (unsigned)(io.ld * (long long)sizeof(double));
+    const char* x = reinterpret_cast<const char*>(io.x + i);
+    const int k = P.perm[j];
     const bool need_n = flags & (CPLB_WANT_G | CPLB_WANT_J);
 
-#pragma unroll(NC > 0 ? NC : 1)
-    for (int j = 0; j < nc; j++) {
-        const int k = P.perm[j];
-        const double* xk = x + (long long)(3 + 9 * k) * ld;
-        double F[3], p[3], n[3] = {0.0, 0.0, 0.0};
+    double c[3], F[3], p[3], n[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-            F[q] = __ldcs(xk + q * ld);
-            p[q] = __ldcs(xk + (3 + q) * ld);
-        }
-        if (need_n) {
+    for (int q = 0; q < 3; q++) c[q] = ld_stream(x, q, pitch);
 #pragma unroll
-            for (int q = 0; q < 3; q++) n[q] = __ldcs(xk + (6 + q) * ld);
-        }
-        const double d0 = p[0] - c[0], d1 = p[1] - c[1], d2 = p[2] - c[2];
-        v0 += F[0];
-        v1 += F[1];
-        v2 += F[2];
-        v3 += d1 * F[2] - d2 * F[1];
-        v4 += d2 * F[0] - d0 * F[2];
-        v5 += d0 * F[1] - d1 * F[0];
-        a31 -= F[2];
-        a32 -= -F[1];
-        a40 -= -F[2];
-        a42 -= F[0];
-        a50 -= F[1];
-        a51 -= -F[0];
-        contact_rows<ENV>(P, em, nc, j, k, c, F, p, n, flags);
-        if (flags & CPLB_WANT_COST) cost += contact_cost(P, k, F, p);
+    for (int q = 0; q < 3; q++) F[q] = ld_stream(x, 3 + 9 * k + q, pitch);
+#pragma unroll
+    for (int q = 0; q < 3; q++) p[q] = ld_stream(x, 6 + 9 * k + q, pitch);
+    if (need_n) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) n[q] = ld_stream(x, 9 + 9 * k + q, pitch);
     }
 
-    if (flags & CPLB_WANT_G) {  // :56-57  value -= wrench; value.head<3>() += m*g
-        em.g(0, (v0 - P.wrench[0]) + P.mg[0]);
-        em.g(1, (v1 - P.wrench[1]) + P.mg[1]);
-        em.g(2, (v2 - P.wrench[2]) + P.mg[2]);
-        em.g(3, v3 - P.wrench[3]);
-        em.g(4, v4 - P.wrench[4]);
-        em.g(5, v5 - P.wrench[5]);
-    }
-    if (flags & CPLB_WANT_J) {
-        const int L = jac_moment_row_len(nc);
-        const int s3 = 3 * nc;
-        em.j(s3 + 0, a31);
-        em.j(s3 + 1, a32);
-        em.j(s3 + L + 0, a40);
-        em.j(s3 + L + 1, a42);
-        em.j(s3 + 2 * L + 0, a50);
-        em.j(s3 + 2 * L + 1, a51);
+    double* mine = sh + (size_t)j * 192 + lane;
+    if (flags & (CPLB_WANT_G | CPLB_WANT_J)) {
+        const double d0 = p[0] - c[0], d1 = p[1] - c[1], d2 = p[2] - c[2];
+        mine[0 * 32] = F[0];
+        mine[1 * 32] = F[1];
+        mine[2 * 32] = F[2];
+        mine[3 * 32] = d1 * F[2] - d2 * F[1];  // (p - CoM).cross(F), CentroidalStatics.cpp:53
+        mine[4 * 32] = d2 * F[0] - d0 * F[2];
+        mine[5 * 32] = d0 * F[1] - d1 * F[0];
     }
     if (flags & CPLB_WANT_COST) {
-        cost += com_cost(P, c);
-        __stcs(io.cost + i, cost);
+        if (!(flags & (CPLB_WANT_G | CPLB_WANT_J))) mine[0] = contact_cost(P, k, F, p);
+        else sh[(size_t)nc * 192 + (size_t)j * 32 + lane] = contact_cost(P, k, F, p);
     }
-    if (flags & CPLB_WANT_GRAD) {
+
+    SoaEmitter em{reinterpret_cast<char*>(io.g + i), reinterpret_cast<char*>(io.jac + i),
+                  reinterpret_cast<char*>(io.grad + i), pitch};
+    if (active) contact_rows<ENV>(P, em, nc, j, k, c, F, p, n, flags);
+
+    __syncthreads();
+    if (!active) return;
+
+    if (flags & (CPLB_WANT_G | CPLB_WANT_J)) {
+        const int L = jac_moment_row_len(nc);
+        for (int r = j; r < 6; r += nc) {
+            const double* col = sh + r * 32 + lane;
+            double v = 0.0;
+            for (int jj = 0; jj < nc; jj++) v += col[(size_t)jj * 192];
+            if (flags & CPLB_WANT_G) em.g(r, r < 3 ? (v - P.wrench[r]) + P.mg[r] : v - P.wrench[r]);  // :56-57
+            if ((flags & CPLB_WANT_J) && r >= 3) {
+                // CoM block (:128-133): row 3 <- (Fz, -Fy), row 4 <- (-Fz, Fx), row 5 <- (Fy, -Fx), each "acc -= term"
+                const int ia = r == 3 ? 2 : (r == 4 ? 2 : 1), ib = r == 3 ? 1 : (r == 4 ? 0 : 0);
+                const bool nega = (r == 4), negb = (r != 4);
+                double a = 0.0, b = 0.0;
+                for (int jj = 0; jj < nc; jj++) {
+                    const double fa = sh[(size_t)jj * 192 + ia * 32 + lane], fb = sh[(size_t)jj * 192 + ib * 32 + lane];
+                    a -= nega ? -fa : fa;
+                    b -= negb ? -fb : fb;
+                }
+                em.j(3 * nc + (r - 3) * L + 0, a);
+                em.j(3 * nc + (r - 3) * L + 1, b);
+            }
+        }
+    }
+    if (j == 0) {
+        if (flags & CPLB_WANT_COST) {  // MinimizeCentroidalVariables.cpp:126-147: contacts in sorted order, then the CoM term
+            const double* cc = (flags & (CPLB_WANT_G | CPLB_WANT_J)) ? sh + (size_t)nc * 192 + lane : sh + lane;
+            const size_t stride = (flags & (CPLB_WANT_G | CPLB_WANT_J)) ? 32 : 192;
+            double cost = 0.0;
+            for (int jj = 0; jj < nc; jj++) cost += cc[(size_t)jj * stride];
+            cost += com_cost(P, c);
+            __stcs(io.cost + i, cost);
+        }
+        if (flags & CPLB_WANT_GRAD) {
 #pragma unroll
-        for (int q = 0; q < 3; q++) em.grad(q, P.W_com * (c[q] - P.com_ref[q]));
+            for (int q = 0; q < 3; q++) em.grad(q, P.W_com * (c[q] - P.com_ref[q]));
+        }
     }
 }
 
@@ -322,12 +347,17 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
 template <int ENV>
 static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
 {
-    const int threads = 128;
-    const unsigned blocks = (unsigned)((io.N + threads - 1) / threads);
-    switch (P.nc) {
-    case 4: eval_component_major<ENV, 4><<<blocks, threads, 0, st>>>(P, io, flags); break;
-    case 8: eval_component_major<ENV, 8><<<blocks, threads, 0, st>>>(P, io, flags); break;
-    default: eval_component_major<ENV, 0><<<blocks, threads, 0, st>>>(P, io, flags); break;
+    const unsigned blocks = (unsigned)((io.N + 31) / 32);
+    const int threads = 32 * P.nc;
+    const size_t smem = (size_t)P.nc * (192 + 32) * sizeof(double);
+    const unsigned gj = CPLB_WANT_G | CPLB_WANT_J;
+    if (P.nc <= 8) {
+        if (flags == gj)
+            eval_component_major_split<ENV, gj, 8><<<blocks, threads, smem, st>>>(P, io, flags);
+        else
+            eval_component_major_split<ENV, 0u, 8><<<blocks, threads, smem, st>>>(P, io, flags);
+    } else {
+        eval_component_major_split<ENV, 0u, 32><<<blocks, threads, smem, st>>>(P, io, flags);
     }
     return cudaGetLastError();
 }
@@ -335,6 +365,7 @@ static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned
 cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
 {
     if (io.N <= 0) return cudaSuccess;
+    if (io.ld >= (1LL << 29)) return cudaErrorInvalidValue;  // row pitch must fit 32 bits of bytes
     switch (P.env) {
     case CPLB_ENV_NONE_K: return launch_cm_env<CPLB_ENV_NONE_K>(P, io, flags, st);
     case CPLB_ENV_GROUND_K: return launch_cm_env<CPLB_ENV_GROUND_K>(P, io, flags, st);

@@ -136,6 +136,7 @@ def assert_parity(got, want, o, what, x=None):
             # EnvironmentConstraint value is a sum of O(>=1) terms minus 1; the normal rows are n - n_env with
             # |n_env| <= 1: relative-to-result is meaningless under cancellation, so the floor is the term scale
             scale = np.maximum(scale, 1.0)
+        scale = np.where(scale > 0.0, scale, 1.0)  # an exact 0.0 in the oracle: absolute 1e-12
         err = np.abs(aa - bb)[fin] / scale[fin]
         worst = float(err.max()) if err.size else 0.0
         assert worst <= RTOL, f"{what}: {key} differs from the oracle by {worst:.3e} relative (> {RTOL})"

@@ -76,11 +76,17 @@ def test_equilibrium_point_and_special_values(cuda_device):
     from test_oracle import equilibrium_x
 
     prob, o, _ = make_pair("ground4", rich=False)
+    prob.SetManipulationWrench(np.zeros(6))
+    o.set_wrench(np.zeros(6))
     x = np.tile(equilibrium_x(), (64, 1))
     x[1, 3:6] = [0.0, 0.0, -0.0]
     x[2, 0:3] = [1e300, -1e300, 1e-300]      # overflow / underflow are values, not errors
     x[3, 9:12] = [np.inf, 0.0, 1.0]
     x[4, 5] = np.nan
+    x[5, 3:6] = [1e-200, -2e-200, 3e-200]    # friction-row divisions outside the fast-division window
+    x[6, 3:6] = [1e200, 2e200, -3e200]
+    x[7, 3:6] = [4.9e-324, 0.0, 1e-310]      # subnormal forces
+    x[8, 9:12] = [1e-170, 1e-170, 1e-170]    # subnormal products
     want = o.eval_batch(x)
     assert np.abs(want["g"][0, :6]).max() <= 1e-12
     for layout in LAYOUTS:
