@@ -112,6 +112,18 @@ struct cplb_problem {
             P.sqRm2P[q] = std::pow(sqR[q], -twoP);
             P.sqR2P[q] = std::pow(sqR[q], twoP);
         }
+        // integer-curvature fast path of the kernels (cplb_device.cuh, superquadric())
+        bool ints = true;
+        double pmax = 0.0;
+        for (int q = 0; q < 3; q++) {
+            ints = ints && sqP[q] >= 2.0 && sqP[q] <= 63.0 && sqP[q] == std::floor(sqP[q]);
+            pmax = sqP[q] > pmax ? sqP[q] : pmax;
+        }
+        for (int q = 0; q < 3; q++) P.sqIntP[q] = ints ? (int)sqP[q] : 0;
+        int bits = 0;
+        for (int e = ints ? 2 * (int)pmax : 0; e > 0; e >>= 1) bits++;
+        P.sqBits = bits;
+        P.sqWindow = ints ? (int)(900.0 / (2.0 * pmax)) : 0;
     }
 };
 

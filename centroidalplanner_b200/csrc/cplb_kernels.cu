@@ -194,10 +194,10 @@ struct TileEmitter {
     __device__ __forceinline__ void grad(int col, double v) const { gradp[col] = v; }
 };
 
-// shared memory per warp (doubles): [x: T*n][g: T*m][jac: T*nnz][grad: T*n][cost: T] + one mbarrier
+// shared memory per warp (doubles): [x0: T*n][x1: T*n][g: T*m][jac: T*nnz][grad: T*n][cost: T]; then 2 mbarriers per warp
 __host__ __device__ inline size_t tile_doubles(int T, int n, int m, int nnz, unsigned flags)
 {
-    size_t d = (size_t)T * n;
+    size_t d = 2 * (size_t)T * n;
     if (flags & CPLB_WANT_G) d += (size_t)T * m;
     if (flags & CPLB_WANT_J) d += (size_t)T * nnz;
     if (flags & CPLB_WANT_GRAD) d += (size_t)T * n;
@@ -211,22 +211,32 @@ __device__ __forceinline__ void warp_copy(double* dst, const double* src, int co
     for (int e = lane; e < count; e += 32) dst[e] = src[e];
 }
 
-template <int ENV, int LPI, int WARPS>
+// Persistent warps.  Warp w of the grid owns tiles w, w + W, w + 2W, ... (W = warps in the grid, the grid is
+// sized to what is resident at once).  Per tile of T = 32/LPI consecutive instances:
+//   - the x slice (T*n contiguous doubles) arrives by one bulk async copy into one of two buffers; the copy of
+//     the NEXT tile is issued before the current one is consumed, so its HBM latency hides behind compute;
+//   - LPI lanes per instance (one lane per contact; the six statics rows are dealt to the same lanes) scatter
+//     results into shared-memory tiles laid out exactly like the output slices;
+//   - the tiles leave with bulk async stores; the warp only waits for the engine to have READ the tiles
+//     right before it overwrites them with the next tile's results.
+// No block-wide barrier: every warp runs its own pipeline (mbarriers + __syncwarp only).
+template <int ENV, int LPI, int WARPS, unsigned FLAGS>
 __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_constant__ CplbParams P, const CplbIo io,
-                                                                   const unsigned flags, const int aligned16)
+                                                                   const unsigned flags_rt, const int aligned16)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int T = 32 / LPI;  // instances per warp tile
+    const unsigned flags = FLAGS ? FLAGS : flags_rt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nc = P.nc, n = P.n, m = P.m, nnz = P.nnz;
-    const long long tile = (long long)blockIdx.x * WARPS + warp;
-    const long long i0 = tile * T;
-    if (i0 >= io.N) return;  // whole warp leaves together; no block-wide barrier is used below
-    const int cnt = (io.N - i0) < T ? (int)(io.N - i0) : T;
+    const long long tiles = (io.N + T - 1) / T;
+    const long long stride = (long long)gridDim.x * WARPS;
+    long long tile = (long long)blockIdx.x * WARPS + warp;
+    if (tile >= tiles) return;  // whole warp leaves together
 
     const size_t per_warp = tile_doubles(T, n, m, nnz, flags);
-    double* xs = reinterpret_cast<double*>(smem_raw) + (size_t)warp * per_warp;
-    double* cur = xs + (size_t)T * n;
+    double* xbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * per_warp;
+    double* cur = xbuf + 2 * (size_t)T * n;
     double* gs = nullptr;
     double* js = nullptr;
     double* grads = nullptr;
@@ -235,109 +245,134 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
     if (flags & CPLB_WANT_J) { js = cur; cur += (size_t)T * nnz; }
     if (flags & CPLB_WANT_GRAD) { grads = cur; cur += (size_t)T * n; }
     if (flags & CPLB_WANT_COST) { costs = cur; }
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)WARPS * per_warp);
-    uint64_t* bar = bars + warp;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)WARPS * per_warp) + 2 * warp;
 
+    const uint32_t xbytes = (uint32_t)(T * n * sizeof(double));
     // bulk copies need 16-byte aligned addresses and sizes: full tiles of 16B-aligned buffers only
-    const bool bulk = aligned16 && cnt == T;
+    auto is_bulk = [&](long long t) { return aligned16 && (t + 1) * T <= io.N; };
 
-    // ---- fetch the tile's x slice -----------------------------------------------------------
-    const double* xsrc = io.x + i0 * n;
-    if (bulk) {
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            fence_proxy_async_smem();
-            mbar_expect_tx(bar, (uint32_t)(T * n * sizeof(double)));
-            bulk_g2s(xs, xsrc, (uint32_t)(T * n * sizeof(double)), bar);
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_proxy_async_smem();
+        if (is_bulk(tile)) {
+            mbar_expect_tx(&bar[0], xbytes);
+            bulk_g2s(xbuf, io.x + tile * T * n, xbytes, &bar[0]);
         }
-        __syncwarp();
-        mbar_wait(bar, 0);
-    } else {
-        warp_copy(xs, xsrc, cnt * n, lane);
-        __syncwarp();
     }
+    __syncwarp();
 
-    // ---- compute: lane (inst, s) handles contacts s, s+LPI, ... and statics rows s, s+LPI, ... ----
     const int inst = lane / LPI, s = lane % LPI;
-    if (inst < cnt) {
-        const double* xi = xs + (size_t)inst * n;
-        TileEmitter em{gs ? gs + (size_t)inst * m : nullptr, js ? js + (size_t)inst * nnz : nullptr,
-                       grads ? grads + (size_t)inst * n : nullptr};
-        const double c[3] = {xi[0], xi[1], xi[2]};
-        for (int j = s; j < nc; j += LPI) {
-            const int k = P.perm[j];
-            const double* xk = xi + 3 + 9 * k;
-            const double F[3] = {xk[0], xk[1], xk[2]};
-            const double p[3] = {xk[3], xk[4], xk[5]};
-            const double nn[3] = {xk[6], xk[7], xk[8]};
-            contact_rows<ENV>(P, em, nc, j, k, c, F, p, nn, flags);
+    bool stores_in_flight = false;
+    for (int it = 0; tile < tiles; tile += stride, it++) {
+        const int b = it & 1;
+        double* xs = xbuf + (size_t)b * T * n;
+        const long long i0 = tile * T;
+        const int cnt = (io.N - i0) < T ? (int)(io.N - i0) : T;
+        const bool bulk = is_bulk(tile);
+
+        // prefetch the next tile's x into the other buffer (its previous contents were consumed an iteration ago)
+        const long long next = tile + stride;
+        if (lane == 0 && next < tiles && is_bulk(next)) {
+            fence_proxy_async_smem();
+            mbar_expect_tx(&bar[b ^ 1], xbytes);
+            bulk_g2s(xbuf + (size_t)(b ^ 1) * T * n, io.x + next * T * n, xbytes, &bar[b ^ 1]);
         }
-        // CentroidalStatics rows: row r's running sum visits the contacts in sorted-name order
-        // (CentroidalStatics.cpp:44-54); the six rows are independent, so they are dealt to the lanes.
-        if (flags & (CPLB_WANT_G | CPLB_WANT_J)) {
-            const int L = jac_moment_row_len(nc);
-            for (int r = s; r < 6; r += LPI) {
-                double v = 0.0, a = 0.0, b = 0.0;
-                for (int j = 0; j < nc; j++) {
-                    const double* xk = xi + 3 + 9 * P.perm[j];
-                    const double F0 = xk[0], F1 = xk[1], F2 = xk[2];
-                    const double d0 = xk[3] - c[0], d1 = xk[4] - c[1], d2 = xk[5] - c[2];
-                    switch (r) {
-                    case 0: v += F0; break;
-                    case 1: v += F1; break;
-                    case 2: v += F2; break;
-                    case 3: v += d1 * F2 - d2 * F1; a -= F2; b -= -F1; break;   // :128-129
-                    case 4: v += d2 * F0 - d0 * F2; a -= -F2; b -= F0; break;   // :130-131
-                    default: v += d0 * F1 - d1 * F0; a -= F1; b -= -F0; break;  // :132-133
+        if (bulk) {
+            mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
+        } else {
+            warp_copy(xs, io.x + i0 * n, cnt * n, lane);
+        }
+        // the output tiles are about to be overwritten: the engine must have finished reading the previous ones
+        if (stores_in_flight) {
+            if (lane == 0) bulk_wait_read_all();
+            stores_in_flight = false;
+        }
+        __syncwarp();
+
+        // ---- compute: lane (inst, s) handles contacts s, s+LPI, ... and statics rows s, s+LPI, ... ----
+        if (inst < cnt) {
+            const double* xi = xs + (size_t)inst * n;
+            TileEmitter em{gs ? gs + (size_t)inst * m : nullptr, js ? js + (size_t)inst * nnz : nullptr,
+                           grads ? grads + (size_t)inst * n : nullptr};
+            const double c[3] = {xi[0], xi[1], xi[2]};
+            for (int j = s; j < nc; j += LPI) {
+                const int k = P.perm[j];
+                const double* xk = xi + 3 + 9 * k;
+                const double F[3] = {xk[0], xk[1], xk[2]};
+                const double p[3] = {xk[3], xk[4], xk[5]};
+                const double nn[3] = {xk[6], xk[7], xk[8]};
+                contact_rows<ENV>(P, em, nc, j, k, c, F, p, nn, flags);
+            }
+            // CentroidalStatics rows: row r's running sum visits the contacts in sorted-name order
+            // (CentroidalStatics.cpp:44-54); the six rows are independent, so they are dealt to the lanes.
+            if (flags & (CPLB_WANT_G | CPLB_WANT_J)) {
+                const int L = jac_moment_row_len(nc);
+                for (int r = s; r < 6; r += LPI) {
+                    double v = 0.0, a = 0.0, bb = 0.0;
+                    for (int j = 0; j < nc; j++) {
+                        const double* xk = xi + 3 + 9 * P.perm[j];
+                        const double F0 = xk[0], F1 = xk[1], F2 = xk[2];
+                        const double d0 = xk[3] - c[0], d1 = xk[4] - c[1], d2 = xk[5] - c[2];
+                        switch (r) {
+                        case 0: v += F0; break;
+                        case 1: v += F1; break;
+                        case 2: v += F2; break;
+                        case 3: v += d1 * F2 - d2 * F1; a -= F2; bb -= -F1; break;   // :128-129
+                        case 4: v += d2 * F0 - d0 * F2; a -= -F2; bb -= F0; break;   // :130-131
+                        default: v += d0 * F1 - d1 * F0; a -= F1; bb -= -F0; break;  // :132-133
+                        }
+                    }
+                    if (flags & CPLB_WANT_G) em.g(r, r < 3 ? (v - P.wrench[r]) + P.mg[r] : v - P.wrench[r]);
+                    if ((flags & CPLB_WANT_J) && r >= 3) {
+                        em.j(3 * nc + (r - 3) * L + 0, a);
+                        em.j(3 * nc + (r - 3) * L + 1, bb);
                     }
                 }
-                if (flags & CPLB_WANT_G) em.g(r, r < 3 ? (v - P.wrench[r]) + P.mg[r] : v - P.wrench[r]);
-                if ((flags & CPLB_WANT_J) && r >= 3) {
-                    em.j(3 * nc + (r - 3) * L + 0, a);
-                    em.j(3 * nc + (r - 3) * L + 1, b);
-                }
             }
-        }
-        if (s == 0) {
-            if (flags & CPLB_WANT_COST) {  // MinimizeCentroidalVariables.cpp:126-147, sorted order
-                double cost = 0.0;
-                for (int j = 0; j < nc; j++) {
-                    const int k = P.perm[j];
-                    const double* xk = xi + 3 + 9 * k;
-                    const double F[3] = {xk[0], xk[1], xk[2]};
-                    const double p[3] = {xk[3], xk[4], xk[5]};
-                    cost += contact_cost(P, k, F, p);
+            if (s == 0) {
+                if (flags & CPLB_WANT_COST) {  // MinimizeCentroidalVariables.cpp:126-147, sorted order
+                    double cost = 0.0;
+                    for (int j = 0; j < nc; j++) {
+                        const int k = P.perm[j];
+                        const double* xk = xi + 3 + 9 * k;
+                        const double F[3] = {xk[0], xk[1], xk[2]};
+                        const double p[3] = {xk[3], xk[4], xk[5]};
+                        cost += contact_cost(P, k, F, p);
+                    }
+                    cost += com_cost(P, c);
+                    costs[inst] = cost;
                 }
-                cost += com_cost(P, c);
-                costs[inst] = cost;
-            }
-            if (flags & CPLB_WANT_GRAD) {
+                if (flags & CPLB_WANT_GRAD) {
 #pragma unroll
-                for (int q = 0; q < 3; q++) em.grad(q, P.W_com * (c[q] - P.com_ref[q]));
+                    for (int q = 0; q < 3; q++) em.grad(q, P.W_com * (c[q] - P.com_ref[q]));
+                }
             }
         }
-    }
 
-    // ---- ship the tiles ------------------------------------------------------------------------
-    if (bulk) {
-        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the async (TMA) proxy
-        __syncwarp();
-        if (lane == 0) {
-            if (gs) bulk_s2g(io.g + i0 * m, gs, (uint32_t)(T * m * sizeof(double)));
-            if (js) bulk_s2g(io.jac + i0 * nnz, js, (uint32_t)(T * nnz * sizeof(double)));
-            if (grads) bulk_s2g(io.grad + i0 * n, grads, (uint32_t)(T * n * sizeof(double)));
-            bulk_commit();
+        // ---- ship the tiles ------------------------------------------------------------------------
+        if (bulk) {
+            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the async (TMA) proxy
+            __syncwarp();
+            if (lane == 0) {
+                if (gs) bulk_s2g(io.g + i0 * m, gs, (uint32_t)(T * m * sizeof(double)));
+                if (js) bulk_s2g(io.jac + i0 * nnz, js, (uint32_t)(T * nnz * sizeof(double)));
+                if (grads) bulk_s2g(io.grad + i0 * n, grads, (uint32_t)(T * n * sizeof(double)));
+                bulk_commit();
+            }
+            stores_in_flight = true;
+            if (costs && lane < T) io.cost[i0 + lane] = costs[lane];
+        } else {
+            __syncwarp();
+            if (gs) warp_copy(io.g + i0 * m, gs, cnt * m, lane);
+            if (js) warp_copy(io.jac + i0 * nnz, js, cnt * nnz, lane);
+            if (grads) warp_copy(io.grad + i0 * n, grads, cnt * n, lane);
+            if (costs && lane < cnt) io.cost[i0 + lane] = costs[lane];
         }
-        if (costs && lane < T) io.cost[i0 + lane] = costs[lane];
-        if (lane == 0) bulk_wait_read_all();  // shared memory must outlive the engine's reads
-        __syncwarp();
-    } else {
-        __syncwarp();
-        if (gs) warp_copy(io.g + i0 * m, gs, cnt * m, lane);
-        if (js) warp_copy(io.jac + i0 * nnz, js, cnt * nnz, lane);
-        if (grads) warp_copy(io.grad + i0 * n, grads, cnt * n, lane);
-        if (costs && lane < cnt) io.cost[i0 + lane] = costs[lane];
+        __syncwarp();  // all lanes done with xs and the tiles before the next iteration touches them
     }
+    if (stores_in_flight && lane == 0) bulk_wait_read_all();  // shared memory must outlive the engine's reads
+    __syncwarp();
 }
 
 // ================================================================================================
@@ -373,21 +408,50 @@ cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsign
     }
 }
 
-template <int ENV, int LPI>
-static cudaError_t launch_im_cfg(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
+template <int ENV, int LPI, int WARPS, unsigned FLAGS>
+static cudaError_t launch_im_kernel(const CplbParams& P, const CplbIo& io, unsigned flags, size_t smem, cudaStream_t st)
 {
-    constexpr int WARPS = 4;
     constexpr int T = 32 / LPI;
-    const size_t smem = tile_doubles(T, P.n, P.m, P.nnz, flags) * sizeof(double) * WARPS + WARPS * sizeof(uint64_t);
-    auto kern = eval_instance_major<ENV, LPI, WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = eval_instance_major<ENV, LPI, WARPS, FLAGS>;
+    // resident CTAs per SM and the SM count are fixed per (kernel, smem, device): looked up once
+    struct Cfg { int device = -1; size_t smem = 0; int resident = 0; };
+    static thread_local Cfg cfg;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    if (cfg.device != dev || cfg.smem != smem) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        cfg.device = dev;
+        cfg.smem = smem;
+        cfg.resident = (per_sm > 0 ? per_sm : 1) * sms;
+    }
     const long long tiles = (io.N + T - 1) / T;
-    const unsigned blocks = (unsigned)((tiles + WARPS - 1) / WARPS);
+    const long long want = (tiles + WARPS - 1) / WARPS;
+    const unsigned blocks = (unsigned)(want < cfg.resident ? want : cfg.resident);
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const int aligned16 = al16(io.x) && al16(io.g) && al16(io.jac) && al16(io.grad) && (T % 2 == 0);
     kern<<<blocks, WARPS * 32, smem, st>>>(P, io, flags, aligned16);
     return cudaGetLastError();
+}
+
+template <int ENV, int LPI>
+static cudaError_t launch_im_cfg(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
+{
+    constexpr int T = 32 / LPI;
+    const size_t per_warp = tile_doubles(T, P.n, P.m, P.nnz, flags) * sizeof(double) + 2 * sizeof(uint64_t);
+    const unsigned gj = CPLB_WANT_G | CPLB_WANT_J;
+    if (4 * per_warp <= 72 * 1024) {  // the common shapes: 4 warps per CTA, 3 CTAs per SM
+        if (flags == gj) return launch_im_kernel<ENV, LPI, 4, gj>(P, io, flags, 4 * per_warp, st);
+        return launch_im_kernel<ENV, LPI, 4, 0u>(P, io, flags, 4 * per_warp, st);
+    }
+    if (per_warp > 227 * 1024) return cudaErrorInvalidConfiguration;
+    return launch_im_kernel<ENV, LPI, 1, 0u>(P, io, flags, per_warp, st);  // many contacts: one warp per CTA
 }
 
 template <int ENV>

@@ -93,6 +93,7 @@ class Oracle:
         lib().cpl_oracle_dims(self._h, C.byref(n), C.byref(m), C.byref(nnz))
         self.n, self.m, self.nnz = n.value, m.value, nnz.value
         self.env_kind = int(env_kind)
+        self.sq = (np.array([0.0, 0.0, 10.0]), np.array([10.0] * 3), np.array([10.0] * 3))  # Superquadric.cpp:7-9
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -140,6 +141,7 @@ class Oracle:
         lib().cpl_oracle_set_ground_z(self._h, float(z))
 
     def set_superquadric(self, Cc, R, P):
+        self.sq = (_vec(Cc, 3).copy(), _vec(R, 3).copy(), _vec(P, 3).copy())
         lib().cpl_oracle_set_superquadric(self._h, _dp(_vec(Cc, 3)), _dp(_vec(R, 3)), _dp(_vec(P, 3)))
 
     def set_force_threshold(self, name, thr):

@@ -31,7 +31,7 @@ def test_all_outputs_match_oracle(case, layout, cuda_device):
     x = gen(1000)
     want = o.eval_batch(x, nthreads=4)
     got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
-    assert_parity(got, want, o, f"{case}/layout{layout}")
+    assert_parity(got, want, o, f"{case}/layout{layout}", x)
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
@@ -42,7 +42,7 @@ def test_ragged_batch_sizes(N, layout, cuda_device):
         x = gen(N)
         want = o.eval_batch(x)
         got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
-        assert_parity(got, want, o, f"{case}/N{N}/layout{layout}")
+        assert_parity(got, want, o, f"{case}/N{N}/layout{layout}", x)
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
@@ -57,7 +57,7 @@ def test_output_subsets_do_not_touch_other_buffers(want, layout, cuda_device):
         if not want.get(k, False):
             assert got[k] is None
             ref[k] = None
-    assert_parity(got, ref, o, f"subset{want}/layout{layout}")
+    assert_parity(got, ref, o, f"subset{want}/layout{layout}", x)
 
 
 def test_default_start_point_nan_pattern(cuda_device):
@@ -69,7 +69,7 @@ def test_default_start_point_nan_pattern(cuda_device):
         assert np.isnan(want["jac"]).any()
         for layout in LAYOUTS:
             got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
-            assert_parity(got, want, o, f"{case}/zeros/layout{layout}")
+            assert_parity(got, want, o, f"{case}/zeros/layout{layout}", x)
 
 
 def test_equilibrium_point_and_special_values(cuda_device):
@@ -92,6 +92,28 @@ def test_equilibrium_point_and_special_values(cuda_device):
     for layout in LAYOUTS:
         got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
         assert_parity(got, want, o, f"special/layout{layout}")
+
+
+def test_superquadric_outside_the_fast_power_window(cuda_device):
+    """Contacts absurdly close to / far from the superquadric centre leave the integer-power fast path
+    (cplb_device.cuh); zero offsets hit the reference's own 1/(p-C)^2 poles."""
+    prob, o, gen = make_pair("superquadric4")
+    x = gen(256)
+    C = np.array([0.0, 0.0, 1.0])
+    x[0, 6:9] = C + [1e-20, 2e-25, -3e-18]
+    x[1, 6:9] = C + [1e15, -1e14, 1e16]
+    x[2, 6:9] = C + [0.0, 0.1, 0.2]        # d_x = 0: inf * 0 in the diagonal entries
+    x[3, 6:9] = C                          # all three zero
+    x[4, 15:18] = C + [1e-3, 1e-2, -1e-2]
+    x[5, 15:18] = [np.inf, 0.0, 1.5]
+    x[6, 15:18] = [np.nan, 0.2, 1.2]
+    x[7, 24:27] = C + [-1e-8, 1e-8, 1e-8]
+    want = o.eval_batch(x)
+    for layout in LAYOUTS:
+        got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
+        # rows 0, 1, 7: d so small/large that d^(2P) and the 1/(p-C)^2 factors over/underflow -- the reference itself
+        # returns 0/inf/NaN mixtures there; positions of non-finite values must agree, finite values to 1e-12
+        assert_parity(got, want, o, f"sq-window/layout{layout}", x)
 
 
 def test_parameter_updates_are_seen_by_the_next_launch(cuda_device):
@@ -145,7 +167,7 @@ def test_full_size_configs(case, N, cuda_device):
     want = o.eval_batch(x[sub], want=("g", "jac"), nthreads=4)
     got = {"g": a["g"][torch.from_numpy(sub).to(cuda_device)].cpu().numpy(),
            "jac": a["jac"][torch.from_numpy(sub).to(cuda_device)].cpu().numpy()}
-    assert_parity(got, want, o, f"{case}/full")
+    assert_parity(got, want, o, f"{case}/full", x[sub])
     # size-independent property: the force-balance Jacobian rows are all 1.0 and row r of g equals
     # Sigma_k F_k[r] - w[r] + m g[r] up to summation-order rounding
     nc = o.nc
