@@ -229,70 +229,95 @@ def run_ours(args):
     layout = cpl.INSTANCE_MAJOR if args.layout == "instance" else cpl.COMPONENT_MAJOR
 
     x_host = make_inputs(rank)
+    stream = torch.cuda.current_stream(dev)
+    W, K = max(3, args.warmup), args.steps
     # buffer sets: total footprint >> L2 so no step finds its lines in L2
     sets = max(4, int(np.ceil(8 * L2_BYTES / bytes_per_launch)))
-    xs, gs, js = [], [], []
-    shape = (lambda length: (N, length)) if layout == cpl.INSTANCE_MAJOR else (lambda length: (length, N))
-    base = torch.from_numpy(x_host if layout == cpl.INSTANCE_MAJOR else np.ascontiguousarray(x_host.T)).to(dev)
-    for s in range(sets):
-        xs.append(base.clone())
-        gs.append(torch.empty(shape(m), dtype=torch.float64, device=dev))
-        js.append(torch.empty(shape(nnz), dtype=torch.float64, device=dev))
-    stream = torch.cuda.current_stream(dev)
-
-    def step(i):
-        s = i % sets
-        prob.eval(xs[s], g=True, jac=True, layout=layout, out={"g": gs[s], "jac": js[s]})
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def time_layout(lay):
+        """W warm-up + K timed back-to-back evaluations in one buffer layout; returns (ms_per_step, launches, ...)."""
+        shp = (lambda length: (N, length)) if lay == cpl.INSTANCE_MAJOR else (lambda length: (length, N))
+        base = torch.from_numpy(x_host if lay == cpl.INSTANCE_MAJOR else np.ascontiguousarray(x_host.T)).to(dev)
+        xs = [base.clone() for _ in range(sets)]
+        gs = [torch.empty(shp(m), dtype=torch.float64, device=dev) for _ in range(sets)]
+        js = [torch.empty(shp(nnz), dtype=torch.float64, device=dev) for _ in range(sets)]
+
+        def step(i):
+            s = i % sets
+            prob.eval(xs[s], g=True, jac=True, layout=lay, out={"g": gs[s], "jac": js[s]})
+
+        for i in range(W):
+            step(i)
+        barrier()
+        # The K timed steps are issued as replays of a CUDA graph holding one rotation over the buffer sets
+        # (`sets` evaluation kernels, captured from the same cplb_eval_device calls) plus a plain-launch remainder:
+        # at ~20 us per kernel the per-launch host path and inter-kernel launch gap would otherwise be >10% of the step.
+        graph = None
+        if not args.no_graph and K >= sets:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    for i in range(sets):
+                        step(W + i)
+            stream.wait_stream(side)
+            graph.replay()  # one untimed replay (upload / first-run cost)
+            barrier()
+        reps, rem = (K // sets, K % sets) if graph is not None else (0, K)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            graph.replay()
+        for i in range(rem):
+            step(W + i)
+        e1.record(stream)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        n_launch = reps * sets + rem  # evaluation kernels executed inside the timed region
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # per-launch device time with an event pair around every launch (same stream), second pass
+        prob.timing_begin()
+        for i in range(min(K, 200)):
+            step(W + K + i)
+        torch.cuda.synchronize(dev)
+        ev_ms, ev_k = prob.timing_end()
+        del xs, gs, js
+        return float(t.item()) / K, n_launch, ev_ms, ev_k
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
 
-    W, K = max(3, args.warmup), args.steps
-    for i in range(W):
-        step(i)
-    barrier()
-    launches0 = prob.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(K):
-        step(W + i)
-    e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = prob.launch_count() - launches0
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / K
+    ms_per_step, launches, ev_ms, ev_k = time_layout(layout)
+    other = cpl.COMPONENT_MAJOR if layout == cpl.INSTANCE_MAJOR else cpl.INSTANCE_MAJOR
+    other_ms, _, other_ev_ms, _ = time_layout(other)
     value = world * N / (ms_per_step * 1e-3)
-
-    # per-launch device time with an event pair around every launch (same stream), second pass
-    prob.timing_begin()
-    for i in range(min(K, 200)):
-        step(W + K + i)
-    torch.cuda.synchronize(dev)
-    ev_ms, ev_k = prob.timing_end()
+    lname = {cpl.INSTANCE_MAJOR: "instance-major", cpl.COMPONENT_MAJOR: "component-major"}
+    kname = {cpl.INSTANCE_MAJOR: "eval_instance_major", cpl.COMPONENT_MAJOR: "eval_component_major_split"}
+    shape = (lambda length: (N, length))  # the e2e leg below uses instance-major host buffers
 
     # ---- e2e: host buffers through cplb_eval_host -------------------------------------------
     lib = _cabi.load()
     hx, px = pinned_array(lib, shape(n))
     hg, pg = pinned_array(lib, shape(m))
     hj, pj = pinned_array(lib, shape(nnz))
-    hx[...] = x_host if layout == cpl.INSTANCE_MAJOR else x_host.T
+    hx[...] = x_host
     e2e_steps = max(3, min(K, 20))
+    e2e_layout = cpl.INSTANCE_MAJOR  # what an IPOPT thread consumes: its instance's x[n] -> g[m], values[nnz] slices
     for _ in range(2):
-        prob.eval(hx, g=True, jac=True, layout=layout, out={"g": hg, "jac": hj})
+        prob.eval(hx, g=True, jac=True, layout=e2e_layout, out={"g": hg, "jac": hj})
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        prob.eval(hx, g=True, jac=True, layout=layout, out={"g": hg, "jac": hj})  # synchronous: outputs landed
+        prob.eval(hx, g=True, jac=True, layout=e2e_layout, out={"g": hg, "jac": hj})  # synchronous: outputs landed
     torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -311,17 +336,22 @@ def run_ours(args):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "num_contacts": NC, "env": "Ground", "instances_per_gpu": N,
-                       "layout": "instance-major" if layout == cpl.INSTANCE_MAJOR else "component-major",
+                       "layout": lname[layout],
                        "outputs": "g+jac", "params": "shared",
+                       "launch": "plain launches" if args.no_graph or K < sets else f"CUDA graph of {sets} evaluation kernels replayed {K // sets}x + {K % sets} plain launches",
                        "l2": f"inputs larger than L2: steps rotate through {sets} buffer sets, {sets * bytes_per_launch / 2**20:.0f} MiB total vs 126 MiB L2"},
             "e2e": {"value": world * N / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": 8 * n * N,
                     "d2h_bytes_per_step": 8 * (m + nnz) * N, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s,
-                    "api": "cplb_eval_host (pinned host buffers; chunked H2D/kernel/D2H on 3 streams)", "checksum": e2e_check},
+                    "api": "cplb_eval_host, instance-major pinned host buffers; chunked H2D/kernel/D2H on 3 streams",
+                    "checksum": e2e_check},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
-                         "kernel": "eval_instance_major" if layout == cpl.INSTANCE_MAJOR else "eval_component_major",
+                         "kernel": kname[layout],
                          "avg_launch_ms": ms_per_step, "avg_launch_ms_event_pairs": ev_ms, "event_pair_launches": ev_k},
+            "other_layout": {"layout": lname[other], "kernel": kname[other], "ms_per_step": other_ms,
+                             "value": world * N / (other_ms * 1e-3), "roofline_frac": bytes_per_launch / (other_ms * 1e-3) / 1e9 / peak,
+                             "avg_launch_ms_event_pairs": other_ev_ms},
             "clocks": clocks,
         }
         traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
@@ -355,8 +385,10 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--layout", default="instance", choices=["instance", "component"])
+    ap.add_argument("--layout", default="component", choices=["instance", "component"],
+                    help="buffer layout of the headline number (the other one is timed too and reported under other_layout)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="issue every timed step as a separate launch instead of CUDA-graph replays")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     if args.impl == "reference":
