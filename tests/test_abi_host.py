@@ -56,6 +56,20 @@ def test_layout_matches_oracle_structure(case):
     assert np.array_equal(lb, lbo) and np.array_equal(ub, ubo)
 
 
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_layout_matches_reference_golden_structure(case):
+    """(iRow, jCol) and bounds as the reference's own CplProblem + ifopt-style assembly report them
+    (tests/golden/ref_vectors.npz, tools/make_golden.py)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"))
+    prob, _, _ = make_pair(case)
+    r, c = prob.GetJacobianStructure()
+    assert np.array_equal(r, z[f"{case}/iRow"]) and np.array_equal(c, z[f"{case}/jCol"])
+    gl, gu = prob.GetBoundsOnConstraints()
+    xl, xu = prob.GetBoundsOnOptimizationVariables()
+    assert np.array_equal(gl, z[f"{case}/gl"]) and np.array_equal(gu, z[f"{case}/gu"])
+    assert np.array_equal(xl, z[f"{case}/xl"]) and np.array_equal(xu, z[f"{case}/xu"])
+
+
 def test_block_columns_and_contact_rows():
     prob = cpl.BatchedCplProblem(["r_foot", "l_foot", "r_hand", "l_hand"], 100.0, cpl.Ground())
     assert prob.GetBlockColumn(cpl.BLOCK_COM) == 0

@@ -35,6 +35,22 @@ def test_all_outputs_match_oracle(case, layout, cuda_device):
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_gpu_matches_reference_golden_vectors(case, layout, cuda_device):
+    """tests/golden/ref_vectors.npz: outputs of the reference's own sources (tools/make_golden.py)."""
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz"))
+    prob, o, _ = make_pair(case)
+    x = z[f"{case}/x"]
+    want = {k: z[f"{case}/{k}"] for k in ("g", "jac", "cost", "grad")}
+    got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
+    assert_parity(got, want, o, f"golden/{case}/layout{layout}", x)
+    r, c = prob.GetJacobianStructure()
+    assert np.array_equal(r, z[f"{case}/iRow"]) and np.array_equal(c, z[f"{case}/jCol"])
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("N", [1, 2, 7, 31, 33, 129, 4097])
 def test_ragged_batch_sizes(N, layout, cuda_device):
     for case in ("ground4", "superquadric3", "noenv8"):
