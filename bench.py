@@ -340,8 +340,8 @@ def run_ours(args):
                        "outputs": "g+jac", "params": "shared",
                        "launch": "plain launches" if args.no_graph or K < sets else f"CUDA graph of {sets} evaluation kernels replayed {K // sets}x + {K % sets} plain launches",
                        "l2": f"inputs larger than L2: steps rotate through {sets} buffer sets, {sets * bytes_per_launch / 2**20:.0f} MiB total vs 126 MiB L2"},
-            "e2e": {"value": world * N / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": 8 * n * N,
-                    "d2h_bytes_per_step": 8 * (m + nnz) * N, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s,
+            "e2e": {"value": world * N / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": world * 8 * n * N,
+                    "d2h_bytes_per_step": world * 8 * (m + nnz) * N, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s,
                     "api": "cplb_eval_host, instance-major pinned host buffers; chunked H2D/kernel/D2H on 3 streams",
                     "checksum": e2e_check},
             "gpu_launches": int(launches),

@@ -121,7 +121,7 @@ struct cplb_problem {
         }
         for (int q = 0; q < 3; q++) P.sqIntP[q] = ints ? (int)sqP[q] : 0;
         int bits = 0;
-        for (int e = ints ? 2 * (int)pmax : 0; e > 0; e >>= 1) bits++;
+        for (int e = ints ? (int)pmax - 2 : 0; e > 0; e >>= 1) bits++;  // largest chain exponent is P - 2
         P.sqBits = bits;
         P.sqWindow = ints ? (int)(900.0 / (2.0 * pmax)) : 0;
     }

@@ -36,7 +36,7 @@ struct CplbParams {
     double sqRm2P[3];     // pow(R, -(P*2.0))       :82,86,107,...
     double sqR2P[3];      // pow(R,  P*2.0)         :95,96,149,150,203,204
     int32_t sqIntP[3];    // P as an integer when all three curvatures are integers in [2, 63], else 0
-    int32_t sqBits;       // squarings needed: bit length of max(2P)
+    int32_t sqBits;       // chain length: bit length of max(P) - 2
     int32_t sqWindow;     // |binary exponent of d| <= window keeps d^(2P) a normal number
     int32_t pad1;
     double F_thr[CPLB_KMAX_CONTACTS];
