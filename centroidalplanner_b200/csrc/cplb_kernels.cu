@@ -306,27 +306,33 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
             }
             // CentroidalStatics rows: row r's running sum visits the contacts in sorted-name order
             // (CentroidalStatics.cpp:44-54); the six rows are independent, so they are dealt to the lanes.
+            // Lanes of a warp hold different r, so the row is selected by indices, not by a switch: row 3+q is
+            //   v += d_{q+1} F_{q+2} - d_{q+2} F_{q+1}   [(p - CoM) x F]
+            // and its CoM block is  a -= sa*F[ia],  b -= sb*F[ib]  (:128-133; multiplying by +-1 is exact).
             if (flags & (CPLB_WANT_G | CPLB_WANT_J)) {
                 const int L = jac_moment_row_len(nc);
                 for (int r = s; r < 6; r += LPI) {
+                    const bool mom = r >= 3;
+                    const int q = mom ? r - 3 : 0;
+                    const int i1 = q == 2 ? 0 : q + 1, i2 = q == 0 ? 2 : q - 1;  // (q+1)%3, (q+2)%3
+                    const int ia = q == 2 ? 1 : 2, ib = q == 0 ? 1 : 0;
+                    const double sa = q == 1 ? -1.0 : 1.0, sb = q == 1 ? 1.0 : -1.0;
                     double v = 0.0, a = 0.0, bb = 0.0;
                     for (int j = 0; j < nc; j++) {
                         const double* xk = xi + 3 + 9 * P.perm[j];
-                        const double F0 = xk[0], F1 = xk[1], F2 = xk[2];
-                        const double d0 = xk[3] - c[0], d1 = xk[4] - c[1], d2 = xk[5] - c[2];
-                        switch (r) {
-                        case 0: v += F0; break;
-                        case 1: v += F1; break;
-                        case 2: v += F2; break;
-                        case 3: v += d1 * F2 - d2 * F1; a -= F2; bb -= -F1; break;   // :128-129
-                        case 4: v += d2 * F0 - d0 * F2; a -= -F2; bb -= F0; break;   // :130-131
-                        default: v += d0 * F1 - d1 * F0; a -= F1; bb -= -F0; break;  // :132-133
+                        if (mom) {
+                            const double x1 = xk[3 + i1] - xi[i1], x2 = xk[3 + i2] - xi[i2];  // p - CoM
+                            v += x1 * xk[i2] - x2 * xk[i1];
+                            a -= sa * xk[ia];
+                            bb -= sb * xk[ib];
+                        } else {
+                            v += xk[r];
                         }
                     }
-                    if (flags & CPLB_WANT_G) em.g(r, r < 3 ? (v - P.wrench[r]) + P.mg[r] : v - P.wrench[r]);
-                    if ((flags & CPLB_WANT_J) && r >= 3) {
-                        em.j(3 * nc + (r - 3) * L + 0, a);
-                        em.j(3 * nc + (r - 3) * L + 1, bb);
+                    if (flags & CPLB_WANT_G) em.g(r, mom ? v - P.wrench[r] : (v - P.wrench[r]) + P.mg[r]);
+                    if ((flags & CPLB_WANT_J) && mom) {
+                        em.j(3 * nc + q * L + 0, a);
+                        em.j(3 * nc + q * L + 1, bb);
                     }
                 }
             }
