@@ -76,6 +76,61 @@ def test_output_subsets_do_not_touch_other_buffers(want, layout, cuda_device):
     assert_parity(got, ref, o, f"subset{want}/layout{layout}", x)
 
 
+@pytest.mark.parametrize("G", [1024, 1023])  # 1023: buffers only 8-byte aligned -> the non-bulk (plain load/store) tile path
+@pytest.mark.parametrize("N", [1, 5, 8, 33, 1000, 4099])
+@pytest.mark.parametrize("case", ["ground4", "superquadric3", "noenv8", "ground12"])
+def test_no_write_outside_the_output_slices(case, N, G, cuda_device):
+    """Guard bands (compute-sanitizer is closed on this pool): every output buffer sits inside a larger allocation
+    filled with a sentinel; after the evaluation the bands before/after -- and, component-major, the pitch padding
+    columns ld > N -- must still hold the sentinel, and the payload must equal the oracle."""
+    import ctypes as C
+
+    import torch
+
+    from centroidalplanner_b200 import _cabi
+
+    prob, o, gen = make_pair(case)
+    x = gen(N)
+    want = o.eval_batch(x)
+    SENT = -7.25e77
+    lib = _cabi.load()
+    for layout in LAYOUTS:
+        ld = N if layout == cpl.INSTANCE_MAJOR else N + 37
+        def make(length):
+            count = N * length if layout == cpl.INSTANCE_MAJOR else length * ld
+            buf = torch.full((count + 2 * G,), SENT, dtype=torch.float64, device=cuda_device)
+            return buf, buf[G:G + count]
+        bufs = {k: make(L) for k, L in (("g", o.m), ("jac", o.nnz), ("grad", o.n), ("cost", 1))}
+        xfull, xin = make(o.n)
+        if layout == cpl.INSTANCE_MAJOR:
+            xin.copy_(torch.from_numpy(x).reshape(-1))
+        else:
+            xin.view(o.n, ld)[:, :N].copy_(torch.from_numpy(np.ascontiguousarray(x.T)))
+            bufs["cost"] = make(1)  # cost is always cost[i]
+        if layout == cpl.COMPONENT_MAJOR:
+            cbuf = torch.full((N + 2 * G,), SENT, dtype=torch.float64, device=cuda_device)
+            bufs["cost"] = (cbuf, cbuf[G:G + N])
+        args = _cabi.EvalArgs(N, layout, 0, ld, xin.data_ptr(), bufs["g"][1].data_ptr(), bufs["jac"][1].data_ptr(),
+                              bufs["cost"][1].data_ptr(), bufs["grad"][1].data_ptr())
+        assert lib.cplb_eval_device(prob._h, C.byref(args), None) == 0, lib.cplb_last_error()
+        torch.cuda.synchronize()
+        got = {}
+        for k, L in (("g", o.m), ("jac", o.nnz), ("grad", o.n)):
+            full, view = bufs[k]
+            assert bool((full[:G] == SENT).all()) and bool((full[-G:] == SENT).all()), f"{case}/{k}: guard band overwritten"
+            if layout == cpl.INSTANCE_MAJOR:
+                got[k] = view.view(N, L).cpu().numpy()
+            else:
+                v2 = view.view(L, ld)
+                assert bool((v2[:, N:] == SENT).all()), f"{case}/{k}: pitch padding overwritten"
+                got[k] = v2[:, :N].t().contiguous().cpu().numpy()
+        full, view = bufs["cost"]
+        assert bool((full[:G] == SENT).all()) and bool((full[-G:] == SENT).all())
+        got["cost"] = view[:N].cpu().numpy()
+        assert bool((xfull[:G] == SENT).all()) and bool((xfull[-G:] == SENT).all())
+        assert_parity(got, want, o, f"guard/{case}/N{N}/layout{layout}", x)
+
+
 def test_default_start_point_nan_pattern(cuda_device):
     """x = 0 (Variable3D.cpp:8-10): NaN exactly where the reference produces NaN."""
     for case in ("ground4", "noenv4", "superquadric4"):
