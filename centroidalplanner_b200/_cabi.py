@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcplb.so")
 OK, INVALID_ARGUMENT, OUT_OF_RANGE, RUNTIME_ERROR, CUDA_ERROR, NULL_POINTER = range(6)
 ENV_NONE, ENV_GROUND, ENV_SUPERQUADRIC = 0, 1, 2
 INSTANCE_MAJOR, COMPONENT_MAJOR = 0, 1
+HOST_JAC_CONSTANTS_PRESENT = 1
 BLOCK_COM, BLOCK_FORCE, BLOCK_POSITION, BLOCK_NORMAL = 0, 1, 2, 3
 
 dp = C.POINTER(C.c_double)
@@ -24,7 +25,7 @@ class EvalArgs(C.Structure):
     _fields_ = [
         ("num_instances", C.c_int64),
         ("layout", C.c_int32),
-        ("reserved", C.c_int32),
+        ("host_flags", C.c_int32),
         ("ld", C.c_int64),
         ("x", C.c_void_p),
         ("g", C.c_void_p),
@@ -45,6 +46,8 @@ PROTOTYPES = {
     "cplb_get_sorted_order": (C.c_int, [C.c_void_p, ip]),
     "cplb_get_block_column": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, ip]),
     "cplb_get_contact_row": (C.c_int, [C.c_void_p, C.c_char_p, ip]),
+    "cplb_get_jacobian_constants": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8), dp]),
+    "cplb_fill_jacobian_constants": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, dp]),
     "cplb_get_variable_bounds": (C.c_int, [C.c_void_p, dp, dp]),
     "cplb_get_constraint_bounds": (C.c_int, [C.c_void_p, dp, dp]),
     "cplb_set_mass": (C.c_int, [C.c_void_p, C.c_double]),

@@ -19,6 +19,10 @@ struct Layout {
     std::vector<int32_t> perm;      // sorted-name rank -> index in the caller's vector
     std::vector<int32_t> rank;      // index in the caller's vector -> sorted-name rank
     std::vector<int32_t> iRow, jCol;
+    std::vector<uint8_t> is_const;  // slot value independent of x (ground == true adds Ground's constants)
+    std::vector<double> const_value;
+    struct Run { int begin, end; };  // [begin, end) runs of x-dependent slots
+    std::vector<Run> var_runs;
 
     static int col_com() { return 0; }
     static int col_F(int k) { return 3 + 9 * k; }  // AddVariableSet order: F_, p_, n_ per name (CplProblem.cpp:31-33)
@@ -27,7 +31,7 @@ struct Layout {
     int rows_per_contact() const { return has_env ? 6 : 2; }
     int contact_row(int sorted_rank) const { return 6 + rows_per_contact() * sorted_rank; }
 
-    void build(const std::vector<std::string>& names, bool env_present)
+    void build(const std::vector<std::string>& names, bool env_present, bool ground = false)
     {
         nc = (int)names.size();
         has_env = env_present;
@@ -42,13 +46,17 @@ struct Layout {
 
         iRow.clear();
         jCol.clear();
-        auto put = [&](int r, int c) {
+        is_const.clear();
+        const_value.clear();
+        auto put = [&](int r, int c, bool constant = false, double value = 0.0) {
             iRow.push_back(r);
             jCol.push_back(c);
+            is_const.push_back(constant ? 1 : 0);
+            const_value.push_back(value);
         };
         // CentroidalStatics rows 0..2: identity on every F block (CentroidalStatics.cpp:93-95)
         for (int r = 0; r < 3; r++)
-            for (int k = 0; k < nc; k++) put(r, col_F(k) + r);
+            for (int k = 0; k < nc; k++) put(r, col_F(k) + r, true, 1.0);
         // rows 3..5: the two columns != q of CoM, F_k, p_k (:96-101, :108-113, :128-133)
         for (int q = 0; q < 3; q++) {
             const int c0 = (q == 0) ? 1 : 0, c1 = (q == 2) ? 1 : 2;
@@ -65,11 +73,11 @@ struct Layout {
             const int k = perm[j];
             int row = contact_row(j);
             if (has_env) {
-                for (int c = 0; c < 3; c++) put(row, col_p(k) + c);  // EnvironmentConstraint.cpp:56-58
+                for (int c = 0; c < 3; c++) put(row, col_p(k) + c, ground, c == 2 ? 1.0 : 0.0);  // EnvironmentConstraint.cpp:56-58; Ground.cpp:33-34
                 row++;
                 for (int i = 0; i < 3; i++) {                        // EnvironmentNormal.cpp:66-68, :75-83
-                    for (int c = 0; c < 3; c++) put(row + i, col_p(k) + c);
-                    put(row + i, col_n(k) + i);
+                    for (int c = 0; c < 3; c++) put(row + i, col_p(k) + c, ground, 0.0);  // Ground.cpp:49
+                    put(row + i, col_n(k) + i, true, 1.0);
                 }
                 row += 3;
             }
@@ -79,6 +87,17 @@ struct Layout {
             }
         }
         nnz = (int)iRow.size();
+        var_runs.clear();
+        for (int s = 0; s < nnz;) {
+            if (is_const[s]) {
+                s++;
+                continue;
+            }
+            int e = s;
+            while (e < nnz && !is_const[e]) e++;
+            var_runs.push_back(Run{s, e});
+            s = e;
+        }
     }
 };
 

@@ -317,14 +317,30 @@ class BatchedCplProblem:
     def _shape(self, length, N, layout):
         return (N, length) if layout == _cabi.INSTANCE_MAJOR else (length, N)
 
-    def eval(self, x, g=True, jac=True, cost=False, grad=False, layout=_cabi.INSTANCE_MAJOR, out=None, stream=None):
+    def GetJacobianConstants(self):
+        """(is_constant[nnz] bool, value[nnz]): structural slots whose value does not depend on x."""
+        mask = np.zeros(self.nnz, dtype=np.uint8)
+        val = np.zeros(self.nnz)
+        _check(self._lib.cplb_get_jacobian_constants(self._h, mask.ctypes.data_as(C.POINTER(C.c_uint8)), val.ctypes.data_as(_cabi.dp)))
+        return mask.astype(bool), val
+
+    def FillJacobianConstants(self, jac_host, layout=_cabi.INSTANCE_MAJOR):
+        """Write the constant slots of a host jac buffer once; later host evaluations into the same buffer may then
+        pass jac_constants_present=True and skip transferring them."""
+        a = jac_host.numpy() if _is_torch(jac_host) else jac_host
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+        N = a.shape[0] if layout == _cabi.INSTANCE_MAJOR else a.shape[1]
+        _check(self._lib.cplb_fill_jacobian_constants(self._h, N, layout, N, a.ctypes.data_as(_cabi.dp)))
+
+    def eval(self, x, g=True, jac=True, cost=False, grad=False, layout=_cabi.INSTANCE_MAJOR, out=None, stream=None,
+             jac_constants_present=False):
         """One batched evaluation.  x: (N, n) [instance-major] or (n, N) [component-major], fp64,
         a torch CUDA tensor (device path, asynchronous on the current stream) or a NumPy array /
         CPU tensor (host path through cplb_eval_host).  Returns a dict of outputs of the same kind."""
         out = dict(out or {})
         if _is_torch(x) and x.is_cuda:
             return self._eval_device(x, g, jac, cost, grad, layout, out, stream)
-        return self._eval_host(x, g, jac, cost, grad, layout, out)
+        return self._eval_host(x, g, jac, cost, grad, layout, out, jac_constants_present)
 
     def _eval_device(self, x, g, jac, cost, grad, layout, out, stream):
         import torch
@@ -351,7 +367,7 @@ class BatchedCplProblem:
         _check(self._lib.cplb_eval_device(self._h, C.byref(args), C.c_void_p(s)))
         return res
 
-    def _eval_host(self, x, g, jac, cost, grad, layout, out):
+    def _eval_host(self, x, g, jac, cost, grad, layout, out, jac_constants_present=False):
         is_t = _is_torch(x)
         xa = x.numpy() if is_t else np.asarray(x, dtype=np.float64)
         xa = np.ascontiguousarray(xa)
@@ -370,8 +386,9 @@ class BatchedCplProblem:
 
         res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self.nnz), "cost": buf("cost", cost, None),
                "grad": buf("grad", grad, self.n)}
-        args = _cabi.EvalArgs(N, layout, 0, N, xa.ctypes.data, *[None if res[k] is None else res[k].ctypes.data
-                                                                for k in ("g", "jac", "cost", "grad")])
+        hflags = _cabi.HOST_JAC_CONSTANTS_PRESENT if jac_constants_present else 0
+        args = _cabi.EvalArgs(N, layout, hflags, N, xa.ctypes.data, *[None if res[k] is None else res[k].ctypes.data
+                                                                     for k in ("g", "jac", "cost", "grad")])
         _check(self._lib.cplb_eval_host(self._h, C.byref(args)))
         return res
 

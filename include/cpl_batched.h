@@ -177,10 +177,17 @@ cplb_status cplb_get_contact_force_weight(const cplb_problem *p, const char *con
  * Any of g / jac / cost / grad may be NULL: that output is not computed and not written.
  * Element counts per instance: x n, g m, jac nnz, cost 1, grad n.  `layout`/`ld` apply to every buffer
  * (cost is always cost[i]); ld is ignored for INSTANCE_MAJOR and may be 0 (= num_instances) otherwise. */
+/* cplb_eval_args.host_flags (cplb_eval_host only) */
+#define CPLB_HOST_JAC_CONSTANTS_PRESENT 1 /* the constant slots of the caller's jac buffer already hold their values
+                                             (cplb_fill_jacobian_constants, or an earlier full evaluation into the same
+                                             buffer): the library MAY skip transferring them.  It does for
+                                             COMPONENT_MAJOR (whole rows of the buffer are skipped); for INSTANCE_MAJOR
+                                             whole instance rows travel (measured faster than strided copies) */
+
 typedef struct cplb_eval_args {
     int64_t num_instances;
     int32_t layout; /* cplb_layout */
-    int32_t reserved;
+    int32_t host_flags; /* 0, or CPLB_HOST_* bits; ignored by cplb_eval_device */
     int64_t ld;
     const double *x;
     double *g;
@@ -198,6 +205,17 @@ cplb_status cplb_eval_device(cplb_problem *p, const cplb_eval_args *args, void *
  * run on one of several internal streams so that both copy directions overlap the kernels.  Returns
  * after every output has landed in the host buffers. */
 cplb_status cplb_eval_host(cplb_problem *p, const cplb_eval_args *args);
+
+/* Structural Jacobian slots whose value does not depend on x: the 1.0 identities of CentroidalStatics
+ * (CentroidalStatics.cpp:93-95) and EnvironmentNormal (EnvironmentNormal.cpp:66-68) and, for Ground, its explicit
+ * zeros and the (0,0,1) gradient (Ground.cpp:33-34,49).  IPOPT keeps one values[] array per problem, so a consumer
+ * can fill these once and let every later cplb_eval_host skip them (CPLB_HOST_JAC_CONSTANTS_PRESENT): for a 4-contact
+ * Ground problem 72 of the 174 slots, i.e. 35 % of the device -> host bytes.
+ * is_constant[nnz] (1/0) and value[nnz] (meaningful where is_constant) may each be NULL. */
+cplb_status cplb_get_jacobian_constants(const cplb_problem *p, uint8_t *is_constant, double *value);
+/* Writes the constant slots of a HOST jac buffer holding num_instances instances in the given layout. */
+cplb_status cplb_fill_jacobian_constants(const cplb_problem *p, int64_t num_instances, int32_t layout, int64_t ld,
+                                         double *jac_host);
 
 /* Pinned host memory for cplb_eval_host buffers (cudaHostAlloc / cudaFreeHost). */
 cplb_status cplb_host_alloc(size_t bytes, void **out);

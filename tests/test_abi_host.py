@@ -70,6 +70,32 @@ def test_layout_matches_reference_golden_structure(case):
     assert np.array_equal(xl, z[f"{case}/xl"]) and np.array_equal(xu, z[f"{case}/xu"])
 
 
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_jacobian_constants_are_constant_in_the_oracle(case):
+    """Every slot the product declares constant holds exactly that value for any x in the oracle (and the reference
+    golden vectors); FillJacobianConstants writes exactly those slots in either layout."""
+    prob, o, gen = make_pair(case)
+    mask, val = prob.GetJacobianConstants()
+    x = gen(200)
+    jac = o.eval_batch(x, want=("jac",))["jac"]
+    assert (jac[:, mask] == val[mask]).all()
+    varying = (jac != jac[0]).any(axis=0) | np.isnan(jac).any(axis=0)
+    assert not (varying & mask).any()
+    if case.startswith("ground"):
+        assert mask.sum() == 3 * o.nc + 15 * o.nc          # statics identities + Ground's constants
+    elif case.startswith("noenv"):
+        assert mask.sum() == 3 * o.nc
+    else:
+        assert mask.sum() == 3 * o.nc + 3 * o.nc           # statics identities + the n-block identity of EnvironmentNormal
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"))
+    assert (z[f"{case}/jac"][:, mask] == val[mask]).all()
+    for layout in (cpl.INSTANCE_MAJOR, cpl.COMPONENT_MAJOR):
+        buf = np.full((7, prob.nnz) if layout == cpl.INSTANCE_MAJOR else (prob.nnz, 7), -3.0)
+        prob.FillJacobianConstants(buf, layout=layout)
+        b = buf if layout == cpl.INSTANCE_MAJOR else buf.T
+        assert (b[:, mask] == val[mask]).all() and (b[:, ~mask] == -3.0).all()
+
+
 def test_block_columns_and_contact_rows():
     prob = cpl.BatchedCplProblem(["r_foot", "l_foot", "r_hand", "l_hand"], 100.0, cpl.Ground())
     assert prob.GetBlockColumn(cpl.BLOCK_COM) == 0

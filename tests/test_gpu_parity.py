@@ -219,6 +219,27 @@ def test_host_buffer_path_matches_device_path(layout, cuda_device):
     assert_parity({k: host[k][sub] for k in host}, want, o, "host path")
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("case", ["ground4", "superquadric4", "noenv8"])
+def test_host_path_can_skip_constant_jacobian_slots(case, layout, cuda_device):
+    """CPLB_HOST_JAC_CONSTANTS_PRESENT: constant slots may be skipped (component-major: a sentinel there survives),
+    every x-dependent slot is transferred; after FillJacobianConstants the buffer equals the full evaluation."""
+    prob, o, gen = make_pair(case)
+    N = 20000
+    x = gen(N)
+    xin = x if layout == cpl.INSTANCE_MAJOR else np.ascontiguousarray(x.T)
+    full = prob.eval(xin, g=True, jac=True, layout=layout)
+    mask, _ = prob.GetJacobianConstants()
+    jac = np.full_like(full["jac"], -9.5)
+    part = prob.eval(xin, g=True, jac=True, layout=layout, out={"jac": jac}, jac_constants_present=True)
+    a, b = to_instance_major(part["jac"], layout), to_instance_major(full["jac"], layout)
+    if layout == cpl.COMPONENT_MAJOR:
+        assert (a[:, mask] == -9.5).all()          # whole rows of constant slots are never transferred
+    assert same_bits(a[:, ~mask], b[:, ~mask]) and same_bits(part["g"], full["g"])
+    prob.FillJacobianConstants(jac, layout=layout)
+    assert same_bits(jac, full["jac"])
+
+
 @pytest.mark.parametrize("case,N", [("ground4", 65536), ("superquadric4", 65536), ("ground8", 1 << 20)])
 def test_full_size_configs(case, N, cuda_device):
     """BASELINE.json configs 2-4 at full size.  The oracle checks a strided sample; the two kernels (different
