@@ -20,6 +20,7 @@
 #include <ifopt/problem.h>
 #include <ifopt/variable_set.h>
 
+#include <condition_variable>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -51,6 +52,7 @@ public:
         _cost = pinned((size_t)_N);
         std::memset(_x, 0, sizeof(double) * _N * _n);  // Variable3D starts at 0 (src/Variable3D.cpp:8-10)
         _prob->GetJacobianStructure(_iRow, _jCol);
+        _dirty.assign((size_t)_N, 1);
         _dirty_lo = 0;
         _dirty_hi = _N;
         const auto& names = _prob->contact_names();
@@ -83,6 +85,7 @@ public:
         if (std::memcmp(dst, v, 3 * sizeof(double)) == 0) return;
         std::lock_guard<std::mutex> lk(_mu);
         std::memcpy(dst, v, 3 * sizeof(double));
+        _dirty[(size_t)i] = 1;
         if (_dirty_lo >= _dirty_hi) {
             _dirty_lo = i;
             _dirty_hi = i + 1;
@@ -94,25 +97,43 @@ public:
     const double* x(int64_t i) const { return _x + i * _n; }
     const double* g(int64_t i)
     {
-        Refresh();
+        Refresh(i);
         return _g + i * _m;
     }
     const double* jac(int64_t i)
     {
-        Refresh();
+        Refresh(i);
         return _jac + i * _nnz;
     }
     const double* grad(int64_t i)
     {
-        Refresh();
+        Refresh(i);
         return _grad + i * _n;
     }
     double cost(int64_t i)
     {
-        Refresh();
+        Refresh(i);
         return _cost[i];
     }
     int64_t evaluations() const { return _evaluations; }
+
+    // Lock-step mode for `participants` solver threads (one IPOPT per thread, each owning one instance at a time):
+    // a thread that reads an output of an instance whose x changed waits until every participant has done the same
+    // (or has called Leave()), and the last one to arrive evaluates the whole dirty range in ONE launch.  IPOPT's
+    // callbacks (eval_f / eval_grad_f / eval_g / eval_jac_g) then cost one kernel launch per round, not one per thread.
+    void EnableLockStep(int participants)
+    {
+        std::lock_guard<std::mutex> lk(_mu);
+        _participants = participants;
+        _arrived = 0;
+    }
+    // a solver thread that has finished (converged / failed) stops taking part in the rounds
+    void Leave()
+    {
+        std::unique_lock<std::mutex> lk(_mu);
+        if (_participants > 0) _participants--;
+        if (_arrived > 0 && _arrived >= _participants) Release();
+    }
 
     // structural entries of the (rows [row0,row0+rows) x variable set v) block, in ifopt order
     const std::vector<Entry>& Block(int row0, int rows, int v)
@@ -135,14 +156,37 @@ private:
         check(cplb_host_alloc(count * sizeof(double), &p));
         return static_cast<double*>(p);
     }
-    void Refresh()
+    void EvaluateDirtyRange()  // _mu held
     {
-        std::lock_guard<std::mutex> lk(_mu);
         if (_dirty_lo >= _dirty_hi) return;
         const int64_t lo = _dirty_lo, cnt = _dirty_hi - _dirty_lo;
         _prob->EvaluateHost(cnt, _x + lo * _n, _g + lo * _m, _jac + lo * _nnz, _cost + lo, _grad + lo * _n);
+        std::fill(_dirty.begin() + lo, _dirty.begin() + lo + cnt, 0);
         _dirty_lo = _dirty_hi = 0;
         _evaluations++;
+    }
+    void Release()  // _mu held: the round is complete
+    {
+        EvaluateDirtyRange();
+        _arrived = 0;
+        _generation++;
+        _cv.notify_all();
+    }
+    void Refresh(int64_t i)
+    {
+        std::unique_lock<std::mutex> lk(_mu);
+        if (!_dirty[(size_t)i]) return;
+        if (_participants <= 1) {
+            EvaluateDirtyRange();
+            return;
+        }
+        _arrived++;
+        if (_arrived >= _participants) {
+            Release();
+        } else {
+            const int64_t gen = _generation;
+            _cv.wait(lk, [&] { return _generation != gen; });
+        }
     }
 
     BatchedProblem::Ptr _prob;
@@ -153,6 +197,10 @@ private:
     std::map<std::string, int> _var_index;
     std::map<long long, std::vector<Entry>> _blocks;
     std::mutex _mu;
+    std::condition_variable _cv;
+    std::vector<char> _dirty;
+    int _participants = 0, _arrived = 0;
+    int64_t _generation = 0;
     int64_t _dirty_lo = 0, _dirty_hi = 0, _evaluations = 0;
 };
 

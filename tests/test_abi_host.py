@@ -194,3 +194,36 @@ def test_evaluation_without_a_gpu_fails_loudly():
     prob, _, gen = make_pair("ground4")
     with pytest.raises(RuntimeError, match="no usable CUDA device"):
         prob.eval(gen(8))
+
+
+def test_pybind11_module_builds_and_keeps_the_exception_mapping():
+    """bindings/python/pycplb.cpp (pybind11 over the same C ABI): importable on a CPU box, reference class and method
+    names, std::invalid_argument -> ValueError, std::out_of_range -> IndexError, evaluation fails loudly without a GPU."""
+    import subprocess
+    import sys
+
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "bindings", "python")], stdout=subprocess.DEVNULL)
+    sys.path.insert(0, os.path.join(ROOT, "centroidalplanner_b200"))
+    import pycplb
+
+    g = pycplb.Ground()
+    g.SetGroundZ(0.1)
+    p = pycplb.BatchedProblem(["r_foot", "l_foot"], 100.0, g)
+    assert (p.n, p.m, p.nnz) == (21, 18, 90) and list(p.GetSortedOrder()) == [1, 0]
+    with pytest.raises(ValueError, match="Invalid friction coefficient"):
+        g.SetMu(-1.0)
+    with pytest.raises(IndexError):
+        p.SetForceThreshold("nose", 1.0)
+    with pytest.raises(ValueError, match="Invalid robot mass"):
+        pycplb.BatchedProblem(["a"], -1.0, g)
+    sq = pycplb.Superquadric()
+    with pytest.raises(ValueError, match="curvatures"):
+        sq.SetParameters([0, 0, 1], [1, 1, 1], [1.5, 2, 2])
+    c = pycplb.BatchedProblem(["a", "b"], 50.0)         # env = nullptr: the CoMPlanner shape
+    c.SetMu(0.3)
+    assert c.GetMu() == 0.3 and (c.m, c.nnz) == (10, 60)
+    import torch
+
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no usable CUDA device"):
+            p.eval(np.zeros((4, 21)))
