@@ -220,6 +220,43 @@ def test_host_buffer_path_matches_device_path(layout, cuda_device):
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
+def test_concurrent_host_threads_on_their_own_streams(layout, cuda_device):
+    """include/cpl_batched.h: evaluation takes x as an argument, so several host threads may evaluate disjoint
+    instance ranges of ONE problem on different streams at once (each IPOPT thread with its own slice)."""
+    import threading
+
+    import torch
+
+    prob, o, gen = make_pair("ground8")
+    N, T = 48000, 6
+    x = gen(N)
+    xd = torch.from_numpy(x).to(cuda_device)
+    ref = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
+    bounds = np.linspace(0, N, T + 1).astype(int)
+    results, errors = [None] * T, []
+
+    def work(t):
+        try:
+            st = torch.cuda.Stream(cuda_device)
+            lo, hi = int(bounds[t]), int(bounds[t + 1])
+            with torch.cuda.stream(st):
+                xin = xd[lo:hi].contiguous() if layout == cpl.INSTANCE_MAJOR else xd[lo:hi].t().contiguous()
+                for _ in range(5):  # repeated launches interleave across the threads
+                    out = prob.eval(xin, g=True, jac=True, cost=True, grad=True, layout=layout, stream=st.cuda_stream)
+                st.synchronize()
+            results[t] = {k: to_instance_major(v.cpu().numpy(), layout) for k, v in out.items()}
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    for k in ("g", "jac", "cost", "grad"):
+        assert same_bits(np.concatenate([r[k] for r in results]), ref[k]), k
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("case", ["ground4", "superquadric4", "noenv8"])
 def test_host_path_can_skip_constant_jacobian_slots(case, layout, cuda_device):
     """CPLB_HOST_JAC_CONSTANTS_PRESENT: constant slots may be skipped (component-major: a sentinel there survives),
