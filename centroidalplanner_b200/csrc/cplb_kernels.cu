@@ -82,12 +82,15 @@ template <int ENV, unsigned FLAGS, int MAX_WARPS>
 __global__ void __launch_bounds__(MAX_WARPS * 32) eval_component_major_split(const __grid_constant__ CplbParams P, const CplbIo io,
                                                                    const unsigned flags_rt)
 {
-    extern __shared__ double sh[];  // [nc][6][32]
+    extern __shared__ double sh_all[];  // [sub-block][nc][6 + 1][32]
     pdl_prologue();
     const unsigned flags = FLAGS ? FLAGS : flags_rt;
-    const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nc = P.nc;
-    const long long i_raw = (long long)blockIdx.x * 32 + lane;
+    const int sub = warp / nc, j = warp - sub * nc;  // a CTA holds blockDim/(32 nc) sub-blocks of 32 instances
+    const int subs = blockDim.x / (32 * nc);
+    double* sh = sh_all + (size_t)sub * nc * (192 + 32);
+    const long long i_raw = ((long long)blockIdx.x * subs + sub) * 32 + lane;
     const bool active = i_raw < io.N;
     const long long i = active ? i_raw : io.N - 1;  // inactive lanes recompute the last instance, store nothing
     const unsigned pitch = (unsigned)(io.ld * (long long)sizeof(double));
@@ -416,9 +419,11 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
 template <int ENV>
 static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
 {
-    const unsigned blocks = (unsigned)((io.N + 31) / 32);
-    const int threads = 32 * P.nc;
-    const size_t smem = (size_t)P.nc * (192 + 32) * sizeof(double);
+    // two 32-instance sub-blocks per CTA when they fit in 256 threads (measured: 22.1 vs 22.5 us on config 2)
+    const int subs = (P.nc <= 4) ? 2 : 1;
+    const unsigned blocks = (unsigned)((io.N + 32 * subs - 1) / (32 * subs));
+    const int threads = 32 * P.nc * subs;
+    const size_t smem = (size_t)subs * P.nc * (192 + 32) * sizeof(double);
     const unsigned gj = CPLB_WANT_G | CPLB_WANT_J;
     if (P.nc <= 8) {
         if (flags == gj)
