@@ -86,6 +86,8 @@ struct cplb_problem {
     std::mutex host_mu;
     cudaStream_t streams[kHostStreams] = {};
     double* stage[kHostStreams] = {};
+    double* bounce[kHostStreams] = {};  // pinned mirrors of stage[], used when the caller's buffers are pageable
+    size_t bounce_bytes = 0;
     size_t stage_bytes = 0;
     bool streams_ready = false;
 
@@ -209,6 +211,7 @@ void cplb_destroy(cplb_problem* p)
                 cudaStreamSynchronize(p->streams[s]);
                 cudaStreamDestroy(p->streams[s]);
                 if (p->stage[s]) cudaFree(p->stage[s]);
+                if (p->bounce[s]) cudaFreeHost(p->bounce[s]);
             }
         }
     }
@@ -699,6 +702,93 @@ static cplb_status ensure_host_pipeline(cplb_problem* p, size_t bytes_per_stream
     return CPLB_OK;
 }
 
+static bool is_pinned(const void* ptr)
+{
+    if (!ptr) return true;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+// Pageable caller buffers: cudaMemcpyAsync on them is synchronous and, measured, several times slower than a host
+// memcpy through a pinned buffer.  Each stream gets a pinned mirror of its device staging buffer; a chunk is packed
+// into it, travels H2D / kernel / D2H asynchronously, and is unpacked when the stream's turn comes round again.
+static cplb_status eval_host_bounced(cplb_problem* p, const cplb_eval_args* args, unsigned flags, long long ld, long long chunk,
+                                     size_t stage_bytes)
+{
+    const long long N = args->num_instances;
+    const int n = p->layout.n, m = p->layout.m, nnz = p->layout.nnz;
+    const bool cm = args->layout == CPLB_COMPONENT_MAJOR;
+    const bool skip_const = (args->host_flags & CPLB_HOST_JAC_CONSTANTS_PRESENT) != 0;
+    if (stage_bytes > p->bounce_bytes) {
+        for (int s = 0; s < kHostStreams; s++) {
+            if (p->bounce[s]) {
+                CPLB_CUDA(cudaStreamSynchronize(p->streams[s]));
+                CPLB_CUDA(cudaFreeHost(p->bounce[s]));
+                p->bounce[s] = nullptr;
+            }
+        }
+        p->bounce_bytes = 0;
+        for (int s = 0; s < kHostStreams; s++) CPLB_CUDA(cudaHostAlloc((void**)&p->bounce[s], stage_bytes, cudaHostAllocDefault));
+        p->bounce_bytes = stage_bytes;
+    }
+    struct Pending { long long i0 = 0, cnt = 0; };
+    Pending pend[kHostStreams];
+    // sections of a staging buffer, in doubles: x | g | jac | grad | cost  (rows of `chunk` for component-major)
+    const size_t ox = 0, og = ox + (size_t)n * chunk, oj = og + ((flags & CPLB_WANT_G) ? (size_t)m * chunk : 0),
+                 ogr = oj + ((flags & CPLB_WANT_J) ? (size_t)nnz * chunk : 0), oc = ogr + ((flags & CPLB_WANT_GRAD) ? (size_t)n * chunk : 0);
+    auto unpack_one = [&](double* user, const double* h, int len, long long i0, long long cnt) {
+        if (!user) return;
+        if (cm) for (int e = 0; e < len; e++) std::memcpy(user + (long long)e * ld + i0, h + (size_t)e * chunk, (size_t)cnt * sizeof(double));
+        else std::memcpy(user + i0 * len, h, (size_t)cnt * len * sizeof(double));
+    };
+    auto drain = [&](int s) -> cplb_status {
+        if (pend[s].cnt == 0) return CPLB_OK;
+        CPLB_CUDA(cudaStreamSynchronize(p->streams[s]));
+        const double* h = p->bounce[s];
+        unpack_one(args->g, h + og, m, pend[s].i0, pend[s].cnt);
+        if (cm && skip_const && args->jac) {  // rows of x-independent slots stay as the caller pre-filled them
+            for (const auto& r : p->layout.var_runs)
+                for (int e = r.begin; e < r.end; e++)
+                    std::memcpy(args->jac + (long long)e * ld + pend[s].i0, h + oj + (size_t)e * chunk, (size_t)pend[s].cnt * sizeof(double));
+        } else {
+            unpack_one(args->jac, h + oj, nnz, pend[s].i0, pend[s].cnt);
+        }
+        unpack_one(args->grad, h + ogr, n, pend[s].i0, pend[s].cnt);
+        if (args->cost) std::memcpy(args->cost + pend[s].i0, h + oc, (size_t)pend[s].cnt * sizeof(double));
+        pend[s].cnt = 0;
+        return CPLB_OK;
+    };
+    int s = 0;
+    for (long long i0 = 0; i0 < N; i0 += chunk, s = (s + 1) % kHostStreams) {
+        const long long cnt = (N - i0) < chunk ? (N - i0) : chunk;
+        cplb_status st = drain(s);
+        if (st != CPLB_OK) return st;
+        cudaStream_t stream = p->streams[s];
+        double* h = p->bounce[s];
+        double* d = p->stage[s];
+        if (cm) for (int e = 0; e < n; e++) std::memcpy(h + ox + (size_t)e * chunk, args->x + (long long)e * ld + i0, (size_t)cnt * sizeof(double));
+        else std::memcpy(h + ox, args->x + i0 * n, (size_t)cnt * n * sizeof(double));
+        CPLB_CUDA(cudaMemcpyAsync(d + ox, h + ox, (size_t)n * chunk * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CplbIo io{d + ox, (flags & CPLB_WANT_G) ? d + og : nullptr, (flags & CPLB_WANT_J) ? d + oj : nullptr,
+                  (flags & CPLB_WANT_COST) ? d + oc : nullptr, (flags & CPLB_WANT_GRAD) ? d + ogr : nullptr, chunk, cnt};
+        st = launch(p, io, args->layout, flags, stream);
+        if (st != CPLB_OK) return st;
+        const size_t out_doubles = (oc - og) + ((flags & CPLB_WANT_COST) ? (size_t)chunk : 0);
+        if (out_doubles) CPLB_CUDA(cudaMemcpyAsync(h + og, d + og, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        pend[s].i0 = i0;
+        pend[s].cnt = cnt;
+    }
+    for (int t = 0; t < kHostStreams; t++) {
+        cplb_status st = drain(t);
+        if (st != CPLB_OK) return st;
+    }
+    return CPLB_OK;
+}
+
 cplb_status cplb_eval_host(cplb_problem* p, const cplb_eval_args* args)
 {
     CPLB_REQUIRE(p);
@@ -728,6 +818,9 @@ cplb_status cplb_eval_host(cplb_problem* p, const cplb_eval_args* args)
     if (flags & CPLB_WANT_GRAD) per_inst += n;
     st = ensure_host_pipeline(p, per_inst * (size_t)chunk * sizeof(double));
     if (st != CPLB_OK) return st;
+
+    if (!(is_pinned(args->x) && is_pinned(args->g) && is_pinned(args->jac) && is_pinned(args->cost) && is_pinned(args->grad)))
+        return eval_host_bounced(p, args, flags, ld, chunk, per_inst * (size_t)chunk * sizeof(double));
 
     const bool cm = args->layout == CPLB_COMPONENT_MAJOR;
     const bool skip_const = (args->host_flags & CPLB_HOST_JAC_CONSTANTS_PRESENT) != 0;

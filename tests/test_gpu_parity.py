@@ -202,15 +202,27 @@ def test_parameter_updates_are_seen_by_the_next_launch(cuda_device):
     assert_parity(got, o.eval_batch(x), o, "updated parameters")
 
 
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("layout", LAYOUTS)
-def test_host_buffer_path_matches_device_path(layout, cuda_device):
-    """cplb_eval_host (H2D, kernel, D2H in chunks on several streams) == cplb_eval_device, bit for bit."""
+def test_host_buffer_path_matches_device_path(layout, pinned, cuda_device):
+    """cplb_eval_host (H2D, kernel, D2H in chunks on several streams) == cplb_eval_device, bit for bit -- with pinned
+    caller buffers (asynchronous copies straight from/to them) and with pageable ones (packed through pinned mirrors)."""
+    import torch
+
     prob, o, gen = make_pair("ground8")
     N = 40000  # > one chunk, ragged last chunk
     x = gen(N)
     xin = x if layout == cpl.INSTANCE_MAJOR else np.ascontiguousarray(x.T)
-    host = prob.eval(xin, g=True, jac=True, cost=True, grad=True, layout=layout)
-    host = {k: to_instance_major(v, layout) for k, v in host.items()}
+    out = None
+    if pinned:
+        shp = (lambda L: (N, L)) if layout == cpl.INSTANCE_MAJOR else (lambda L: (L, N))
+        xt = torch.empty(xin.shape, dtype=torch.float64, pin_memory=True)
+        xt.copy_(torch.from_numpy(xin))
+        xin = xt
+        out = {"g": torch.empty(shp(o.m), dtype=torch.float64, pin_memory=True), "jac": torch.empty(shp(o.nnz), dtype=torch.float64, pin_memory=True),
+               "cost": torch.empty(N, dtype=torch.float64, pin_memory=True), "grad": torch.empty(shp(o.n), dtype=torch.float64, pin_memory=True)}
+    host = prob.eval(xin, g=True, jac=True, cost=True, grad=True, layout=layout, out=out)
+    host = {k: to_instance_major(np.asarray(v), layout) for k, v in host.items()}
     dev = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
     for k in ("g", "jac", "cost", "grad"):
         assert same_bits(host[k], dev[k]), k
