@@ -79,7 +79,7 @@ __device__ __forceinline__ double ld_stream(const char* base, int e, unsigned pi
 // leaves its contact's force and moment term in shared memory and, after one barrier, warp r adds
 // row r's terms in sorted-name order (CentroidalStatics.cpp:44-54), the order that fixes rounding.
 template <int ENV, unsigned FLAGS, int MAX_WARPS>
-__global__ void __launch_bounds__(MAX_WARPS * 32) eval_component_major_split(const __grid_constant__ CplbParams P, const CplbIo io,
+__global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1)) eval_component_major_split(const __grid_constant__ CplbParams P, const CplbIo io,
                                                                    const unsigned flags_rt)
 {
     extern __shared__ double sh_all[];  // [sub-block][nc][6 + 1][32]
