@@ -258,18 +258,19 @@ def run_ours(args):
         # (`sets` evaluation kernels, captured from the same cplb_eval_device calls) plus a plain-launch remainder:
         # at ~20 us per kernel the per-launch host path and inter-kernel launch gap would otherwise be >10% of the step.
         graph = None
-        if not args.no_graph and K >= sets:
+        gsteps = min(K, sets)
+        if not args.no_graph and gsteps >= 2:
             side = torch.cuda.Stream(dev)
             side.wait_stream(stream)
             with torch.cuda.stream(side):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=side):
-                    for i in range(sets):
+                    for i in range(gsteps):
                         step(W + i)
             stream.wait_stream(side)
             graph.replay()  # one untimed replay (upload / first-run cost)
             barrier()
-        reps, rem = (K // sets, K % sets) if graph is not None else (0, K)
+        reps, rem = (K // gsteps, K % gsteps) if graph is not None else (0, K)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(reps):
@@ -279,7 +280,7 @@ def run_ours(args):
         e1.record(stream)
         barrier()
         ms_total = e0.elapsed_time(e1)
-        n_launch = reps * sets + rem  # evaluation kernels executed inside the timed region
+        n_launch = reps * gsteps + rem  # evaluation kernels executed inside the timed region
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -370,7 +371,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "num_contacts": NC, "env": "Ground", "instances_per_gpu": N,
                        "layout": lname[layout],
                        "outputs": "g+jac", "params": "shared",
-                       "launch": "plain launches" if args.no_graph or K < sets else f"CUDA graph of {sets} evaluation kernels replayed {K // sets}x + {K % sets} plain launches",
+                       "launch": "plain launches" if args.no_graph or min(K, sets) < 2 else
+                       f"CUDA graph of {min(K, sets)} evaluation kernels replayed {K // min(K, sets)}x + {K % min(K, sets)} plain launches",
                        "l2": f"inputs larger than L2: steps rotate through {sets} buffer sets, {sets * bytes_per_launch / 2**20:.0f} MiB total vs 126 MiB L2"},
             "e2e": {"value": world * N / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": world * 8 * n * N,
                     "d2h_bytes_per_step": world * 8 * (m + nnz) * N, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s,
