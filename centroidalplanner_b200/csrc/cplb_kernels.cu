@@ -1,8 +1,9 @@
 // cplb_kernels.cu -- the two evaluation kernels (sm_100a, fp64, no tensor cores: the path is
 // ~0.1 flop/byte, HBM-bound) and their launchers.
 //
-//  eval_component_major : struct-of-arrays buffers buf[e*ld + i].  One thread per instance; every
-//      load and store of a warp is one contiguous 256-byte segment.
+//  eval_component_major_split : struct-of-arrays buffers buf[e*ld + i].  One thread per (instance,
+//      contact): a warp is one contact of 32 consecutive instances, so every load and store of a
+//      warp is one contiguous 256-byte segment; the six statics sums cross warps through shared memory.
 //  eval_instance_major  : per-instance contiguous slices buf[i*len + e] (what an IPOPT thread
 //      consumes).  A warp owns a tile of 32/LPI consecutive instances, LPI lanes per instance
 //      (one lane per contact).  The tile's x slice is fetched with ONE bulk async copy
@@ -79,8 +80,8 @@ __device__ __forceinline__ double ld_stream(const char* base, int e, unsigned pi
 // leaves its contact's force and moment term in shared memory and, after one barrier, warp r adds
 // row r's terms in sorted-name order (CentroidalStatics.cpp:44-54), the order that fixes rounding.
 template <int ENV, unsigned FLAGS, int MAX_WARPS>
-__global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1)) eval_component_major_split(const __grid_constant__ CplbParams P, const CplbIo io,
-                                                                   const unsigned flags_rt)
+__global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // <= 64 registers: 32 warps per SM
+    eval_component_major_split(const __grid_constant__ CplbParams P, const CplbIo io, const unsigned flags_rt)
 {
     extern __shared__ double sh_all[];  // [sub-block][nc][6 + 1][32]
     pdl_prologue();
@@ -430,10 +431,8 @@ static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned
             return launch_pdl(eval_component_major_split<ENV, gj, 8>, blocks, threads, smem, st, P, io, flags);
         else
             return launch_pdl(eval_component_major_split<ENV, 0u, 8>, blocks, threads, smem, st, P, io, flags);
-    } else {
-        return launch_pdl(eval_component_major_split<ENV, 0u, 32>, blocks, threads, smem, st, P, io, flags);
     }
-    return cudaGetLastError();
+    return launch_pdl(eval_component_major_split<ENV, 0u, 32>, blocks, threads, smem, st, P, io, flags);
 }
 
 cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
