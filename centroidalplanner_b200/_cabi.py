@@ -21,6 +21,15 @@ dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
 
 
+INSTANCE_PARAM_FIELDS = ("mass", "wrench", "mu", "force_threshold", "ground_z", "com_ref", "com_weight", "pos_ref", "force_ref",
+                         "pos_weight", "force_weight")
+
+
+class InstanceParams(C.Structure):
+    """cplb_instance_params: optional per-instance parameter arrays (NULL = the problem's shared value)."""
+    _fields_ = [(name, C.c_void_p) for name in INSTANCE_PARAM_FIELDS]
+
+
 class EvalArgs(C.Structure):
     _fields_ = [
         ("num_instances", C.c_int64),
@@ -32,6 +41,7 @@ class EvalArgs(C.Structure):
         ("jac", C.c_void_p),
         ("cost", C.c_void_p),
         ("grad", C.c_void_p),
+        ("per_instance", C.POINTER(InstanceParams)),
     ]
 
 

@@ -237,7 +237,9 @@ public:
     double GetForceThreshold(const std::string& n) const { double t; check(cplb_get_force_threshold(_p, n.c_str(), &t)); return t; }
 
     // ---- evaluation (host buffers, instance-major: instance i owns x[i*n..], g[i*m..], jac[i*nnz..]) ----
-    void EvaluateHost(int64_t N, const double* x, double* g, double* jac, double* cost, double* grad)
+    // per_instance: optional per-instance parameter arrays (host pointers, instance-major), nullptr = shared parameters
+    void EvaluateHost(int64_t N, const double* x, double* g, double* jac, double* cost, double* grad,
+                      const cplb_instance_params* per_instance = nullptr)
     {
         cplb_eval_args a{};
         a.num_instances = N;
@@ -247,11 +249,12 @@ public:
         a.jac = jac;
         a.cost = cost;
         a.grad = grad;
+        a.per_instance = per_instance;
         check(cplb_eval_host(_p, &a));
     }
     // device buffers, either layout, asynchronous on `stream`
     void EvaluateDevice(int64_t N, cplb_layout layout, int64_t ld, const double* x, double* g, double* jac, double* cost,
-                        double* grad, void* stream)
+                        double* grad, void* stream, const cplb_instance_params* per_instance = nullptr)
     {
         cplb_eval_args a{};
         a.num_instances = N;
@@ -262,6 +265,7 @@ public:
         a.jac = jac;
         a.cost = cost;
         a.grad = grad;
+        a.per_instance = per_instance;
         check(cplb_eval_device(_p, &a, stream));
     }
 

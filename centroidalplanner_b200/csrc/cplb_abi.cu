@@ -104,6 +104,7 @@ struct cplb_problem {
         // _m * _g with _g = (0, 0, -9.81) (CentroidalStatics.cpp:15,57): one multiply per component
         const double g[3] = {0.0, 0.0, -9.81};
         for (int i = 0; i < 3; i++) P.mg[i] = mass * g[i];
+        P.mass = mass;
         for (int q = 0; q < 3; q++) {
             P.sqC[q] = sqC[q];
             P.sqR[q] = sqR[q];
@@ -636,10 +637,42 @@ static cplb_status check_args(const cplb_problem* p, const cplb_eval_args* a, un
     return CPLB_OK;
 }
 
-static cplb_status launch(cplb_problem* p, const CplbIo& io, int layout, unsigned flags, cudaStream_t st)
+// the per-instance arrays, in one table: ABI field, device-struct field, elements per instance
+using AbiField = const double* cplb_instance_params::*;
+using DevField = const double* CplbInstParams::*;
+struct InstField {
+    AbiField src;
+    DevField dst;
+    int len_fixed, len_per_contact;
+    int len(int nc) const { return len_fixed + len_per_contact * nc; }
+};
+static const InstField kInstFields[] = {
+    {&cplb_instance_params::mass, &CplbInstParams::mass, 1, 0},
+    {&cplb_instance_params::wrench, &CplbInstParams::wrench, 6, 0},
+    {&cplb_instance_params::mu, &CplbInstParams::mu, 1, 0},
+    {&cplb_instance_params::force_threshold, &CplbInstParams::F_thr, 0, 1},
+    {&cplb_instance_params::ground_z, &CplbInstParams::ground_z, 1, 0},
+    {&cplb_instance_params::com_ref, &CplbInstParams::com_ref, 3, 0},
+    {&cplb_instance_params::com_weight, &CplbInstParams::W_com, 1, 0},
+    {&cplb_instance_params::pos_ref, &CplbInstParams::p_ref, 0, 3},
+    {&cplb_instance_params::force_ref, &CplbInstParams::F_ref, 0, 3},
+    {&cplb_instance_params::pos_weight, &CplbInstParams::W_p, 0, 1},
+    {&cplb_instance_params::force_weight, &CplbInstParams::W_F, 0, 1},
+};
+
+static bool any_instance_param(const cplb_instance_params* q)
 {
-    cudaError_t e = layout == CPLB_COMPONENT_MAJOR ? cplb::launch_component_major(p->P, io, flags, st)
-                                                   : cplb::launch_instance_major(p->P, io, flags, st);
+    if (!q) return false;
+    for (const auto& f : kInstFields)
+        if (q->*(f.src)) return true;
+    return false;
+}
+
+static cplb_status launch(cplb_problem* p, const CplbIo& io, int layout, unsigned flags, cudaStream_t st,
+                          const CplbInstParams* q = nullptr)
+{
+    cudaError_t e = layout == CPLB_COMPONENT_MAJOR ? cplb::launch_component_major(p->P, io, flags, q, st)
+                                                   : cplb::launch_instance_major(p->P, io, flags, q, st);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     p->launches.fetch_add(1, std::memory_order_relaxed);
     return CPLB_OK;
@@ -672,7 +705,11 @@ cplb_status cplb_eval_device(cplb_problem* p, const cplb_eval_args* args, void* 
         CPLB_CUDA(cudaEventCreate(&e1));
         CPLB_CUDA(cudaEventRecord(e0, stream));
     }
-    st = launch(p, io, args->layout, flags, stream);
+    CplbInstParams q{};
+    const bool per_inst = any_instance_param(args->per_instance);
+    if (per_inst)
+        for (const auto& f : kInstFields) q.*(f.dst) = args->per_instance->*(f.src);
+    st = launch(p, io, args->layout, flags, stream, per_inst ? &q : nullptr);
     if (timed) {
         cudaEventRecord(e1, stream);
         std::lock_guard<std::mutex> lk(p->timing_mu);
@@ -716,6 +753,29 @@ static bool is_pinned(const void* ptr)
 // Pageable caller buffers: cudaMemcpyAsync on them is synchronous and, measured, several times slower than a host
 // memcpy through a pinned buffer.  Each stream gets a pinned mirror of its device staging buffer; a chunk is packed
 // into it, travels H2D / kernel / D2H asynchronously, and is unpacked when the stream's turn comes round again.
+struct HostInput {  // one host input array (x or a per-instance parameter array): len elements per instance
+    const double* user;
+    int len;
+    size_t off;  // offset (doubles) inside a staging buffer
+    DevField dst;  // nullptr for x
+};
+
+// x and every per-instance array that is present, laid out after the output sections of a staging buffer
+static std::vector<HostInput> host_inputs(const cplb_problem* p, const cplb_eval_args* args, long long chunk, size_t first_free, size_t* end)
+{
+    std::vector<HostInput> in;
+    in.push_back(HostInput{args->x, p->layout.n, 0, nullptr});
+    size_t off = first_free;
+    if (args->per_instance)
+        for (const auto& f : kInstFields)
+            if (args->per_instance->*(f.src)) {
+                in.push_back(HostInput{args->per_instance->*(f.src), f.len(p->layout.nc), off, f.dst});
+                off += (size_t)f.len(p->layout.nc) * chunk;
+            }
+    *end = off;
+    return in;
+}
+
 static cplb_status eval_host_bounced(cplb_problem* p, const cplb_eval_args* args, unsigned flags, long long ld, long long chunk,
                                      size_t stage_bytes)
 {
@@ -740,6 +800,8 @@ static cplb_status eval_host_bounced(cplb_problem* p, const cplb_eval_args* args
     // sections of a staging buffer, in doubles: x | g | jac | grad | cost  (rows of `chunk` for component-major)
     const size_t ox = 0, og = ox + (size_t)n * chunk, oj = og + ((flags & CPLB_WANT_G) ? (size_t)m * chunk : 0),
                  ogr = oj + ((flags & CPLB_WANT_J) ? (size_t)nnz * chunk : 0), oc = ogr + ((flags & CPLB_WANT_GRAD) ? (size_t)n * chunk : 0);
+    size_t in_end = 0;
+    const std::vector<HostInput> inputs = host_inputs(p, args, chunk, oc + ((flags & CPLB_WANT_COST) ? (size_t)chunk : 0), &in_end);
     auto unpack_one = [&](double* user, const double* h, int len, long long i0, long long cnt) {
         if (!user) return;
         if (cm) for (int e = 0; e < len; e++) std::memcpy(user + (long long)e * ld + i0, h + (size_t)e * chunk, (size_t)cnt * sizeof(double));
@@ -770,12 +832,17 @@ static cplb_status eval_host_bounced(cplb_problem* p, const cplb_eval_args* args
         cudaStream_t stream = p->streams[s];
         double* h = p->bounce[s];
         double* d = p->stage[s];
-        if (cm) for (int e = 0; e < n; e++) std::memcpy(h + ox + (size_t)e * chunk, args->x + (long long)e * ld + i0, (size_t)cnt * sizeof(double));
-        else std::memcpy(h + ox, args->x + i0 * n, (size_t)cnt * n * sizeof(double));
-        CPLB_CUDA(cudaMemcpyAsync(d + ox, h + ox, (size_t)n * chunk * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CplbInstParams q{};
+        for (const auto& in : inputs) {
+            double* hb = h + in.off;
+            if (cm) for (int e = 0; e < in.len; e++) std::memcpy(hb + (size_t)e * chunk, in.user + (long long)e * ld + i0, (size_t)cnt * sizeof(double));
+            else std::memcpy(hb, in.user + i0 * in.len, (size_t)cnt * in.len * sizeof(double));
+            CPLB_CUDA(cudaMemcpyAsync(d + in.off, hb, (size_t)in.len * chunk * sizeof(double), cudaMemcpyHostToDevice, stream));
+            if (in.dst) q.*(in.dst) = d + in.off;
+        }
         CplbIo io{d + ox, (flags & CPLB_WANT_G) ? d + og : nullptr, (flags & CPLB_WANT_J) ? d + oj : nullptr,
                   (flags & CPLB_WANT_COST) ? d + oc : nullptr, (flags & CPLB_WANT_GRAD) ? d + ogr : nullptr, chunk, cnt};
-        st = launch(p, io, args->layout, flags, stream);
+        st = launch(p, io, args->layout, flags, stream, inputs.size() > 1 ? &q : nullptr);
         if (st != CPLB_OK) return st;
         const size_t out_doubles = (oc - og) + ((flags & CPLB_WANT_COST) ? (size_t)chunk : 0);
         if (out_doubles) CPLB_CUDA(cudaMemcpyAsync(h + og, d + og, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -816,10 +883,16 @@ cplb_status cplb_eval_host(cplb_problem* p, const cplb_eval_args* args)
     if (flags & CPLB_WANT_J) per_inst += nnz;
     if (flags & CPLB_WANT_COST) per_inst += 1;
     if (flags & CPLB_WANT_GRAD) per_inst += n;
+    if (args->per_instance)
+        for (const auto& f : kInstFields)
+            if (args->per_instance->*(f.src)) per_inst += f.len(p->layout.nc);
     st = ensure_host_pipeline(p, per_inst * (size_t)chunk * sizeof(double));
     if (st != CPLB_OK) return st;
 
-    if (!(is_pinned(args->x) && is_pinned(args->g) && is_pinned(args->jac) && is_pinned(args->cost) && is_pinned(args->grad)))
+    bool all_pinned = is_pinned(args->x) && is_pinned(args->g) && is_pinned(args->jac) && is_pinned(args->cost) && is_pinned(args->grad);
+    if (args->per_instance)
+        for (const auto& f : kInstFields) all_pinned = all_pinned && is_pinned(args->per_instance->*(f.src));
+    if (!all_pinned)
         return eval_host_bounced(p, args, flags, ld, chunk, per_inst * (size_t)chunk * sizeof(double));
 
     const bool cm = args->layout == CPLB_COMPONENT_MAJOR;
@@ -835,16 +908,29 @@ cplb_status cplb_eval_host(cplb_problem* p, const cplb_eval_args* args)
         if (flags & CPLB_WANT_G) { dg_ = d; d += (size_t)m * chunk; }
         if (flags & CPLB_WANT_J) { dj = d; d += (size_t)nnz * chunk; }
         if (flags & CPLB_WANT_GRAD) { dgr = d; d += (size_t)n * chunk; }
-        if (flags & CPLB_WANT_COST) { dc = d; }
+        if (flags & CPLB_WANT_COST) { dc = d; d += (size_t)chunk; }
         // device-side chunk buffers use pitch `chunk` (component-major) or are dense (instance-major)
-        if (cm) {
-            CPLB_CUDA(cudaMemcpy2DAsync(dx, chunk * sizeof(double), args->x + i0, ld * sizeof(double), cnt * sizeof(double), n,
-                                        cudaMemcpyHostToDevice, stream));
-        } else {
-            CPLB_CUDA(cudaMemcpyAsync(dx, args->x + i0 * n, (size_t)cnt * n * sizeof(double), cudaMemcpyHostToDevice, stream));
-        }
+        CplbInstParams q{};
+        bool per_inst = false;
+        auto h2d = [&](double* dst, const double* src, int len) -> cplb_status {
+            if (cm) CPLB_CUDA(cudaMemcpy2DAsync(dst, chunk * sizeof(double), src + i0, ld * sizeof(double), cnt * sizeof(double), len, cudaMemcpyHostToDevice, stream));
+            else CPLB_CUDA(cudaMemcpyAsync(dst, src + i0 * len, (size_t)cnt * len * sizeof(double), cudaMemcpyHostToDevice, stream));
+            return CPLB_OK;
+        };
+        st = h2d(dx, args->x, n);
+        if (st != CPLB_OK) return st;
+        if (args->per_instance)
+            for (const auto& f : kInstFields)
+                if (const double* src = args->per_instance->*(f.src)) {
+                    const int len = f.len(p->layout.nc);
+                    st = h2d(d, src, len);
+                    if (st != CPLB_OK) return st;
+                    q.*(f.dst) = d;
+                    d += (size_t)len * chunk;
+                    per_inst = true;
+                }
         CplbIo io{dx, dg_, dj, dc, dgr, chunk, cnt};
-        st = launch(p, io, args->layout, flags, stream);
+        st = launch(p, io, args->layout, flags, stream, per_inst ? &q : nullptr);
         if (st != CPLB_OK) return st;
         if (cm) {
             if (dg_) CPLB_CUDA(cudaMemcpy2DAsync(args->g + i0, ld * sizeof(double), dg_, chunk * sizeof(double), cnt * sizeof(double), m, cudaMemcpyDeviceToHost, stream));

@@ -44,6 +44,20 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned blocks, unsigne
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+template <bool PERINST, bool COMPONENT_MAJOR>
+struct ParamSource {
+    using type = SharedParams;
+    __device__ __forceinline__ static type make(const CplbParams& P, const CplbInstParams&, long long, long long) { return type{P}; }
+};
+template <bool COMPONENT_MAJOR>
+struct ParamSource<true, COMPONENT_MAJOR> {
+    using type = InstanceParams<COMPONENT_MAJOR>;
+    __device__ __forceinline__ static type make(const CplbParams& P, const CplbInstParams& Q, long long i, long long ld)
+    {
+        return type{P, Q, i, ld};
+    }
+};
+
 // ================================================================================================
 // component-major (SoA)
 // ================================================================================================
@@ -79,9 +93,10 @@ __device__ __forceinline__ double ld_stream(const char* base, int e, unsigned pi
 // is the limit.  The only cross-contact quantities are the six CentroidalStatics sums; each warp
 // leaves its contact's force and moment term in shared memory and, after one barrier, warp r adds
 // row r's terms in sorted-name order (CentroidalStatics.cpp:44-54), the order that fixes rounding.
-template <int ENV, unsigned FLAGS, int MAX_WARPS>
+template <int ENV, unsigned FLAGS, int MAX_WARPS, bool PERINST>
 __global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // <= 64 registers: 32 warps per SM
-    eval_component_major_split(const __grid_constant__ CplbParams P, const CplbIo io, const unsigned flags_rt)
+    eval_component_major_split(const __grid_constant__ CplbParams P, const CplbIo io, const unsigned flags_rt,
+                               const __grid_constant__ CplbInstParams Q)
 {
     extern __shared__ double sh_all[];  // [sub-block][nc][6 + 1][32]
     pdl_prologue();
@@ -98,6 +113,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // 
     const char* x = reinterpret_cast<const char*>(io.x + i);
     const int k = P.perm[j];
     const bool need_n = flags & (CPLB_WANT_G | CPLB_WANT_J);
+    const auto ps = ParamSource<PERINST, true>::make(P, Q, i, io.ld);
 
     double c[3], F[3], p[3], n[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -122,13 +138,13 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // 
         mine[5 * 32] = d0 * F[1] - d1 * F[0];
     }
     if (flags & CPLB_WANT_COST) {
-        if (!(flags & (CPLB_WANT_G | CPLB_WANT_J))) mine[0] = contact_cost(P, k, F, p);
-        else sh[(size_t)nc * 192 + (size_t)j * 32 + lane] = contact_cost(P, k, F, p);
+        if (!(flags & (CPLB_WANT_G | CPLB_WANT_J))) mine[0] = contact_cost(ps, k, F, p);
+        else sh[(size_t)nc * 192 + (size_t)j * 32 + lane] = contact_cost(ps, k, F, p);
     }
 
     SoaEmitter em{reinterpret_cast<char*>(io.g + i), reinterpret_cast<char*>(io.jac + i),
                   reinterpret_cast<char*>(io.grad + i), pitch};
-    if (active) contact_rows<ENV>(P, em, nc, j, k, c, F, p, n, flags);
+    if (active) contact_rows<ENV>(P, ps, em, nc, j, k, c, F, p, n, flags);
 
     __syncthreads();
     if (!active) return;
@@ -139,7 +155,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // 
             const double* col = sh + r * 32 + lane;
             double v = 0.0;
             for (int jj = 0; jj < nc; jj++) v += col[(size_t)jj * 192];
-            if (flags & CPLB_WANT_G) em.g(r, r < 3 ? (v - P.wrench[r]) + P.mg[r] : v - P.wrench[r]);  // :56-57
+            if (flags & CPLB_WANT_G) em.g(r, r < 3 ? (v - ps.wrench(r)) + ps.mg(r) : v - ps.wrench(r));  // :56-57
             if ((flags & CPLB_WANT_J) && r >= 3) {
                 // CoM block (:128-133): row 3 <- (Fz, -Fy), row 4 <- (-Fz, Fx), row 5 <- (Fy, -Fx), each "acc -= term"
                 const int ia = r == 3 ? 2 : (r == 4 ? 2 : 1), ib = r == 3 ? 1 : (r == 4 ? 0 : 0);
@@ -161,12 +177,12 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // 
             const size_t stride = (flags & (CPLB_WANT_G | CPLB_WANT_J)) ? 32 : 192;
             double cost = 0.0;
             for (int jj = 0; jj < nc; jj++) cost += cc[(size_t)jj * stride];
-            cost += com_cost(P, c);
+            cost += com_cost(ps, c);
             __stcs(io.cost + i, cost);
         }
         if (flags & CPLB_WANT_GRAD) {
 #pragma unroll
-            for (int q = 0; q < 3; q++) em.grad(q, P.W_com * (c[q] - P.com_ref[q]));
+            for (int q = 0; q < 3; q++) em.grad(q, ps.W_com() * (c[q] - ps.com_ref(q)));
         }
     }
 }
@@ -251,9 +267,10 @@ __device__ __forceinline__ void warp_copy(double* dst, const double* src, int co
 //   - the tiles leave with bulk async stores; the warp only waits for the engine to have READ the tiles
 //     right before it overwrites them with the next tile's results.
 // No block-wide barrier: every warp runs its own pipeline (mbarriers + __syncwarp only).
-template <int ENV, int LPI, int WARPS, unsigned FLAGS>
+template <int ENV, int LPI, int WARPS, unsigned FLAGS, bool PERINST>
 __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_constant__ CplbParams P, const CplbIo io,
-                                                                   const unsigned flags_rt, const int aligned16)
+                                                                   const unsigned flags_rt, const int aligned16,
+                                                                   const __grid_constant__ CplbInstParams Q)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_prologue();
@@ -328,13 +345,14 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
             TileEmitter em{gs ? gs + (size_t)inst * m : nullptr, js ? js + (size_t)inst * nnz : nullptr,
                            grads ? grads + (size_t)inst * n : nullptr};
             const double c[3] = {xi[0], xi[1], xi[2]};
+            const auto ps = ParamSource<PERINST, false>::make(P, Q, i0 + inst, 0);
             for (int j = s; j < nc; j += LPI) {
                 const int k = P.perm[j];
                 const double* xk = xi + 3 + 9 * k;
                 const double F[3] = {xk[0], xk[1], xk[2]};
                 const double p[3] = {xk[3], xk[4], xk[5]};
                 const double nn[3] = {xk[6], xk[7], xk[8]};
-                contact_rows<ENV>(P, em, nc, j, k, c, F, p, nn, flags);
+                contact_rows<ENV>(P, ps, em, nc, j, k, c, F, p, nn, flags);
             }
             // CentroidalStatics rows: row r's running sum visits the contacts in sorted-name order
             // (CentroidalStatics.cpp:44-54); the six rows are independent, so they are dealt to the lanes.
@@ -361,7 +379,7 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
                             v += xk[r];
                         }
                     }
-                    if (flags & CPLB_WANT_G) em.g(r, mom ? v - P.wrench[r] : (v - P.wrench[r]) + P.mg[r]);
+                    if (flags & CPLB_WANT_G) em.g(r, mom ? v - ps.wrench(r) : (v - ps.wrench(r)) + ps.mg(r));
                     if ((flags & CPLB_WANT_J) && mom) {
                         em.j(3 * nc + q * L + 0, a);
                         em.j(3 * nc + q * L + 1, bb);
@@ -376,14 +394,14 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
                         const double* xk = xi + 3 + 9 * k;
                         const double F[3] = {xk[0], xk[1], xk[2]};
                         const double p[3] = {xk[3], xk[4], xk[5]};
-                        cost += contact_cost(P, k, F, p);
+                        cost += contact_cost(ps, k, F, p);
                     }
-                    cost += com_cost(P, c);
+                    cost += com_cost(ps, c);
                     costs[inst] = cost;
                 }
                 if (flags & CPLB_WANT_GRAD) {
 #pragma unroll
-                    for (int q = 0; q < 3; q++) em.grad(q, P.W_com * (c[q] - P.com_ref[q]));
+                    for (int q = 0; q < 3; q++) em.grad(q, ps.W_com() * (c[q] - ps.com_ref(q)));
                 }
             }
         }
@@ -417,8 +435,10 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
 // launchers
 // ================================================================================================
 
+static const CplbInstParams kNoInstParams = {};
+
 template <int ENV>
-static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
+static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
     // two 32-instance sub-blocks per CTA when they fit in 256 threads (measured: 22.1 vs 22.5 us on config 2)
     const int subs = (P.nc <= 4) ? 2 : 1;
@@ -426,31 +446,36 @@ static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned
     const int threads = 32 * P.nc * subs;
     const size_t smem = (size_t)subs * P.nc * (192 + 32) * sizeof(double);
     const unsigned gj = CPLB_WANT_G | CPLB_WANT_J;
+    if (Q) {  // per-instance parameter arrays
+        if (P.nc <= 8) return launch_pdl(eval_component_major_split<ENV, 0u, 8, true>, blocks, threads, smem, st, P, io, flags, *Q);
+        return launch_pdl(eval_component_major_split<ENV, 0u, 32, true>, blocks, threads, smem, st, P, io, flags, *Q);
+    }
     if (P.nc <= 8) {
         if (flags == gj)
-            return launch_pdl(eval_component_major_split<ENV, gj, 8>, blocks, threads, smem, st, P, io, flags);
+            return launch_pdl(eval_component_major_split<ENV, gj, 8, false>, blocks, threads, smem, st, P, io, flags, kNoInstParams);
         else
-            return launch_pdl(eval_component_major_split<ENV, 0u, 8>, blocks, threads, smem, st, P, io, flags);
+            return launch_pdl(eval_component_major_split<ENV, 0u, 8, false>, blocks, threads, smem, st, P, io, flags, kNoInstParams);
     }
-    return launch_pdl(eval_component_major_split<ENV, 0u, 32>, blocks, threads, smem, st, P, io, flags);
+    return launch_pdl(eval_component_major_split<ENV, 0u, 32, false>, blocks, threads, smem, st, P, io, flags, kNoInstParams);
 }
 
-cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
+cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
     if (io.N <= 0) return cudaSuccess;
     if (io.ld >= (1LL << 29)) return cudaErrorInvalidValue;  // row pitch must fit 32 bits of bytes
     switch (P.env) {
-    case CPLB_ENV_NONE_K: return launch_cm_env<CPLB_ENV_NONE_K>(P, io, flags, st);
-    case CPLB_ENV_GROUND_K: return launch_cm_env<CPLB_ENV_GROUND_K>(P, io, flags, st);
-    default: return launch_cm_env<CPLB_ENV_SUPERQUADRIC_K>(P, io, flags, st);
+    case CPLB_ENV_NONE_K: return launch_cm_env<CPLB_ENV_NONE_K>(P, io, flags, Q, st);
+    case CPLB_ENV_GROUND_K: return launch_cm_env<CPLB_ENV_GROUND_K>(P, io, flags, Q, st);
+    default: return launch_cm_env<CPLB_ENV_SUPERQUADRIC_K>(P, io, flags, Q, st);
     }
 }
 
-template <int ENV, int LPI, int WARPS, unsigned FLAGS>
-static cudaError_t launch_im_kernel(const CplbParams& P, const CplbIo& io, unsigned flags, size_t smem, cudaStream_t st)
+template <int ENV, int LPI, int WARPS, unsigned FLAGS, bool PERINST>
+static cudaError_t launch_im_kernel(const CplbParams& P, const CplbIo& io, unsigned flags, size_t smem, const CplbInstParams* Q,
+                                    cudaStream_t st)
 {
     constexpr int T = 32 / LPI;
-    auto kern = eval_instance_major<ENV, LPI, WARPS, FLAGS>;
+    auto kern = eval_instance_major<ENV, LPI, WARPS, FLAGS, PERINST>;
     // resident CTAs per SM and the SM count are fixed per (kernel, smem, device): looked up once
     struct Cfg { int device = -1; size_t smem = 0; int resident = 0; };
     static thread_local Cfg cfg;
@@ -474,40 +499,42 @@ static cudaError_t launch_im_kernel(const CplbParams& P, const CplbIo& io, unsig
     const unsigned blocks = (unsigned)(want < cfg.resident ? want : cfg.resident);
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const int aligned16 = al16(io.x) && al16(io.g) && al16(io.jac) && al16(io.grad) && (T % 2 == 0);
-    return launch_pdl(kern, blocks, WARPS * 32, smem, st, P, io, flags, aligned16);
+    return launch_pdl(kern, blocks, WARPS * 32, smem, st, P, io, flags, aligned16, Q ? *Q : kNoInstParams);
 }
 
 template <int ENV, int LPI>
-static cudaError_t launch_im_cfg(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
+static cudaError_t launch_im_cfg(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
     constexpr int T = 32 / LPI;
     const size_t per_warp = tile_doubles(T, P.n, P.m, P.nnz, flags) * sizeof(double) + 2 * sizeof(uint64_t);
     const unsigned gj = CPLB_WANT_G | CPLB_WANT_J;
     if (4 * per_warp <= 72 * 1024) {  // the common shapes: 4 warps per CTA, 3 CTAs per SM
-        if (flags == gj) return launch_im_kernel<ENV, LPI, 4, gj>(P, io, flags, 4 * per_warp, st);
-        return launch_im_kernel<ENV, LPI, 4, 0u>(P, io, flags, 4 * per_warp, st);
+        if (Q) return launch_im_kernel<ENV, LPI, 4, 0u, true>(P, io, flags, 4 * per_warp, Q, st);
+        if (flags == gj) return launch_im_kernel<ENV, LPI, 4, gj, false>(P, io, flags, 4 * per_warp, Q, st);
+        return launch_im_kernel<ENV, LPI, 4, 0u, false>(P, io, flags, 4 * per_warp, Q, st);
     }
     if (per_warp > 227 * 1024) return cudaErrorInvalidConfiguration;
-    return launch_im_kernel<ENV, LPI, 1, 0u>(P, io, flags, per_warp, st);  // many contacts: one warp per CTA
+    if (Q) return launch_im_kernel<ENV, LPI, 1, 0u, true>(P, io, flags, per_warp, Q, st);
+    return launch_im_kernel<ENV, LPI, 1, 0u, false>(P, io, flags, per_warp, Q, st);  // many contacts: one warp per CTA
 }
 
 template <int ENV>
-static cudaError_t launch_im_env(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
+static cudaError_t launch_im_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
     // lanes per instance: the smallest power of two >= nc (capped at 8; more contacts loop)
-    if (P.nc <= 1) return launch_im_cfg<ENV, 1>(P, io, flags, st);
-    if (P.nc <= 2) return launch_im_cfg<ENV, 2>(P, io, flags, st);
-    if (P.nc <= 4) return launch_im_cfg<ENV, 4>(P, io, flags, st);
-    return launch_im_cfg<ENV, 8>(P, io, flags, st);
+    if (P.nc <= 1) return launch_im_cfg<ENV, 1>(P, io, flags, Q, st);
+    if (P.nc <= 2) return launch_im_cfg<ENV, 2>(P, io, flags, Q, st);
+    if (P.nc <= 4) return launch_im_cfg<ENV, 4>(P, io, flags, Q, st);
+    return launch_im_cfg<ENV, 8>(P, io, flags, Q, st);
 }
 
-cudaError_t launch_instance_major(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st)
+cudaError_t launch_instance_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
     if (io.N <= 0) return cudaSuccess;
     switch (P.env) {
-    case CPLB_ENV_NONE_K: return launch_im_env<CPLB_ENV_NONE_K>(P, io, flags, st);
-    case CPLB_ENV_GROUND_K: return launch_im_env<CPLB_ENV_GROUND_K>(P, io, flags, st);
-    default: return launch_im_env<CPLB_ENV_SUPERQUADRIC_K>(P, io, flags, st);
+    case CPLB_ENV_NONE_K: return launch_im_env<CPLB_ENV_NONE_K>(P, io, flags, Q, st);
+    case CPLB_ENV_GROUND_K: return launch_im_env<CPLB_ENV_GROUND_K>(P, io, flags, Q, st);
+    default: return launch_im_env<CPLB_ENV_SUPERQUADRIC_K>(P, io, flags, Q, st);
     }
 }
 

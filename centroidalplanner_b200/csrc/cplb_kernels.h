@@ -8,10 +8,11 @@
 
 namespace cplb {
 
-// buf[e*ld + i]: one thread per instance, fully coalesced.
-cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st);
+// per_instance: optional per-instance parameter arrays (device pointers), nullptr = the shared parameter block.
+// buf[e*ld + i]: one thread per (instance, contact), fully coalesced.
+cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* per_instance, cudaStream_t st);
 // buf[i*len + e]: warp tiles staged through shared memory with bulk async (TMA) copies.
-cudaError_t launch_instance_major(const CplbParams& P, const CplbIo& io, unsigned flags, cudaStream_t st);
+cudaError_t launch_instance_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* per_instance, cudaStream_t st);
 
 }  // namespace cplb
 #endif

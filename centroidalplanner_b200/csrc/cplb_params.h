@@ -25,6 +25,7 @@ struct CplbParams {
     int32_t pad0;
     int32_t perm[CPLB_KMAX_CONTACTS];  // sorted-name rank -> index in the caller's vector
     double mg[3];                       // _m * _g, one IEEE multiply per component, done on the host
+    double mass;                        // _m (per-instance mode recomputes _m * _g on the device)
     double wrench[6];
     double mu;
     double ground_z;
@@ -46,6 +47,23 @@ struct CplbParams {
     double F_ref[CPLB_KMAX_CONTACTS][3];
     double W_p[CPLB_KMAX_CONTACTS];
     double W_F[CPLB_KMAX_CONTACTS];
+};
+
+// Optional per-instance parameter arrays (device memory; NULL = use the shared value of CplbParams), see
+// cplb_instance_params in include/cpl_batched.h.  Same layout rule as x: element e of instance i is arr[i*len + e]
+// (instance-major) or arr[e*ld + i] (component-major); len = 1, 6, nc, 3, 3*nc as noted.
+struct CplbInstParams {
+    const double* mass;      // 1
+    const double* wrench;    // 6
+    const double* mu;        // 1
+    const double* F_thr;     // nc   (contact index = position in the caller's name vector)
+    const double* ground_z;  // 1
+    const double* com_ref;   // 3
+    const double* W_com;     // 1
+    const double* p_ref;     // 3*nc (x,y,z of contact 0, then contact 1, ...)
+    const double* F_ref;     // 3*nc
+    const double* W_p;       // nc
+    const double* W_F;       // nc
 };
 
 // Pointers of one evaluation (device memory), see cplb_eval_args in include/cpl_batched.h.

@@ -332,17 +332,40 @@ class BatchedCplProblem:
         N = a.shape[0] if layout == _cabi.INSTANCE_MAJOR else a.shape[1]
         _check(self._lib.cplb_fill_jacobian_constants(self._h, N, layout, N, a.ctypes.data_as(_cabi.dp)))
 
+    def _instance_params(self, per_instance, N, layout, on_device):
+        """dict name -> array (cplb_instance_params fields) -> (ctypes struct, keep-alive list); shapes follow x's
+        layout: (N,) / (N, len) instance-major, (len, N) component-major."""
+        if not per_instance:
+            return None, []
+        lens = {"mass": 1, "wrench": 6, "mu": 1, "force_threshold": len(self._names), "ground_z": 1, "com_ref": 3, "com_weight": 1,
+                "pos_ref": 3 * len(self._names), "force_ref": 3 * len(self._names), "pos_weight": len(self._names),
+                "force_weight": len(self._names)}
+        st, keep = _cabi.InstanceParams(), []
+        for name, arr in per_instance.items():
+            if name not in lens:
+                raise ValueError(f"unknown per-instance parameter '{name}'")
+            L = lens[name]
+            if on_device:
+                assert arr.is_cuda and arr.is_contiguous() and arr.numel() == N * L, name
+                setattr(st, name, arr.data_ptr())
+            else:
+                arr = np.ascontiguousarray(arr.numpy() if _is_torch(arr) else np.asarray(arr, dtype=np.float64))
+                assert arr.size == N * L, name
+                setattr(st, name, arr.ctypes.data)
+            keep.append(arr)
+        return st, keep
+
     def eval(self, x, g=True, jac=True, cost=False, grad=False, layout=_cabi.INSTANCE_MAJOR, out=None, stream=None,
-             jac_constants_present=False):
+             jac_constants_present=False, per_instance=None):
         """One batched evaluation.  x: (N, n) [instance-major] or (n, N) [component-major], fp64,
         a torch CUDA tensor (device path, asynchronous on the current stream) or a NumPy array /
         CPU tensor (host path through cplb_eval_host).  Returns a dict of outputs of the same kind."""
         out = dict(out or {})
         if _is_torch(x) and x.is_cuda:
-            return self._eval_device(x, g, jac, cost, grad, layout, out, stream)
-        return self._eval_host(x, g, jac, cost, grad, layout, out, jac_constants_present)
+            return self._eval_device(x, g, jac, cost, grad, layout, out, stream, per_instance)
+        return self._eval_host(x, g, jac, cost, grad, layout, out, jac_constants_present, per_instance)
 
-    def _eval_device(self, x, g, jac, cost, grad, layout, out, stream):
+    def _eval_device(self, x, g, jac, cost, grad, layout, out, stream, per_instance=None):
         import torch
 
         assert x.dtype == torch.float64 and x.is_contiguous() and x.dim() == 2
@@ -361,13 +384,15 @@ class BatchedCplProblem:
 
         res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self.nnz), "cost": buf("cost", cost, None),
                "grad": buf("grad", grad, self.n)}
+        pi, keep = self._instance_params(per_instance, N, layout, True)
         args = _cabi.EvalArgs(N, layout, 0, N, x.data_ptr(), *[None if res[k] is None else res[k].data_ptr()
-                                                              for k in ("g", "jac", "cost", "grad")])
+                                                              for k in ("g", "jac", "cost", "grad")],
+                              C.pointer(pi) if pi is not None else None)
         s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
         _check(self._lib.cplb_eval_device(self._h, C.byref(args), C.c_void_p(s)))
         return res
 
-    def _eval_host(self, x, g, jac, cost, grad, layout, out, jac_constants_present=False):
+    def _eval_host(self, x, g, jac, cost, grad, layout, out, jac_constants_present=False, per_instance=None):
         is_t = _is_torch(x)
         xa = x.numpy() if is_t else np.asarray(x, dtype=np.float64)
         xa = np.ascontiguousarray(xa)
@@ -387,8 +412,10 @@ class BatchedCplProblem:
         res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self.nnz), "cost": buf("cost", cost, None),
                "grad": buf("grad", grad, self.n)}
         hflags = _cabi.HOST_JAC_CONSTANTS_PRESENT if jac_constants_present else 0
+        pi, keep = self._instance_params(per_instance, N, layout, False)
         args = _cabi.EvalArgs(N, layout, hflags, N, xa.ctypes.data, *[None if res[k] is None else res[k].ctypes.data
-                                                                     for k in ("g", "jac", "cost", "grad")])
+                                                                     for k in ("g", "jac", "cost", "grad")],
+                              C.pointer(pi) if pi is not None else None)
         _check(self._lib.cplb_eval_host(self._h, C.byref(args)))
         return res
 

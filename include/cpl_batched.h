@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CPLB_ABI_VERSION 1
+#define CPLB_ABI_VERSION 2
 #define CPLB_MAX_CONTACTS 32
 
 typedef enum cplb_status {
@@ -177,6 +177,27 @@ cplb_status cplb_get_contact_force_weight(const cplb_problem *p, const char *con
  * Any of g / jac / cost / grad may be NULL: that output is not computed and not written.
  * Element counts per instance: x n, g m, jac nnz, cost 1, grad n.  `layout`/`ld` apply to every buffer
  * (cost is always cost[i]); ld is ignored for INSTANCE_MAJOR and may be 0 (= num_instances) otherwise. */
+/* Optional per-instance parameters.  The reference holds ONE parameter set per CplProblem; a batch whose instances are
+ * different planning problems of the same shape (other wrench, mass, friction, references ...) passes arrays here.
+ * Every pointer may be NULL (= the problem's shared value set with cplb_set_*).  Arrays live in the same memory space
+ * as x and follow the same layout rule: element e of instance i is arr[i*len + e] (INSTANCE_MAJOR) or arr[e*ld + i]
+ * (COMPONENT_MAJOR), with len = the count given below; contact index = position in the caller's name vector.
+ * Values are used as they are (no validation: they never pass through the host).  The Superquadric shape (C, R, P) is
+ * always shared. */
+typedef struct cplb_instance_params {
+    const double *mass;             /* 1    CentroidalStatics::_m          (src/Constraints/CentroidalStatics.cpp:14,57) */
+    const double *wrench;           /* 6    CentroidalStatics::_wrench_manip (:25-28,56) */
+    const double *mu;               /* 1    EnvironmentClass::_mu           (Environment.h:46) */
+    const double *force_threshold;  /* nc   FrictionCone::_F_thr            (src/Constraints/FrictionCone.cpp:14,39) */
+    const double *ground_z;         /* 1    Ground::_ground_z               (src/Ground.cpp:26) */
+    const double *com_ref;          /* 3    MinimizeCentroidalVariables::_CoM_ref (src/MinimizeCentroidalVariables.cpp:11) */
+    const double *com_weight;       /* 1    _W_CoM (:13) */
+    const double *pos_ref;          /* 3*nc _contact_vars_ref_map[..].position_value (:30-34) */
+    const double *force_ref;        /* 3*nc ...force_value (:43-47) */
+    const double *pos_weight;       /* nc   _pos_weight_map (:80-93) */
+    const double *force_weight;     /* nc   _force_weight_map (:102-115) */
+} cplb_instance_params;
+
 /* cplb_eval_args.host_flags (cplb_eval_host only) */
 #define CPLB_HOST_JAC_CONSTANTS_PRESENT 1 /* the constant slots of the caller's jac buffer already hold their values
                                              (cplb_fill_jacobian_constants, or an earlier full evaluation into the same
@@ -194,6 +215,7 @@ typedef struct cplb_eval_args {
     double *jac;
     double *cost;
     double *grad;
+    const cplb_instance_params *per_instance; /* NULL: every instance uses the problem's shared parameters */
 } cplb_eval_args;
 
 /* All pointers are DEVICE pointers on the problem's device; the kernel is enqueued on `cuda_stream`

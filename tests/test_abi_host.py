@@ -26,7 +26,7 @@ def test_library_exports_every_symbol_the_header_declares():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libcplb.so does not export {name}"
     assert declared == set(_cabi.PROTOTYPES), declared ^ set(_cabi.PROTOTYPES)
-    assert _cabi.load().cplb_abi_version() == 1
+    assert _cabi.load().cplb_abi_version() == 2
 
 
 def test_product_never_imports_the_oracle():

@@ -111,7 +111,7 @@ def test_no_write_outside_the_output_slices(case, N, G, cuda_device):
             cbuf = torch.full((N + 2 * G,), SENT, dtype=torch.float64, device=cuda_device)
             bufs["cost"] = (cbuf, cbuf[G:G + N])
         args = _cabi.EvalArgs(N, layout, 0, ld, xin.data_ptr(), bufs["g"][1].data_ptr(), bufs["jac"][1].data_ptr(),
-                              bufs["cost"][1].data_ptr(), bufs["grad"][1].data_ptr())
+                              bufs["cost"][1].data_ptr(), bufs["grad"][1].data_ptr(), None)
         assert lib.cplb_eval_device(prob._h, C.byref(args), None) == 0, lib.cplb_last_error()
         torch.cuda.synchronize()
         got = {}
@@ -229,6 +229,69 @@ def test_host_buffer_path_matches_device_path(layout, pinned, cuda_device):
     sub = np.arange(0, N, 37)
     want = o.eval_batch(x[sub])
     assert_parity({k: host[k][sub] for k in host}, want, o, "host path")
+
+
+@pytest.mark.parametrize("path", ["device", "host"])
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("case", ["ground4", "noenv8", "superquadric3"])
+def test_per_instance_parameters(case, layout, path, cuda_device):
+    """cplb_instance_params: every instance carries its own mass, wrench, mu, thresholds, ground height, references and
+    weights.  The oracle plays N different CplProblems, one per instance."""
+    import torch
+
+    prob, o, gen = make_pair(case)
+    N = 300
+    nc = o.nc
+    x = gen(N)
+    rng = np.random.default_rng(42)
+    pi = {"mass": rng.uniform(20, 150, N), "wrench": rng.uniform(-50, 50, (N, 6)), "mu": rng.uniform(0.2, 1.2, N),
+          "force_threshold": rng.uniform(0, 30, (N, nc)), "com_ref": rng.uniform(-1, 1, (N, 3)), "com_weight": rng.uniform(0, 3, N),
+          "pos_ref": rng.uniform(-1, 1, (N, 3 * nc)), "force_ref": rng.uniform(-100, 100, (N, 3 * nc)),
+          "pos_weight": rng.uniform(0, 2, (N, nc)), "force_weight": rng.uniform(0, 0.1, (N, nc))}
+    if case.startswith("ground"):
+        pi["ground_z"] = rng.uniform(-0.2, 0.4, N)
+    want = {"g": np.zeros((N, o.m)), "jac": np.zeros((N, o.nnz)), "cost": np.zeros(N), "grad": np.zeros((N, o.n))}
+    names = o.names
+    for i in range(N):
+        o.set_mass(pi["mass"][i])
+        o.set_wrench(pi["wrench"][i])
+        o.set_mu(pi["mu"][i])
+        o.set_com_ref(pi["com_ref"][i])
+        o.set_com_weight(pi["com_weight"][i])
+        if "ground_z" in pi:
+            o.set_ground_z(pi["ground_z"][i])
+        for k, nm in enumerate(names):
+            o.set_force_threshold(nm, pi["force_threshold"][i, k])
+            o.set_pos_ref(nm, pi["pos_ref"][i, 3 * k:3 * k + 3])
+            o.set_force_ref(nm, pi["force_ref"][i, 3 * k:3 * k + 3])
+            o.set_contact_pos_weight(nm, pi["pos_weight"][i, k])
+            o.set_contact_force_weight(nm, pi["force_weight"][i, k])
+        e = o.eval(x[i])
+        for key in want:
+            want[key][i] = e[key]
+    cm = layout == cpl.COMPONENT_MAJOR
+    lay = lambda a: np.ascontiguousarray(a.T) if (cm and a.ndim == 2) else np.ascontiguousarray(a)  # noqa: E731
+    if path == "device":
+        pid = {k: torch.from_numpy(lay(v)).to(cuda_device) for k, v in pi.items()}
+        xd = torch.from_numpy(lay(x)).to(cuda_device)
+        out = prob.eval(xd, g=True, jac=True, cost=True, grad=True, layout=layout, per_instance=pid)
+        torch.cuda.synchronize()
+        got = {k: to_instance_major(v.cpu().numpy(), layout) for k, v in out.items()}
+    else:
+        out = prob.eval(lay(x), g=True, jac=True, cost=True, grad=True, layout=layout, per_instance={k: lay(v) for k, v in pi.items()})
+        got = {k: to_instance_major(v, layout) for k, v in out.items()}
+    assert_parity(got, want, o, f"per-instance/{case}/layout{layout}/{path}", x)
+    # a subset of the arrays: the others fall back to the shared values (the oracle still holds instance N-1's)
+    sub = {"wrench": pi["wrench"], "mu": pi["mu"]}
+    if path == "device":
+        out = prob.eval(xd, g=True, jac=False, layout=layout, per_instance={k: torch.from_numpy(lay(v)).to(cuda_device) for k, v in sub.items()})
+        torch.cuda.synchronize()
+        g_sub = to_instance_major(out["g"].cpu().numpy(), layout)
+        o2 = make_pair(case)[1]
+        for i in (0, N - 1):
+            o2.set_wrench(pi["wrench"][i])
+            o2.set_mu(pi["mu"][i])
+            assert same_bits(g_sub[i][:6], o2.eval(x[i])["g"][:6])
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
