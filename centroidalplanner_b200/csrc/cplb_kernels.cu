@@ -446,6 +446,11 @@ static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned
     const int threads = 32 * P.nc * subs;
     const size_t smem = (size_t)subs * P.nc * (192 + 32) * sizeof(double);
     const unsigned gj = CPLB_WANT_G | CPLB_WANT_J;
+    if (smem > 48 * 1024) {  // more than ~26 contacts: opt in to the larger dynamic shared memory (57 KB at 32 contacts)
+        cudaError_t e = cudaFuncSetAttribute(eval_component_major_split<ENV, 0u, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_component_major_split<ENV, 0u, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     if (Q) {  // per-instance parameter arrays
         if (P.nc <= 8) return launch_pdl(eval_component_major_split<ENV, 0u, 8, true>, blocks, threads, smem, st, P, io, flags, *Q);
         return launch_pdl(eval_component_major_split<ENV, 0u, 32, true>, blocks, threads, smem, st, P, io, flags, *Q);

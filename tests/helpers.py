@@ -24,6 +24,8 @@ CASES = {
     "noenv8": (synthetic.NAMES8, "none", lambda N: synthetic.ground_batch(N, 8, 13)),
     "superquadric8": (synthetic.NAMES8, "superquadric", lambda N: synthetic.superquadric_batch(N, 8, 15)),
     "ground12": (["k%02d" % (11 - i) for i in range(12)], "ground", lambda N: synthetic.ground_batch(N, 12, 17)),
+    # CPLB_MAX_CONTACTS: 32 warps per CTA in the component-major kernel, one warp per CTA in the instance-major one
+    "superquadric32": (["k%02d" % ((7 * i) % 32) for i in range(32)], "superquadric", lambda N: synthetic.superquadric_batch(N, 32, 19)),
     # fractional curvatures: every pow() of the reference is a real pow() on the GPU too (no integer fast path);
     # contacts on the positive side of the centre only (pow(negative, fractional) is NaN -- also covered, see below)
     "superquadric4_fracP": (synthetic.NAMES4, "superquadric", lambda N: _positive_side(synthetic.superquadric_batch(N, 4, 23)),
