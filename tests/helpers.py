@@ -21,6 +21,7 @@ CASES = {
     "ground1": (["contact1"], "ground", lambda N: synthetic.ground_batch(N, 1, 5)),
     "superquadric3": (["c", "a", "b"], "superquadric", lambda N: synthetic.superquadric_batch(N, 3, 9)),
     "ground5": (["e", "d", "c", "b", "a"], "ground", lambda N: synthetic.ground_batch(N, 5, 11)),
+    "noenv2": (["right", "left"], "none", lambda N: synthetic.ground_batch(N, 2, 12)),
     "noenv8": (synthetic.NAMES8, "none", lambda N: synthetic.ground_batch(N, 8, 13)),
     "superquadric8": (synthetic.NAMES8, "superquadric", lambda N: synthetic.superquadric_batch(N, 8, 15)),
     "ground12": (["k%02d" % (11 - i) for i in range(12)], "ground", lambda N: synthetic.ground_batch(N, 12, 17)),

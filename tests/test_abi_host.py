@@ -227,3 +227,29 @@ def test_pybind11_module_builds_and_keeps_the_exception_mapping():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no usable CUDA device"):
             p.eval(np.zeros((4, 21)))
+
+
+def test_eval_argument_checks_happen_before_any_device_work():
+    """Bad arguments are INVALID_ARGUMENT / NULL_POINTER on any machine; an empty batch is a no-op that succeeds."""
+    import ctypes as C
+
+    lib = _cabi.load()
+    prob = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, cpl.Ground())
+    x = np.zeros((4, prob.n))
+    g = np.zeros((4, prob.m))
+
+    def call(fn, **kw):
+        a = dict(num_instances=4, layout=cpl.INSTANCE_MAJOR, host_flags=0, ld=0, x=x.ctypes.data, g=g.ctypes.data, jac=None, cost=None,
+                 grad=None, per_instance=None)
+        a.update(kw)
+        args = _cabi.EvalArgs(*[a[k] for k in ("num_instances", "layout", "host_flags", "ld", "x", "g", "jac", "cost", "grad", "per_instance")])
+        return fn(prob._h, C.byref(args)) if fn is lib.cplb_eval_host else fn(prob._h, C.byref(args), None)
+
+    for fn in (lib.cplb_eval_host, lib.cplb_eval_device):
+        assert call(fn, num_instances=-1) == _cabi.INVALID_ARGUMENT
+        assert call(fn, layout=7) == _cabi.INVALID_ARGUMENT
+        assert call(fn, x=None) == _cabi.NULL_POINTER
+        assert call(fn, layout=cpl.COMPONENT_MAJOR, ld=3) == _cabi.INVALID_ARGUMENT and b"ld" in lib.cplb_last_error()
+        assert call(fn, num_instances=0) == _cabi.OK                      # empty batch
+        assert call(fn, g=None) == _cabi.OK                               # nothing requested
+    assert lib.cplb_eval_host(None, None) == _cabi.NULL_POINTER
