@@ -253,3 +253,17 @@ def test_eval_argument_checks_happen_before_any_device_work():
         assert call(fn, num_instances=0) == _cabi.OK                      # empty batch
         assert call(fn, g=None) == _cabi.OK                               # nothing requested
     assert lib.cplb_eval_host(None, None) == _cabi.NULL_POINTER
+
+
+def test_header_is_valid_c99_and_usable_from_plain_c(tmp_path):
+    """include/cpl_batched.h compiled by gcc as strict C99 and driven from a C program (no C++, no Python, no GPU)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc") or "gcc"
+    exe = str(tmp_path / "abi_c_check")
+    pkg = os.path.join(ROOT, "centroidalplanner_b200")
+    subprocess.check_call([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "native", "abi_c_check.c"), "-o", exe, "-L", pkg, "-lcplb", f"-Wl,-rpath,{pkg}"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "C ABI ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
