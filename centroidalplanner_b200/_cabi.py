@@ -62,6 +62,7 @@ PROTOTYPES = {
     "cplb_get_constraint_bounds": (C.c_int, [C.c_void_p, dp, dp]),
     "cplb_set_mass": (C.c_int, [C.c_void_p, C.c_double]),
     "cplb_get_mass": (C.c_int, [C.c_void_p, dp]),
+    "cplb_set_reduction_order": (C.c_int, [C.c_void_p, C.c_int32]),
     "cplb_set_manipulation_wrench": (C.c_int, [C.c_void_p, dp]),
     "cplb_get_manipulation_wrench": (C.c_int, [C.c_void_p, dp]),
     "cplb_set_mu": (C.c_int, [C.c_void_p, C.c_double]),

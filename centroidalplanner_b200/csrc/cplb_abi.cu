@@ -357,6 +357,14 @@ cplb_status cplb_get_mass(const cplb_problem* p, double* mass)
     return CPLB_OK;
 }
 
+cplb_status cplb_set_reduction_order(cplb_problem* p, int32_t order)
+{
+    CPLB_REQUIRE(p);
+    if (order != 0 && order != 1) return fail(CPLB_INVALID_ARGUMENT, "reduction order must be 0 ((v0+v1)+v2) or 1 (v0+(v1+v2))");
+    p->P.reduction_order = order;
+    return CPLB_OK;
+}
+
 cplb_status cplb_set_manipulation_wrench(cplb_problem* p, const double wrench[6])
 {
     CPLB_REQUIRE(p);

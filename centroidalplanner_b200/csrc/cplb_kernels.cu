@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // 
         mine[5 * 32] = d0 * F[1] - d1 * F[0];
     }
     if (flags & CPLB_WANT_COST) {
-        if (!(flags & (CPLB_WANT_G | CPLB_WANT_J))) mine[0] = contact_cost(ps, k, F, p);
-        else sh[(size_t)nc * 192 + (size_t)j * 32 + lane] = contact_cost(ps, k, F, p);
+        if (!(flags & (CPLB_WANT_G | CPLB_WANT_J))) mine[0] = contact_cost(ps, P.reduction_order, k, F, p);
+        else sh[(size_t)nc * 192 + (size_t)j * 32 + lane] = contact_cost(ps, P.reduction_order, k, F, p);
     }
 
     SoaEmitter em{reinterpret_cast<char*>(io.g + i), reinterpret_cast<char*>(io.jac + i),
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // 
             const size_t stride = (flags & (CPLB_WANT_G | CPLB_WANT_J)) ? 32 : 192;
             double cost = 0.0;
             for (int jj = 0; jj < nc; jj++) cost += cc[(size_t)jj * stride];
-            cost += com_cost(ps, c);
+            cost += com_cost(ps, P.reduction_order, c);
             __stcs(io.cost + i, cost);
         }
         if (flags & CPLB_WANT_GRAD) {
@@ -394,9 +394,9 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
                         const double* xk = xi + 3 + 9 * k;
                         const double F[3] = {xk[0], xk[1], xk[2]};
                         const double p[3] = {xk[3], xk[4], xk[5]};
-                        cost += contact_cost(ps, k, F, p);
+                        cost += contact_cost(ps, P.reduction_order, k, F, p);
                     }
-                    cost += com_cost(ps, c);
+                    cost += com_cost(ps, P.reduction_order, c);
                     costs[inst] = cost;
                 }
                 if (flags & CPLB_WANT_GRAD) {

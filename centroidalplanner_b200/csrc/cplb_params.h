@@ -22,7 +22,7 @@ struct CplbParams {
     int32_t nc;
     int32_t env;
     int32_t n, m, nnz;
-    int32_t pad0;
+    int32_t reduction_order;            // Eigen fixed-size 3-term reductions: 0 = (v0+v1)+v2, 1 = v0+(v1+v2)
     int32_t perm[CPLB_KMAX_CONTACTS];  // sorted-name rank -> index in the caller's vector
     double mg[3];                       // _m * _g, one IEEE multiply per component, done on the host
     double mass;                        // _m (per-instance mode recomputes _m * _g on the device)

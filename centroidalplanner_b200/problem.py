@@ -310,6 +310,10 @@ class BatchedCplProblem:
     def GetForceThreshold(self, contact_name):
         return self._get1(self._lib.cplb_get_force_threshold, str(contact_name).encode())
 
+    def SetReductionOrder(self, order):
+        """0: (v0+v1)+v2 (default, Eigen >= 3.3); 1: v0+(v1+v2).  See cplb_set_reduction_order."""
+        _check(self._lib.cplb_set_reduction_order(self._h, int(order)))
+
     def SetMass(self, mass):
         _check(self._lib.cplb_set_mass(self._h, float(mass)))
 

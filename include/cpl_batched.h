@@ -121,6 +121,11 @@ cplb_status cplb_get_constraint_bounds(const cplb_problem *p, double *lower, dou
 /* CentroidalStatics::SetMass (src/Constraints/CentroidalStatics.cpp:20-23); mass <= 0 rejected like the planner ctor. */
 cplb_status cplb_set_mass(cplb_problem *p, double mass);
 cplb_status cplb_get_mass(const cplb_problem *p, double *mass);
+/* Association of the 3-term sums behind Eigen's Vector3d dot() / norm() / squaredNorm() (FrictionCone.cpp:39-40,71,
+ * Superquadric.cpp:66-68, MinimizeCentroidalVariables.cpp:142,145): 0 = (v0+v1)+v2 (Eigen >= 3.3 with its default
+ * vectorisation; the default here), 1 = v0+(v1+v2) (Eigen 3.2 / EIGEN_DONT_VECTORIZE).  The reference pins no Eigen
+ * version; results differ by at most one rounding of the reduced quantity.  Anything else -> CPLB_INVALID_ARGUMENT. */
+cplb_status cplb_set_reduction_order(cplb_problem *p, int32_t order);
 /* CplProblem::Set/GetManipulationWrench (src/CplProblem.cpp:263-272) */
 cplb_status cplb_set_manipulation_wrench(cplb_problem *p, const double wrench[6]);
 cplb_status cplb_get_manipulation_wrench(const cplb_problem *p, double wrench[6]);

@@ -187,6 +187,24 @@ def test_superquadric_outside_the_fast_power_window(cuda_device):
         assert_parity(got, want, o, f"sq-window/layout{layout}", x)
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("case", ["ground4", "noenv8", "superquadric4", "superquadric4_fracP"])
+def test_other_eigen_reduction_order(case, layout, cuda_device):
+    """cplb_set_reduction_order(1): v0+(v1+v2) instead of (v0+v1)+v2 in every Eigen 3-term reduction the reference
+    relies on -- the oracle has the same switch, and the two must stay bit-identical (pow-free outputs) in both modes."""
+    prob, o, gen = make_pair(case)
+    x = gen(2000)
+    a = o.eval_batch(x)
+    prob.SetReductionOrder(1)
+    o.set_reduction_order(1)
+    b = o.eval_batch(x)
+    assert not np.array_equal(a["g"], b["g"], equal_nan=True)   # the switch changes some last bits ...
+    got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
+    assert_parity(got, b, o, f"order1/{case}/layout{layout}", x)  # ... and the GPU follows the oracle
+    with pytest.raises(ValueError):
+        prob.SetReductionOrder(2)
+
+
 def test_parameter_updates_are_seen_by_the_next_launch(cuda_device):
     prob, o, gen = make_pair("ground4")
     x = gen(256)
