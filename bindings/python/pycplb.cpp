@@ -86,6 +86,7 @@ PYBIND11_MODULE(pycplb, m)
             p.SetManipulationWrench(Vec6{{w[0], w[1], w[2], w[3], w[4], w[5]}});
         })
         .def("GetManipulationWrench", &cplb::BatchedProblem::GetManipulationWrench)
+        .def("SetReductionOrder", &cplb::BatchedProblem::SetReductionOrder)
         .def("SetMu", &cplb::BatchedProblem::SetMu)
         .def("GetMu", &cplb::BatchedProblem::GetMu)
         .def("SetForceThreshold", &cplb::BatchedProblem::SetForceThreshold)

@@ -231,6 +231,7 @@ public:
     double GetContactForceWeight(const std::string& n) const { double w; check(cplb_get_contact_force_weight(_p, n.c_str(), &w)); return w; }
     void SetManipulationWrench(const Vec6& w) { check(cplb_set_manipulation_wrench(_p, w.data())); }
     Vec6 GetManipulationWrench() const { Vec6 w; check(cplb_get_manipulation_wrench(_p, w.data())); return w; }
+    void SetReductionOrder(int order) { check(cplb_set_reduction_order(_p, order)); }  // Eigen 3-term reductions: 0 (default) or 1
     void SetMu(double mu) { (_env ? _env : env::EnvironmentClass::Ptr(_ground_fake))->SetMu(mu); }  // CplProblem.cpp:275-287
     double GetMu() const { return (_env ? _env : env::EnvironmentClass::Ptr(_ground_fake))->GetMu(); }
     void SetForceThreshold(const std::string& n, double t) { check(cplb_set_force_threshold(_p, n.c_str(), t)); }

@@ -187,6 +187,81 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // 
     }
 }
 
+// One thread per instance, for LARGER batches (where several waves of CTAs keep HBM busy and the per-contact split's
+// extra threads, shared-memory exchange and barrier only cost): all 3 + 9 nc loads of a thread are issued up front, the
+// statics sums stay in registers (164 / 248 registers for nc = 4 / 8; capping them spills and loses 8 % at 1M).
+// Measured at 1,048,576 instances: 97.7-98.3 % of the HBM roofline against 95 % for the split kernel; at 65,536
+// four-contact instances it is the other way round (80 % vs 88 %).
+template <int ENV, int NC, unsigned FLAGS>
+__global__ void __launch_bounds__(128) eval_component_major_whole(const __grid_constant__ CplbParams P, const CplbIo io,
+                                                                   const unsigned flags_rt)
+{
+    pdl_prologue();
+    const unsigned flags = FLAGS ? FLAGS : flags_rt;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= io.N) return;
+    const unsigned pitch = (unsigned)(io.ld * (long long)sizeof(double));
+    const char* x = reinterpret_cast<const char*>(io.x + i);
+    const SharedParams ps{P};
+    SoaEmitter em{reinterpret_cast<char*>(io.g + i), reinterpret_cast<char*>(io.jac + i), reinterpret_cast<char*>(io.grad + i), pitch};
+
+    double c[3], F[NC][3], p[NC][3], n[NC][3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) c[q] = ld_stream(x, q, pitch);
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const int k = P.perm[j];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            F[j][q] = ld_stream(x, 3 + 9 * k + q, pitch);
+            p[j][q] = ld_stream(x, 6 + 9 * k + q, pitch);
+            n[j][q] = ld_stream(x, 9 + 9 * k + q, pitch);
+        }
+    }
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double a31 = 0.0, a32 = 0.0, a40 = 0.0, a42 = 0.0, a50 = 0.0, a51 = 0.0, cost = 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) {  // sorted-name order (CentroidalStatics.cpp:44-54, :121-135)
+        const int k = P.perm[j];
+        const double d0 = p[j][0] - c[0], d1 = p[j][1] - c[1], d2 = p[j][2] - c[2];
+        v[0] += F[j][0];
+        v[1] += F[j][1];
+        v[2] += F[j][2];
+        v[3] += d1 * F[j][2] - d2 * F[j][1];
+        v[4] += d2 * F[j][0] - d0 * F[j][2];
+        v[5] += d0 * F[j][1] - d1 * F[j][0];
+        a31 -= F[j][2];
+        a32 -= -F[j][1];
+        a40 -= -F[j][2];
+        a42 -= F[j][0];
+        a50 -= F[j][1];
+        a51 -= -F[j][0];
+        contact_rows<ENV>(P, ps, em, NC, j, k, c, F[j], p[j], n[j], flags);
+        if (flags & CPLB_WANT_COST) cost += contact_cost(ps, P.reduction_order, k, F[j], p[j]);
+    }
+    if (flags & CPLB_WANT_G) {
+#pragma unroll
+        for (int r = 0; r < 6; r++) em.g(r, r < 3 ? (v[r] - P.wrench[r]) + P.mg[r] : v[r] - P.wrench[r]);  // :56-57
+    }
+    if (flags & CPLB_WANT_J) {
+        const int L = jac_moment_row_len(NC), s3 = 3 * NC;
+        em.j(s3 + 0, a31);
+        em.j(s3 + 1, a32);
+        em.j(s3 + L + 0, a40);
+        em.j(s3 + L + 1, a42);
+        em.j(s3 + 2 * L + 0, a50);
+        em.j(s3 + 2 * L + 1, a51);
+    }
+    if (flags & CPLB_WANT_COST) {
+        cost += com_cost(ps, P.reduction_order, c);
+        __stcs(io.cost + i, cost);
+    }
+    if (flags & CPLB_WANT_GRAD) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) em.grad(q, P.W_com * (c[q] - P.com_ref[q]));
+    }
+}
+
 // ================================================================================================
 // instance-major (AoS): warp tile, LPI lanes per instance, bulk async copies in and out
 // ================================================================================================
@@ -446,6 +521,19 @@ static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned
     const int threads = 32 * P.nc * subs;
     const size_t smem = (size_t)subs * P.nc * (192 + 32) * sizeof(double);
     const unsigned gj = CPLB_WANT_G | CPLB_WANT_J;
+    // shared-parameter batches of the two benchmark shapes, once they are large enough: one thread per instance.
+    // Measured crossovers (B200): nc = 4: 88 % (split) vs 80 % (whole) at 65,536 but 89 % vs 95 % at 98,304;
+    // nc = 8: 90.5 % vs 95 % already at 65,536.  Both reach 97-98 % at 1,048,576 (split: 95 %).
+    const long long whole_from = P.nc == 4 ? 90112 : 49152;
+    if (!Q && io.N >= whole_from && (P.nc == 4 || P.nc == 8)) {
+        const unsigned wb = (unsigned)((io.N + 127) / 128);
+        if (P.nc == 4) {
+            if (flags == gj) return launch_pdl(eval_component_major_whole<ENV, 4, gj>, wb, 128u, 0, st, P, io, flags);
+            return launch_pdl(eval_component_major_whole<ENV, 4, 0u>, wb, 128u, 0, st, P, io, flags);
+        }
+        if (flags == gj) return launch_pdl(eval_component_major_whole<ENV, 8, gj>, wb, 128u, 0, st, P, io, flags);
+        return launch_pdl(eval_component_major_whole<ENV, 8, 0u>, wb, 128u, 0, st, P, io, flags);
+    }
     if (smem > 48 * 1024) {  // more than ~26 contacts: opt in to the larger dynamic shared memory (57 KB at 32 contacts)
         cudaError_t e = cudaFuncSetAttribute(eval_component_major_split<ENV, 0u, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_component_major_split<ENV, 0u, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
