@@ -267,3 +267,11 @@ def test_header_is_valid_c99_and_usable_from_plain_c(tmp_path):
                            os.path.join(ROOT, "tests", "native", "abi_c_check.c"), "-o", exe, "-L", pkg, "-lcplb", f"-Wl,-rpath,{pkg}"])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "C ABI ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: without libcplb.so the package cannot create a problem at all."""
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "libcplb.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, cpl.Ground())
