@@ -640,6 +640,8 @@ static cplb_status check_args(const cplb_problem* p, const cplb_eval_args* a, un
     long long pitch = a->ld == 0 ? a->num_instances : a->ld;
     if (a->layout == CPLB_COMPONENT_MAJOR && pitch < a->num_instances)
         return fail(CPLB_INVALID_ARGUMENT, "ld (%lld) is smaller than num_instances (%lld)", pitch, (long long)a->num_instances);
+    if (a->layout == CPLB_COMPONENT_MAJOR && pitch >= (1LL << 29))
+        return fail(CPLB_INVALID_ARGUMENT, "ld (%lld) must be below 2^29: the kernels hold the row pitch in bytes in 32 bits", pitch);
     *ld = pitch;
     (void)p;
     return CPLB_OK;

@@ -250,6 +250,7 @@ def test_eval_argument_checks_happen_before_any_device_work():
         assert call(fn, layout=7) == _cabi.INVALID_ARGUMENT
         assert call(fn, x=None) == _cabi.NULL_POINTER
         assert call(fn, layout=cpl.COMPONENT_MAJOR, ld=3) == _cabi.INVALID_ARGUMENT and b"ld" in lib.cplb_last_error()
+        assert call(fn, layout=cpl.COMPONENT_MAJOR, ld=1 << 29) == _cabi.INVALID_ARGUMENT and b"2^29" in lib.cplb_last_error()
         assert call(fn, num_instances=0) == _cabi.OK                      # empty batch
         assert call(fn, g=None) == _cabi.OK                               # nothing requested
     assert lib.cplb_eval_host(None, None) == _cabi.NULL_POINTER
