@@ -15,6 +15,7 @@ OK, INVALID_ARGUMENT, OUT_OF_RANGE, RUNTIME_ERROR, CUDA_ERROR, NULL_POINTER = ra
 ENV_NONE, ENV_GROUND, ENV_SUPERQUADRIC = 0, 1, 2
 INSTANCE_MAJOR, COMPONENT_MAJOR = 0, 1
 HOST_JAC_CONSTANTS_PRESENT = 1
+DEVICE_INPUTS_READY = 2
 BLOCK_COM, BLOCK_FORCE, BLOCK_POSITION, BLOCK_NORMAL = 0, 1, 2, 3
 
 dp = C.POINTER(C.c_double)

@@ -719,6 +719,7 @@ cplb_status cplb_eval_device(cplb_problem* p, const cplb_eval_args* args, void* 
     const bool per_inst = any_instance_param(args->per_instance);
     if (per_inst)
         for (const auto& f : kInstFields) q.*(f.dst) = args->per_instance->*(f.src);
+    if (args->host_flags & CPLB_DEVICE_INPUTS_READY) flags |= CPLB_INPUTS_READY;
     st = launch(p, io, args->layout, flags, stream, per_inst ? &q : nullptr);
     if (timed) {
         cudaEventRecord(e1, stream);

@@ -22,10 +22,19 @@ namespace cplb {
 // launching right away and (2) waits for the PREVIOUS kernel to complete and flush before touching global memory,
 // so stream-order semantics are unchanged for any producer/consumer of the buffers; what overlaps is the launch
 // latency and CTA scheduling of back-to-back evaluations (~1 us of a ~20 us kernel).
-__device__ __forceinline__ void pdl_prologue()
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// With CPLB_INPUTS_READY (the caller vouches that x and the per-instance arrays were complete before the preceding
+// kernel started, i.e. they are not its outputs) the loads are issued BEFORE the wait: the ~3 us HBM latency of a
+// kernel's first wave of loads then overlaps the tail of the previous evaluation.  Stores always come after the wait.
+__device__ __forceinline__ void pdl_prologue(unsigned flags)
 {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_trigger();
+    if (!(flags & CPLB_INPUTS_READY)) pdl_wait();
+}
+__device__ __forceinline__ void pdl_after_loads(unsigned flags)
+{
+    if (flags & CPLB_INPUTS_READY) pdl_wait();
 }
 
 template <class... KArgs, class... Args>
@@ -99,8 +108,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // 
                                const __grid_constant__ CplbInstParams Q)
 {
     extern __shared__ double sh_all[];  // [sub-block][nc][6 + 1][32]
-    pdl_prologue();
-    const unsigned flags = FLAGS ? FLAGS : flags_rt;
+    pdl_prologue(flags_rt);
+    const unsigned flags = FLAGS ? FLAGS : (flags_rt & 15u);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nc = P.nc;
     const int sub = warp / nc, j = warp - sub * nc;  // a CTA holds blockDim/(32 nc) sub-blocks of 32 instances
@@ -126,6 +135,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, (MAX_WARPS == 8 ? 4 : 1))  // 
 #pragma unroll
         for (int q = 0; q < 3; q++) n[q] = ld_stream(x, 9 + 9 * k + q, pitch);
     }
+    pdl_after_loads(flags_rt);  // the loads above are in flight; everything below may store
 
     double* mine = sh + (size_t)j * 192 + lane;
     if (flags & (CPLB_WANT_G | CPLB_WANT_J)) {
@@ -196,10 +206,13 @@ template <int ENV, int NC, unsigned FLAGS>
 __global__ void __launch_bounds__(128) eval_component_major_whole(const __grid_constant__ CplbParams P, const CplbIo io,
                                                                    const unsigned flags_rt)
 {
-    pdl_prologue();
-    const unsigned flags = FLAGS ? FLAGS : flags_rt;
+    pdl_prologue(flags_rt);
+    const unsigned flags = FLAGS ? FLAGS : (flags_rt & 15u);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= io.N) return;
+    if (i >= io.N) {
+        pdl_after_loads(flags_rt);
+        return;
+    }
     const unsigned pitch = (unsigned)(io.ld * (long long)sizeof(double));
     const char* x = reinterpret_cast<const char*>(io.x + i);
     const SharedParams ps{P};
@@ -218,6 +231,7 @@ __global__ void __launch_bounds__(128) eval_component_major_whole(const __grid_c
             n[j][q] = ld_stream(x, 9 + 9 * k + q, pitch);
         }
     }
+    pdl_after_loads(flags_rt);
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double a31 = 0.0, a32 = 0.0, a40 = 0.0, a42 = 0.0, a50 = 0.0, a51 = 0.0, cost = 0.0;
 #pragma unroll
@@ -348,9 +362,10 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
                                                                    const __grid_constant__ CplbInstParams Q)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    pdl_prologue();
+    pdl_trigger();
+    if (!(flags_rt & CPLB_INPUTS_READY)) pdl_wait();
     constexpr int T = 32 / LPI;  // instances per warp tile
-    const unsigned flags = FLAGS ? FLAGS : flags_rt;
+    const unsigned flags = FLAGS ? FLAGS : (flags_rt & 15u);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nc = P.nc, n = P.n, m = P.m, nnz = P.nnz;
     const long long tiles = (io.N + T - 1) / T;
@@ -385,6 +400,7 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
         }
     }
     __syncwarp();
+    if (flags_rt & CPLB_INPUTS_READY) pdl_wait();  // the first tile's x is already on its way; nothing is stored before this
 
     const int inst = lane / LPI, s = lane % LPI;
     bool stores_in_flight = false;
@@ -528,10 +544,10 @@ static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned
     if (!Q && io.N >= whole_from && (P.nc == 4 || P.nc == 8)) {
         const unsigned wb = (unsigned)((io.N + 127) / 128);
         if (P.nc == 4) {
-            if (flags == gj) return launch_pdl(eval_component_major_whole<ENV, 4, gj>, wb, 128u, 0, st, P, io, flags);
+            if ((flags & 15u) == gj) return launch_pdl(eval_component_major_whole<ENV, 4, gj>, wb, 128u, 0, st, P, io, flags);
             return launch_pdl(eval_component_major_whole<ENV, 4, 0u>, wb, 128u, 0, st, P, io, flags);
         }
-        if (flags == gj) return launch_pdl(eval_component_major_whole<ENV, 8, gj>, wb, 128u, 0, st, P, io, flags);
+        if ((flags & 15u) == gj) return launch_pdl(eval_component_major_whole<ENV, 8, gj>, wb, 128u, 0, st, P, io, flags);
         return launch_pdl(eval_component_major_whole<ENV, 8, 0u>, wb, 128u, 0, st, P, io, flags);
     }
     if (smem > 48 * 1024) {  // more than ~26 contacts: opt in to the larger dynamic shared memory (57 KB at 32 contacts)
@@ -544,7 +560,7 @@ static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned
         return launch_pdl(eval_component_major_split<ENV, 0u, 32, true>, blocks, threads, smem, st, P, io, flags, *Q);
     }
     if (P.nc <= 8) {
-        if (flags == gj)
+        if ((flags & 15u) == gj)
             return launch_pdl(eval_component_major_split<ENV, gj, 8, false>, blocks, threads, smem, st, P, io, flags, kNoInstParams);
         else
             return launch_pdl(eval_component_major_split<ENV, 0u, 8, false>, blocks, threads, smem, st, P, io, flags, kNoInstParams);
@@ -599,11 +615,11 @@ template <int ENV, int LPI>
 static cudaError_t launch_im_cfg(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
     constexpr int T = 32 / LPI;
-    const size_t per_warp = tile_doubles(T, P.n, P.m, P.nnz, flags) * sizeof(double) + 2 * sizeof(uint64_t);
+    const size_t per_warp = tile_doubles(T, P.n, P.m, P.nnz, flags & 15u) * sizeof(double) + 2 * sizeof(uint64_t);
     const unsigned gj = CPLB_WANT_G | CPLB_WANT_J;
     if (4 * per_warp <= 72 * 1024) {  // the common shapes: 4 warps per CTA, 3 CTAs per SM
         if (Q) return launch_im_kernel<ENV, LPI, 4, 0u, true>(P, io, flags, 4 * per_warp, Q, st);
-        if (flags == gj) return launch_im_kernel<ENV, LPI, 4, gj, false>(P, io, flags, 4 * per_warp, Q, st);
+        if ((flags & 15u) == gj) return launch_im_kernel<ENV, LPI, 4, gj, false>(P, io, flags, 4 * per_warp, Q, st);
         return launch_im_kernel<ENV, LPI, 4, 0u, false>(P, io, flags, 4 * per_warp, Q, st);
     }
     if (per_warp > 227 * 1024) return cudaErrorInvalidConfiguration;

@@ -17,6 +17,7 @@
 #define CPLB_WANT_J 2u
 #define CPLB_WANT_COST 4u
 #define CPLB_WANT_GRAD 8u
+#define CPLB_INPUTS_READY 16u  // x / per-instance arrays are not outputs of the preceding kernel: read them before griddepcontrol.wait
 
 struct CplbParams {
     int32_t nc;

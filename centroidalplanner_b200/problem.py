@@ -360,16 +360,16 @@ class BatchedCplProblem:
         return st, keep
 
     def eval(self, x, g=True, jac=True, cost=False, grad=False, layout=_cabi.INSTANCE_MAJOR, out=None, stream=None,
-             jac_constants_present=False, per_instance=None):
+             jac_constants_present=False, per_instance=None, inputs_ready=False):
         """One batched evaluation.  x: (N, n) [instance-major] or (n, N) [component-major], fp64,
         a torch CUDA tensor (device path, asynchronous on the current stream) or a NumPy array /
         CPU tensor (host path through cplb_eval_host).  Returns a dict of outputs of the same kind."""
         out = dict(out or {})
         if _is_torch(x) and x.is_cuda:
-            return self._eval_device(x, g, jac, cost, grad, layout, out, stream, per_instance)
+            return self._eval_device(x, g, jac, cost, grad, layout, out, stream, per_instance, inputs_ready)
         return self._eval_host(x, g, jac, cost, grad, layout, out, jac_constants_present, per_instance)
 
-    def _eval_device(self, x, g, jac, cost, grad, layout, out, stream, per_instance=None):
+    def _eval_device(self, x, g, jac, cost, grad, layout, out, stream, per_instance=None, inputs_ready=False):
         import torch
 
         assert x.dtype == torch.float64 and x.is_contiguous() and x.dim() == 2
@@ -389,7 +389,7 @@ class BatchedCplProblem:
         res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self.nnz), "cost": buf("cost", cost, None),
                "grad": buf("grad", grad, self.n)}
         pi, keep = self._instance_params(per_instance, N, layout, True)
-        args = _cabi.EvalArgs(N, layout, 0, N, x.data_ptr(), *[None if res[k] is None else res[k].data_ptr()
+        args = _cabi.EvalArgs(N, layout, _cabi.DEVICE_INPUTS_READY if inputs_ready else 0, N, x.data_ptr(), *[None if res[k] is None else res[k].data_ptr()
                                                               for k in ("g", "jac", "cost", "grad")],
                               C.pointer(pi) if pi is not None else None)
         s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream

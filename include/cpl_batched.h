@@ -210,10 +210,17 @@ typedef struct cplb_instance_params {
                                              COMPONENT_MAJOR (whole rows of the buffer are skipped); for INSTANCE_MAJOR
                                              whole instance rows travel (measured faster than strided copies) */
 
+/* cplb_eval_args.host_flags bit for cplb_eval_device: the caller vouches that x and the per-instance arrays are NOT
+ * outputs of the kernel launched just before on the same stream (they were complete before it started -- e.g. a queue
+ * of independent batches).  Evaluation kernels are launched with programmatic stream serialization; with this bit they
+ * issue their loads before waiting for the preceding kernel, hiding a first-wave HBM latency behind its tail.  Outputs
+ * are always written after the preceding kernel has completed.  Without the bit, plain stream order holds. */
+#define CPLB_DEVICE_INPUTS_READY 2
+
 typedef struct cplb_eval_args {
     int64_t num_instances;
     int32_t layout; /* cplb_layout */
-    int32_t host_flags; /* 0, or CPLB_HOST_* bits; ignored by cplb_eval_device */
+    int32_t host_flags; /* 0, or CPLB_HOST_* (cplb_eval_host) / CPLB_DEVICE_* (cplb_eval_device) bits */
     int64_t ld;
     const double *x;
     double *g;

@@ -205,6 +205,30 @@ def test_other_eigen_reduction_order(case, layout, cuda_device):
         prob.SetReductionOrder(2)
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_inputs_ready_queue_of_independent_batches(layout, cuda_device):
+    """CPLB_DEVICE_INPUTS_READY: a queue of independent batches on one stream, each evaluation allowed to read its x
+    while the previous kernel is still running.  Results must be those of plain stream order; each batch is written to
+    its own outputs, and a final plain-order evaluation that REUSES an output buffer of the queue must still come last."""
+    import torch
+
+    prob, o, gen = make_pair("ground4")
+    N, Q = 65536, 6
+    xs = [torch.from_numpy(gen(N) + 0.001 * q).to(cuda_device) for q in range(Q)]
+    xin = [x if layout == cpl.INSTANCE_MAJOR else x.t().contiguous() for x in xs]
+    outs = [prob.eval(xi, g=True, jac=True, layout=layout, inputs_ready=True) for xi in xin]      # back to back, one stream
+    again = prob.eval(xin[0], g=True, jac=True, layout=layout, out={"g": outs[3]["g"], "jac": outs[3]["jac"]})  # plain order
+    torch.cuda.synchronize()
+    ref0 = prob.eval(xin[0], g=True, jac=True, layout=layout)
+    torch.cuda.synchronize()
+    assert torch.equal(again["jac"].view(torch.int64), ref0["jac"].view(torch.int64))               # not clobbered by batch 3
+    for q in (1, 2, 4, 5):
+        sub = np.arange(0, N, 997)
+        want = o.eval_batch(xs[q].cpu().numpy()[sub], want=("g", "jac"))
+        got = {k: to_instance_major(outs[q][k].cpu().numpy(), layout)[sub] for k in ("g", "jac")}
+        assert_parity(got, want, o, f"ready-queue/{q}/layout{layout}")
+
+
 def test_parameter_updates_are_seen_by_the_next_launch(cuda_device):
     prob, o, gen = make_pair("ground4")
     x = gen(256)

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--sets", type=int, default=0, help="buffer sets to rotate through (0 = enough to exceed L2 8x)")
     ap.add_argument("--all", action="store_true", help="also cost + gradient")
+    ap.add_argument("--ready", action="store_true", help="pass inputs_ready=True (x is not produced by the preceding kernel)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     prob, _, gen = make_pair(a.case, rich=False)
@@ -54,7 +55,7 @@ def main():
     e0.record()
     for i in range(a.steps):
         s = (a.warmup + i) % sets
-        prob.eval(xs[s], g=True, jac=True, cost=a.all, grad=a.all, layout=layout, out=outs[s])
+        prob.eval(xs[s], g=True, jac=True, cost=a.all, grad=a.all, layout=layout, out=outs[s], inputs_ready=a.ready)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
