@@ -131,6 +131,38 @@ def test_no_write_outside_the_output_slices(case, N, G, cuda_device):
         assert_parity(got, want, o, f"guard/{case}/N{N}/layout{layout}", x)
 
 
+def test_config1_testbasic_parameter_set(cuda_device):
+    """BASELINE.json configs[0] (tests/TestBasic.cpp:64-99, testGroundEnv) with its exact parameters: mass 100, Ground
+    z = 0.1, mu = 0.5, W_CoM = 2, W_F = 0, W_p = 1, wrench (100,0,0,0,0,100), p bounds [-0.3,0.3]^2 x [0,1].  IPOPT is
+    absent, so the solve itself cannot run; the evaluator is checked on this parameter set at (i) the start point
+    x = 0, (ii) the closed-form equilibrium point, (iii) 1,000 random points -- GPU vs oracle, bit for bit."""
+    from test_oracle import equilibrium_x
+
+    from helpers import OracleProblem
+
+    names = synthetic.NAMES4
+    env = cpl.Ground()
+    env.SetGroundZ(synthetic.TESTBASIC["ground_z"])
+    env.SetMu(synthetic.TESTBASIC["mu"])
+    prob = cpl.BatchedCplProblem(names, synthetic.TESTBASIC["mass"], env)
+    synthetic.configure_testbasic(prob, names)
+    op = OracleProblem(names, "ground", synthetic.TESTBASIC["mass"])
+    op.SetGroundZ(synthetic.TESTBASIC["ground_z"])
+    op.SetMu(synthetic.TESTBASIC["mu"])
+    synthetic.configure_testbasic(op, names)
+    o = op.o
+    lb, ub = prob.GetBoundsOnOptimizationVariables()
+    for k in range(4):
+        assert list(lb[6 + 9 * k:9 + 9 * k]) == [-0.3, -0.3, 0.0] and list(ub[6 + 9 * k:9 + 9 * k]) == [0.3, 0.3, 1.0]
+    x = np.concatenate([np.zeros((1, 39)), equilibrium_x()[None, :], synthetic.ground_batch(1000)])
+    want = o.eval_batch(x)
+    assert np.isnan(want["jac"][0]).sum() == 24            # (i): 0/0 in the six entries of each friction-cone row
+    assert list(want["g"][1, :6]) == [-100.0, 0.0, 0.0, 0.0, 0.0, -100.0]   # (ii): balanced except for the manipulation wrench
+    for layout in LAYOUTS:
+        got = run_device(prob, x, layout, cuda_device, g=True, jac=True, cost=True, grad=True)
+        assert_parity(got, want, o, f"config1/layout{layout}")
+
+
 def test_default_start_point_nan_pattern(cuda_device):
     """x = 0 (Variable3D.cpp:8-10): NaN exactly where the reference produces NaN."""
     for case in ("ground4", "noenv4", "superquadric4"):
