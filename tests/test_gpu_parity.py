@@ -368,6 +368,36 @@ def test_per_instance_parameters(case, layout, path, cuda_device):
             assert same_bits(g_sub[i][:6], o2.eval(x[i])["g"][:6])
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("want", [dict(g=True, jac=False), dict(g=False, jac=True), dict(g=False, jac=False, cost=True),
+                                  dict(g=False, jac=False, grad=True), dict(g=True, jac=False, cost=True, grad=True)])
+def test_host_path_output_subsets(want, layout, pinned, cuda_device):
+    """Every subset of outputs through cplb_eval_host: the staging-buffer sections shift with the subset."""
+    import torch
+
+    prob, o, gen = make_pair("noenv8")
+    N = 20011  # two chunks, ragged
+    x = gen(N)
+    ref = o.eval_batch(x, nthreads=4)
+    xin = x if layout == cpl.INSTANCE_MAJOR else np.ascontiguousarray(x.T)
+    out = None
+    if pinned:
+        shp = (lambda L: (N, L)) if layout == cpl.INSTANCE_MAJOR else (lambda L: (L, N))
+        xt = torch.empty(xin.shape, dtype=torch.float64, pin_memory=True)
+        xt.copy_(torch.from_numpy(xin))
+        xin = xt
+        lens = {"g": o.m, "jac": o.nnz, "grad": o.n}
+        out = {k: torch.empty((N,) if k == "cost" else shp(lens[k]), dtype=torch.float64, pin_memory=True)
+               for k in ("g", "jac", "cost", "grad") if want.get(k, False)}
+    got = prob.eval(xin, layout=layout, out=out, **want)
+    for k in ("g", "jac", "cost", "grad"):
+        if not want.get(k, False):
+            assert got[k] is None
+        else:
+            assert same_bits(to_instance_major(np.asarray(got[k]), layout), ref[k]), k
+
+
 @pytest.mark.parametrize("layout", LAYOUTS)
 def test_concurrent_host_threads_on_their_own_streams(layout, cuda_device):
     """include/cpl_batched.h: evaluation takes x as an argument, so several host threads may evaluate disjoint
