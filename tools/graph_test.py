@@ -1,4 +1,6 @@
-import sys, time; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+"""Diagnostic: host issue rate of back-to-back evaluations from Python vs the device time per step, and the same steps
+replayed from a CUDA graph (what bench.py times).  python tools/graph_test.py  (needs a GPU)"""
+import sys, time; import os; ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,ROOT); sys.path.insert(0,os.path.join(ROOT,'tests'))
 import numpy as np, torch
 import centroidalplanner_b200 as cpl
 from helpers import make_pair

@@ -2,7 +2,9 @@
 """Largest deviation of the GPU evaluation from the CPU oracle over ALL instances of the Superquadric benchmark batches
 (config 3: 65,536 x 4 contacts; and the 8-contact variant).  Outputs without a pow() upstream must be bit-identical; for
 the others the script prints the maximum and median relative deviation.  Recorded in DESIGN.md section 5."""
-import sys; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
 import centroidalplanner_b200 as cpl
 from helpers import make_pair, pow_downstream_masks, same_bits
