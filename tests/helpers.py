@@ -216,3 +216,31 @@ def assert_parity(got, want, o, what, x=None):
 def to_instance_major(arr, layout):
     a = np.asarray(arr)
     return a.T if (layout == cpl.COMPONENT_MAJOR and a.ndim == 2) else a
+
+
+class OracleEvalProblem(OracleProblem):
+    """The oracle behind the evaluation surface a solver drives (`n, m, nnz, eval, GetJacobianStructure,
+    GetBoundsOn*`): lets the lock-step solve driver run the identical loop on the CPU reference restatement."""
+
+    def __init__(self, names, env_name, mass, nthreads=1):
+        super().__init__(names, env_name, mass)
+        self.n, self.m, self.nnz = self.o.n, self.o.m, self.o.nnz
+        self.nthreads = nthreads
+        self.calls = 0
+
+    def GetJacobianStructure(self):
+        return self.o.structure()
+
+    def GetBoundsOnOptimizationVariables(self):
+        return self.o.var_bounds()
+
+    def GetBoundsOnConstraints(self):
+        return self.o.con_bounds()
+
+    def eval(self, x, g=True, jac=True, cost=False, grad=False):
+        import torch
+
+        want = tuple(k for k, w in (("g", g), ("jac", jac), ("cost", cost), ("grad", grad)) if w)
+        self.calls += 1
+        out = self.o.eval_batch(x.detach().cpu().numpy(), want=want, nthreads=self.nthreads)
+        return {k: (None if out[k] is None else torch.as_tensor(out[k])) for k in ("g", "jac", "cost", "grad")}

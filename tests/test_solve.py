@@ -1,0 +1,241 @@
+"""The reference's own test suite (tests/TestBasic.cpp) replayed through the lock-step solve driver.
+
+The reference's four tests build a planner, call Solve() (IPOPT) and assert post-solve invariants.  IPOPT is absent from
+this image; `centroidalplanner_b200.lockstep_solver.LockStepInteriorPoint` is the stand-in (the same interior-point
+scheme, batched over instances, every callback round one batched evaluation).  Each test below is one TEST_F with its
+parameters and its EXPECT lines, asserted for EVERY instance of a small batch of different starting points:
+
+  * CPU (`not gpu`): the evaluator behind the driver is the oracle -- pins the driver and the assertions themselves;
+  * GPU (`-m gpu`): the evaluator is the CUDA path through the C ABI, x never leaves the device.  For Ground and
+    no-environment problems every output of the CUDA path is bit-identical to the oracle's, so with the linear algebra on
+    the same device the two solves must walk the SAME iterates bit for bit (`test_gpu_solve_trajectory_is_the_oracle_s`).
+
+Where the reference asserts a strict `<= 0.0` on a quantity an interior-point method only drives to its bound within the
+bound relaxation (IPOPT bound_relax_factor = 1e-8), the tolerance is written out.
+"""
+import numpy as np
+import pytest
+import torch
+
+import centroidalplanner_b200 as cpl
+from centroidalplanner_b200.lockstep_solver import SUCCESS, LockStepInteriorPoint, default_start
+from helpers import OracleEvalProblem
+
+G = -9.81
+MASS = 100.0
+NAMES = ["contact1", "contact2", "contact3", "contact4"]
+RELAX = 1e-8  # IPOPT bound_relax_factor
+
+
+def starts(problem, N, seed, device=None):
+    """Instance 0 starts at default_start, the others at perturbations of it."""
+    x0 = default_start(problem, N)
+    rng = np.random.default_rng(seed)
+    x0[1:] += torch.as_tensor(rng.normal(0.0, 0.05, tuple(x0[1:].shape)))
+    return x0 if device is None else x0.to(device)
+
+
+# ---- the four TEST_F setups, applied to anything with the CplProblem setter names --------------------------------
+def setup_simple(problem, env):                     # TestBasic.cpp:27-61
+    env.SetGroundZ(0.1)
+    return dict(ground_z=0.1)
+
+
+def setup_ground(problem, env):                     # TestBasic.cpp:64-136
+    env.SetGroundZ(0.1)
+    env.SetMu(0.5)
+    problem.SetCoMWeight(2.0)
+    problem.SetForceWeight(0.0)
+    for nm in NAMES:
+        problem.SetPosBounds(nm, [-0.3, -0.3, 0.0], [0.3, 0.3, 1.0])
+    problem.SetManipulationWrench([100.0, 0, 0, 0, 0, 100.0])
+    return dict(ground_z=0.1, mu=0.5, wrench=np.array([100.0, 0, 0, 0, 0, 100.0]))
+
+
+def setup_superquadric(problem, env):               # TestBasic.cpp:139-222
+    env.SetMu(0.5)
+    env.SetParameters([0.0, 0.0, 1.0], [0.3, 0.3, 10.0], [10.0, 10.0, 10.0])
+    problem.SetForceWeight(0.0)
+    for nm in NAMES:
+        problem.SetPosBounds(nm, [-0.5, -0.5, 0.5], [0.5, 0.5, 1.5])
+    problem.SetManipulationWrench([100.0, 0, 0, 0, 0, 100.0])
+    return dict(mu=0.5, wrench=np.array([100.0, 0, 0, 0, 0, 100.0]), C=np.array([0, 0, 1.0]), R=np.array([0.3, 0.3, 10.0]),
+                P=np.array([10.0, 10, 10]), p_lb=np.array([-0.5, -0.5, 0.5]), p_ub=np.array([0.5, 0.5, 1.5]))
+
+
+def setup_com_planner(problem, env):                # TestBasic.cpp:225-292 with the CoMPlanner bookkeeping (src/CoMPlanner.cpp)
+    problem.SetPosWeight(0.0)                       # CoMPlanner.cpp:10-11
+    problem.SetForceWeight(0.0)
+    problem.SetMu(0.5)
+    pts = {"contact1": [1.0, 1.0, 0.0], "contact2": [-1.0, 1.0, 0.0], "contact3": [-1.0, -1.0, 0.0], "contact4": [1.0, -1.0, 0.0]}
+    for nm in NAMES:
+        problem.SetNormalBounds(nm, [0, 0, 1.0], [0, 0, 1.0])   # SetContactNormal
+        problem.SetPosBounds(nm, pts[nm], pts[nm])               # SetContactPosition
+    problem.SetForceBounds("contact4", [0, 0, 0], [0, 0, 0])     # SetLiftingContact: zero force, threshold 0
+    problem.SetForceThreshold("contact4", 0.0)
+    for nm in NAMES[:3]:
+        problem.SetForceThreshold(nm, 20.0)                     # CentroidalPlanner.cpp:340: not forwarded to contact4
+    return dict(mu=0.5, wrench=np.zeros(6))
+
+
+SETUPS = {"simple": (["contact1"], "ground", setup_simple), "ground": (NAMES, "ground", setup_ground),
+          "superquadric": (NAMES, "superquadric", setup_superquadric), "com_planner": (NAMES, "none", setup_com_planner)}
+
+
+def oracle_problem(case):
+    names, env_name, setup = SETUPS[case]
+    op = OracleEvalProblem(names, env_name, MASS)
+    return op, names, setup(op, op)
+
+
+def product_problem(case):
+    names, env_name, setup = SETUPS[case]
+    env = {"none": None, "ground": cpl.Ground, "superquadric": cpl.Superquadric}[env_name]
+    env = env() if env is not None else None
+    prob = cpl.BatchedCplProblem(names, MASS, env)
+    return prob, names, setup(prob, env)
+
+
+def solution_maps(problem_names, x):
+    """CplProblem::GetSolution for every instance: list of (com, {name: (F, p, n)}) in sorted-name order."""
+    out = []
+    order = sorted(range(len(problem_names)), key=lambda k: problem_names[k])
+    for xi in np.asarray(x):
+        out.append((xi[0:3], {problem_names[k]: (xi[3 + 9 * k:6 + 9 * k], xi[6 + 9 * k:9 + 9 * k], xi[9 + 9 * k:12 + 9 * k]) for k in order}))
+    return out
+
+
+def check_expectations(case, names, par, x):
+    """The EXPECT_* lines of the corresponding TEST_F, for every instance."""
+    for com, cmap in solution_maps(names, x):
+        F_sum, T_sum = np.zeros(3), np.zeros(3)
+        for F, p, n in cmap.values():
+            F_sum += F
+            T_sum += np.cross(p - com, F)
+            if case in ("simple", "ground"):
+                assert abs(p[2] - par["ground_z"]) < 1e-6            # :53,119
+                assert abs(np.linalg.norm(n) - 1.0) < 1e-6           # :54,120
+                assert abs(n[2] - 1.0) < 1e-6                        # :55,121
+            if case == "superquadric":
+                sq = (((p - par["C"]) / par["R"]) ** par["P"]).sum()
+                assert abs(sq - 1.0) < 1e-4                          # :196
+                assert abs(np.linalg.norm(n) - 1.0) < 1e-6           # :197
+                assert (p - par["p_lb"] >= 0.0).all() and (p - par["p_ub"] <= 0.0).all()   # :206-211
+            if case != "simple":
+                mu = par["mu"]
+                assert -F.dot(n) <= RELAX                            # :127,203,279 (strict in the reference)
+                assert np.linalg.norm(F - n.dot(F) * n) - mu * F.dot(n) <= RELAX   # :128,204,280
+        if case == "simple":
+            assert abs(F_sum[2] - (-MASS * G)) < 1e-6                # :59
+            continue
+        w = par["wrench"]
+        tol_t = 1e-5 if case == "ground" else 1e-4
+        assert abs(F_sum[0] - w[0]) < 1e-6 and abs(F_sum[1] - w[1]) < 1e-6   # :131-132
+        assert abs(F_sum[2] - (-MASS * G + w[2])) < 1e-6             # :133
+        assert np.abs(T_sum - w[3:6]).max() < tol_t                  # :134-136
+
+
+@pytest.mark.parametrize("case", list(SETUPS))
+def test_testbasic_through_the_oracle(case):
+    op, names, par = oracle_problem(case)
+    x0 = starts(op, 4, seed=7)
+    res = LockStepInteriorPoint().Solve(op, x0)
+    assert (res.status == SUCCESS).all(), (res.status.tolist(), res.iterations.tolist())
+    assert res.evaluations == op.calls                               # one oracle batch per evaluator call
+    check_expectations(case, names, par, res.x.numpy())
+
+
+def test_solver_agrees_with_scipy_slsqp_on_a_nondegenerate_problem():
+    """With a force weight the minimiser is unique: the driver (tol 1e-8) and SciPy's SLSQP on the same oracle callbacks
+    must find the same optimal cost."""
+    from scipy.optimize import minimize
+
+    op, names, _ = oracle_problem("ground")
+    op.SetForceWeight(1e-4)
+    x0 = default_start(op, 1)
+    res = LockStepInteriorPoint(tol=1e-8).Solve(op, x0)
+    assert res.ok() and int(res.iterations[0]) < 60
+    iRow, jCol = op.GetJacobianStructure()
+    lb, ub = op.GetBoundsOnOptimizationVariables()
+    cl, cu = op.GetBoundsOnConstraints()
+    eq = cl == cu
+
+    def dense(x):
+        J = np.zeros((op.m, op.n))
+        J[iRow, jCol] = op.o.eval(x)["jac"]
+        return J
+
+    cons = [{"type": "eq", "fun": lambda x: op.o.eval(x)["g"][eq] - cl[eq], "jac": lambda x: dense(x)[eq]},
+            {"type": "ineq", "fun": lambda x: cu[~eq] - op.o.eval(x)["g"][~eq], "jac": lambda x: -dense(x)[~eq]}]
+    r = minimize(lambda x: op.o.eval(x)["cost"], x0[0].numpy(), jac=lambda x: op.o.eval(x)["grad"], bounds=list(zip(lb, ub)),
+                 constraints=cons, method="SLSQP", options={"maxiter": 500, "ftol": 1e-12})
+    assert r.status == 0
+    assert abs(float(res.cost[0]) - r.fun) < 1e-6 * abs(r.fun)
+
+
+def test_start_at_zero_is_reported_as_invalid_number():
+    """x = 0 is the reference's start (Variable3D.cpp:8-10); the friction Jacobian there is 0/0 and the driver
+    says so instead of iterating on NaNs."""
+    from centroidalplanner_b200.lockstep_solver import INVALID_NUMBER
+
+    op, _, _ = oracle_problem("ground")
+    res = LockStepInteriorPoint(max_iter=5).Solve(op, torch.zeros(1, op.n, dtype=torch.float64))
+    assert int(res.status[0]) == INVALID_NUMBER
+
+
+# ---- GPU: the CUDA evaluator behind the same driver ---------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(SETUPS))
+def test_testbasic_through_the_cuda_path(case, cuda_device):
+    prob, names, par = product_problem(case)
+    x0 = starts(prob, 64, seed=7, device=cuda_device)
+    before = prob.launch_count()
+    res = LockStepInteriorPoint().Solve(prob, x0)
+    assert (res.status == SUCCESS).all(), (res.status.tolist(), res.iterations.tolist())
+    assert prob.launch_count() - before == res.evaluations           # every evaluator call of the solve was one kernel launch
+    check_expectations(case, names, par, res.x.cpu().numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["ground", "com_planner"])
+def test_gpu_solve_trajectory_is_the_oracle_s(case, cuda_device):
+    """Host-path evaluations (cplb_eval_host, CUDA kernels) and oracle evaluations under the same CPU linear algebra:
+    bit-identical evaluator outputs => bit-identical iterates, iteration counts and solutions."""
+    prob, names, _ = product_problem(case)
+    op, _, _ = oracle_problem(case)
+    x0 = starts(op, 8, seed=11)
+    a = LockStepInteriorPoint().Solve(prob, x0)          # CPU tensors -> cplb_eval_host
+    b = LockStepInteriorPoint().Solve(op, x0)
+    assert a.rounds == b.rounds and a.evaluations == b.evaluations
+    assert (a.iterations == b.iterations).all() and (a.status == b.status).all()
+    assert (a.x.numpy().view(np.int64) == b.x.numpy().view(np.int64)).all()
+
+
+@pytest.mark.gpu
+def test_com_planner_facade_solve(cuda_device):
+    """TEST_F(TestBasic, testCoMPlanner) (tests/TestBasic.cpp:225-292) call for call through the facade mirror."""
+    planner = cpl.BatchedCoMPlanner(NAMES, MASS)
+    planner.SetMu(0.5)
+    assert planner.GetMu() == 0.5
+    planner.SetContactPosition("contact1", [1.0, 1.0, 0.0])
+    planner.SetContactPosition("contact2", [-1.0, 1.0, 0.0])
+    planner.SetContactPosition("contact3", [-1.0, -1.0, 0.0])
+    planner.SetContactPosition("contact4", [1.0, -1.0, 0.0])
+    planner.SetLiftingContact("contact4")
+    assert planner.GetLiftingContacts() == ["contact4"]
+    for c in NAMES:
+        planner.SetForceThreshold(c, 20.0)
+    sols = planner.Solve()
+    assert planner.last_solve.ok()
+    sol = sols[0]
+    assert list(sol["contact_values_map"]) == sorted(NAMES)
+    F_sum, T_sum = np.zeros(3), np.zeros(3)
+    for v in sol["contact_values_map"].values():
+        F, p, n = v["force_value"], v["position_value"], v["normal_value"]
+        F_sum += F
+        T_sum += np.cross(p - sol["com_sol"], F)
+        assert -F.dot(n) <= RELAX
+        assert np.linalg.norm(F - n.dot(F) * n) - 0.5 * F.dot(n) <= RELAX
+    assert np.abs(F_sum - [0.0, 0.0, -MASS * G]).max() < 1e-6
+    assert np.abs(T_sum).max() < 1e-4
+    assert np.abs(sol["contact_values_map"]["contact4"]["force_value"]).max() == 0.0   # lifting contact carries nothing
