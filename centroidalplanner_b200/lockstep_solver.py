@@ -442,7 +442,8 @@ class LockStepInteriorPoint:
             n_back = torch.log2((a_p / alpha.clamp(min=1e-300)).clamp(min=1.0)).round()
             n_back = torch.where(pol, torch.ones_like(n_back), n_back)
             delta_lm = torch.where(active & (n_back >= 2), torch.clamp(delta_last * 8.0, min=1e-6),
-                                   torch.where(active & (n_back == 0), delta_last / 4.0, delta_last))
+                                   torch.where(active & (n_back >= 1), torch.clamp(delta_last * 2.0, min=1e-6),
+                                               torch.where(active, delta_last / 4.0, delta_last)))
             delta_lm = torch.where(delta_lm < 1e-12, torch.zeros_like(delta_lm), delta_lm).clamp(max=1.0)
             failed = ~accepted           # search exhausted: take the last (tiny) step
             if bool(failed.any()):
