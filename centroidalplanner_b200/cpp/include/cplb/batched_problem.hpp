@@ -11,7 +11,10 @@
 
 #include <array>
 #include <cstdint>
+#include <map>
 #include <memory>
+#include <ostream>
+#include <sstream>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -41,6 +44,63 @@ inline void check(cplb_status st)
     default: throw std::runtime_error(msg);
     }
 }
+
+namespace solver {
+
+// cpl::solver::ContactValues / Solution (include/CentroidalPlanner/Ifopt/Types.h:8-21): what CplProblem::GetSolution
+// hands back for one instance -- the only "wire format" the reference defines.
+struct ContactValues {
+    Vec3 force_value;
+    Vec3 position_value;
+    Vec3 normal_value;
+};
+
+struct Solution {
+    std::map<std::string, ContactValues> contact_values_map;  // std::map: sorted-name order, like the reference's
+    Vec3 com_sol;
+};
+
+namespace detail {
+// One 3-vector the way `os << v.transpose()` prints an Eigen::Vector3d with the default Eigen::IOFormat [M: Eigen's
+// print_matrix -- every coefficient formatted with the stream's own precision/flags, right-aligned to the widest one,
+// coefficients separated by one blank]
+inline void print_row(std::ostream& os, const Vec3& v)
+{
+    std::string txt[3];
+    size_t width = 0;
+    for (int i = 0; i < 3; i++) {
+        std::ostringstream one;
+        one.copyfmt(os);
+        one.width(0);
+        one << v[i];
+        txt[i] = one.str();
+        if (txt[i].size() > width) width = txt[i].size();
+    }
+    for (int i = 0; i < 3; i++) {
+        if (i) os << " ";
+        os << std::string(width - txt[i].size(), ' ') << txt[i];
+    }
+}
+}  // namespace detail
+
+// operator<<(std::ostream&, const Solution&) of src/CplProblem.cpp:319-346: CoM, then all forces, all positions, all
+// normals, each group in map (sorted-name) order
+inline std::ostream& operator<<(std::ostream& os, const Solution& sol)
+{
+    os << "CoM: ";
+    detail::print_row(os, sol.com_sol);
+    os << "\n";
+    const char* tag[3] = {"F_", "p_", "n_"};
+    for (int what = 0; what < 3; what++)
+        for (auto& elem : sol.contact_values_map) {
+            os << tag[what] + elem.first + ": ";
+            detail::print_row(os, what == 0 ? elem.second.force_value : what == 1 ? elem.second.position_value : elem.second.normal_value);
+            os << "\n";
+        }
+    return os;
+}
+
+}  // namespace solver
 
 namespace env {
 
@@ -236,6 +296,23 @@ public:
     double GetMu() const { return (_env ? _env : env::EnvironmentClass::Ptr(_ground_fake))->GetMu(); }
     void SetForceThreshold(const std::string& n, double t) { check(cplb_set_force_threshold(_p, n.c_str(), t)); }
     double GetForceThreshold(const std::string& n) const { double t; check(cplb_get_force_threshold(_p, n.c_str(), &t)); return t; }
+
+    // CplProblem::GetSolution (src/CplProblem.cpp:85-106) for one instance's x[n]: unpack by the column map
+    // (CoM 0..2; contact k of the caller's vector: F 3+9k, p +3, n +6) into the name-keyed map
+    void GetSolution(const double* x_i, solver::Solution& sol) const
+    {
+        for (int c = 0; c < 3; c++) sol.com_sol[c] = x_i[c];
+        for (size_t k = 0; k < _contact_names.size(); k++) {
+            const double* b = x_i + 3 + 9 * k;
+            solver::ContactValues v;
+            for (int c = 0; c < 3; c++) {
+                v.force_value[c] = b[c];
+                v.position_value[c] = b[3 + c];
+                v.normal_value[c] = b[6 + c];
+            }
+            sol.contact_values_map[_contact_names[k]] = v;
+        }
+    }
 
     // ---- evaluation (host buffers, instance-major: instance i owns x[i*n..], g[i*m..], jac[i*nnz..]) ----
     // per_instance: optional per-instance parameter arrays (host pointers, instance-major), nullptr = shared parameters

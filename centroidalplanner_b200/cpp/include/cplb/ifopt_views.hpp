@@ -369,6 +369,10 @@ public:
     void SetPosBounds(const std::string& n, const Eigen::Vector3d& lb, const Eigen::Vector3d& ub) { _vars.at(n)[1]->SetBounds(lb, ub); }
     void SetNormalBounds(const std::string& n, const Eigen::Vector3d& lb, const Eigen::Vector3d& ub) { _vars.at(n)[2]->SetBounds(lb, ub); }
 
+    // CplProblem::GetSolution (src/CplProblem.cpp:85-106): this instance's current variables -- after a solve, what
+    // IpoptAdapter::finalize_solution wrote back through SetVariables
+    void GetSolution(Solution& sol) const { _batch->problem()->GetSolution(_batch->x(_i), sol); }
+
 private:
     InstanceBatch::Ptr _batch;
     int64_t _i;

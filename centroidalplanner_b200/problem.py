@@ -448,6 +448,20 @@ class BatchedCplProblem:
                                   "normal_value": x_i[b + 6:b + 9].copy()}
         return {"com_sol": x_i[0:3].copy(), "contact_values_map": cv}
 
+    @staticmethod
+    def FormatSolution(sol):
+        """`std::cout << sol` (operator<< of src/CplProblem.cpp:319-346): CoM, then every F_, p_, n_ line in map order.
+        Vectors print like an Eigen row with the default IOFormat [M]: '%g' coefficients right-aligned to the widest."""
+        def row(v):
+            txt = ["%g" % float(c) for c in v]
+            w = max(len(t) for t in txt)
+            return " ".join(t.rjust(w) for t in txt)
+
+        lines = ["CoM: " + row(sol["com_sol"])]
+        for tag, key in (("F_", "force_value"), ("p_", "position_value"), ("n_", "normal_value")):
+            lines += [tag + name + ": " + row(v[key]) for name, v in sol["contact_values_map"].items()]
+        return "\n".join(lines) + "\n"
+
     # ---- measurement helpers -----------------------------------------------------------------
     def launch_count(self):
         v = C.c_int64()

@@ -270,6 +270,32 @@ def test_header_is_valid_c99_and_usable_from_plain_c(tmp_path):
     assert r.returncode == 0 and "C ABI ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
 
 
+def test_solution_extraction_and_printing_cpp_vs_python(tmp_path):
+    """CplProblem::GetSolution + operator<<(Solution) (src/CplProblem.cpp:85-106, 319-346): the C++ facade and the Python
+    mirror unpack x by the same column map into sorted-name order and print the same text."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++") or "g++"
+    exe = str(tmp_path / "solution_check")
+    pkg = os.path.join(ROOT, "centroidalplanner_b200")
+    subprocess.check_call([gxx, "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(pkg, "cpp", "include"), os.path.join(ROOT, "tests", "native", "solution_check.cpp"),
+                           "-o", exe, "-L", pkg, "-lcplb", f"-Wl,-rpath,{pkg}"])
+    names = ["r_foot", "l_foot", "r_hand"]
+    prob = cpl.BatchedCplProblem(names, 100.0, cpl.Ground())
+    x = np.array([0.0401, 0.01695, 0.99591] + [34.78973, -69.5, 156.02521, 0.09298, -0.03415, 0.1, 0.0, 0.0, 1.0]
+                 + [-106.8, 1e-7, 345.35119, -0.23352, 0.20405, 0.1, -0.0, 0.0, 1.0] + [1234567.0, 2.5, 1.0 / 3.0, 0.14, -0.06, 0.1, 0.6, 0.0, 0.8])
+    r = subprocess.run([exe] + [repr(float(v)) for v in x], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    sol = prob.GetSolution(x)
+    assert list(sol["contact_values_map"]) == ["l_foot", "r_foot", "r_hand"]
+    assert r.stdout == prob.FormatSolution(sol)
+    assert r.stdout.splitlines()[0] == "CoM:  0.0401 0.01695 0.99591"
+    assert r.stdout.splitlines()[1] == "F_l_foot:  -106.8   1e-07 345.351"          # l_foot is the SECOND name of the caller's vector
+    assert r.stdout.splitlines()[3] == "F_r_hand: 1.23457e+06         2.5    0.333333"
+
+
 def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
     """No silent fallback: without libcplb.so the package cannot create a problem at all."""
     monkeypatch.setattr(_cabi, "_lib", None)
