@@ -10,6 +10,7 @@
 //      (cp.async.bulk, TMA unit) into shared memory, the lanes scatter their results into shared
 //      memory tiles laid out exactly like the output slices, and the tiles leave with bulk async
 //      stores -- HBM only ever sees full, contiguous, 16-byte aligned bursts.
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -540,8 +541,17 @@ static cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned
     // shared-parameter batches of the two benchmark shapes, once they are large enough: one thread per instance.
     // Measured crossovers (B200): nc = 4: 88 % (split) vs 80 % (whole) at 65,536 but 89 % vs 95 % at 98,304;
     // nc = 8: 90.5 % vs 95 % already at 65,536.  Both reach 97-98 % at 1,048,576 (split: 95 %).
+    // Superquadric with 8 contacts stays with the split kernel at every size: one thread holding 75 inputs plus the
+    // closed-form normal Jacobian needs 250 registers and 320 B of local memory (2 CTAs per SM) and measures 64-65 % of the
+    // roofline at 65,536 and 1,048,576 instances (profiles/r01_variants.md).
     const long long whole_from = P.nc == 4 ? 90112 : 49152;
-    if (!Q && io.N >= whole_from && (P.nc == 4 || P.nc == 8)) {
+    static const int forced = [] {  // CPLB_CM_KERNEL=split|whole: dispatch experiments only (tools/variant_table.py)
+        const char* e = std::getenv("CPLB_CM_KERNEL");
+        return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'w' ? 2 : 0));
+    }();
+    const bool whole_ok = !Q && (P.nc == 4 || P.nc == 8);
+    const bool whole_auto = io.N >= whole_from && !(ENV == CPLB_ENV_SUPERQUADRIC_K && P.nc == 8);
+    if (whole_ok && (forced == 2 || (forced == 0 && whole_auto))) {
         const unsigned wb = (unsigned)((io.N + 127) / 128);
         if (P.nc == 4) {
             if ((flags & 15u) == gj) return launch_pdl(eval_component_major_whole<ENV, 4, gj>, wb, 128u, 0, st, P, io, flags);
