@@ -360,7 +360,8 @@ __device__ __forceinline__ void warp_copy(double* dst, const double* src, int co
 template <int ENV, int LPI, int WARPS, unsigned FLAGS, bool PERINST>
 __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_constant__ CplbParams P, const CplbIo io,
                                                                    const unsigned flags_rt, const int aligned16,
-                                                                   const __grid_constant__ CplbInstParams Q)
+                                                                   const __grid_constant__ CplbInstParams Q,
+                                                                   const __grid_constant__ CplbParamTile PT)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
@@ -374,9 +375,11 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
     long long tile = (long long)blockIdx.x * WARPS + warp;
     if (tile >= tiles) return;  // whole warp leaves together
 
-    const size_t per_warp = tile_doubles(T, n, m, nnz, flags);
+    const int ptot = PERINST ? PT.total : 0;  // staged per-instance parameter slices, double-buffered like x
+    const size_t per_warp = tile_doubles(T, n, m, nnz, flags) + 2 * (size_t)ptot;
     double* xbuf = reinterpret_cast<double*>(smem_raw) + (size_t)warp * per_warp;
-    double* cur = xbuf + 2 * (size_t)T * n;
+    double* pbuf = xbuf + 2 * (size_t)T * n;
+    double* cur = pbuf + 2 * (size_t)ptot;
     double* gs = nullptr;
     double* js = nullptr;
     double* grads = nullptr;
@@ -390,15 +393,26 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
     const uint32_t xbytes = (uint32_t)(T * n * sizeof(double));
     // bulk copies need 16-byte aligned addresses and sizes: full tiles of 16B-aligned buffers only
     auto is_bulk = [&](long long t) { return aligned16 && (t + 1) * T <= io.N; };
+    const double* const parr[CPLB_NUM_INST_ARRAYS] = {Q.mass, Q.wrench, Q.mu, Q.F_thr, Q.ground_z, Q.com_ref, Q.W_com,
+                                                       Q.p_ref, Q.F_ref, Q.W_p, Q.W_F};
+    // one elected lane: x tile + every staged parameter slice of tile t into buffer `buf`, all on one mbarrier
+    auto issue_loads = [&](long long t, int buf) {
+        mbar_expect_tx(&bar[buf], xbytes + (uint32_t)(ptot * sizeof(double)));
+        bulk_g2s(xbuf + (size_t)buf * T * n, io.x + t * T * n, xbytes, &bar[buf]);
+        if (PERINST) {
+#pragma unroll
+            for (int a = 0; a < CPLB_NUM_INST_ARRAYS; a++)
+                if (PT.off[a] >= 0)
+                    bulk_g2s(pbuf + (size_t)buf * ptot + PT.off[a], parr[a] + t * T * PT.len[a],
+                             (uint32_t)(T * PT.len[a] * sizeof(double)), &bar[buf]);
+        }
+    };
 
     if (lane == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_proxy_async_smem();
-        if (is_bulk(tile)) {
-            mbar_expect_tx(&bar[0], xbytes);
-            bulk_g2s(xbuf, io.x + tile * T * n, xbytes, &bar[0]);
-        }
+        if (is_bulk(tile)) issue_loads(tile, 0);
     }
     __syncwarp();
     if (flags_rt & CPLB_INPUTS_READY) pdl_wait();  // the first tile's x is already on its way; nothing is stored before this
@@ -416,13 +430,19 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
         const long long next = tile + stride;
         if (lane == 0 && next < tiles && is_bulk(next)) {
             fence_proxy_async_smem();
-            mbar_expect_tx(&bar[b ^ 1], xbytes);
-            bulk_g2s(xbuf + (size_t)(b ^ 1) * T * n, io.x + next * T * n, xbytes, &bar[b ^ 1]);
+            issue_loads(next, b ^ 1);
         }
+        const double* ptile = pbuf + (size_t)b * ptot;
         if (bulk) {
             mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
         } else {
             warp_copy(xs, io.x + i0 * n, cnt * n, lane);
+            if (PERINST) {
+#pragma unroll
+                for (int a = 0; a < CPLB_NUM_INST_ARRAYS; a++)
+                    if (PT.off[a] >= 0)
+                        warp_copy(pbuf + (size_t)b * ptot + PT.off[a], parr[a] + i0 * PT.len[a], cnt * PT.len[a], lane);
+            }
         }
         // the output tiles are about to be overwritten: the engine must have finished reading the previous ones
         if (stores_in_flight) {
@@ -432,12 +452,13 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
         __syncwarp();
 
         // ---- compute: lane (inst, s) handles contacts s, s+LPI, ... and statics rows s, s+LPI, ... ----
-        if (inst < cnt) {
+        // The body is instantiated per parameter source: shared block, staged per-instance tiles, or per-instance arrays read
+        // with read-only global loads (kept free of any shared-memory alternative so that the compiler can hoist and batch them).
+        auto compute_instance = [&](const auto& ps) {
             const double* xi = xs + (size_t)inst * n;
             TileEmitter em{gs ? gs + (size_t)inst * m : nullptr, js ? js + (size_t)inst * nnz : nullptr,
                            grads ? grads + (size_t)inst * n : nullptr};
             const double c[3] = {xi[0], xi[1], xi[2]};
-            const auto ps = ParamSource<PERINST, false>::make(P, Q, i0 + inst, 0);
             for (int j = s; j < nc; j += LPI) {
                 const int k = P.perm[j];
                 const double* xk = xi + 3 + 9 * k;
@@ -495,6 +516,16 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
 #pragma unroll
                     for (int q = 0; q < 3; q++) em.grad(q, ps.W_com() * (c[q] - ps.com_ref(q)));
                 }
+            }
+        };
+        if (inst < cnt) {
+            if constexpr (PERINST) {
+                if (ptot)
+                    compute_instance(TileInstanceParams{P, Q, PT, ptile, inst});
+                else
+                    compute_instance(InstanceParams<false>{P, Q, i0 + inst, 0});
+            } else {
+                compute_instance(SharedParams{P});
             }
         }
 
@@ -591,7 +622,7 @@ cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsign
 
 template <int ENV, int LPI, int WARPS, unsigned FLAGS, bool PERINST>
 static cudaError_t launch_im_kernel(const CplbParams& P, const CplbIo& io, unsigned flags, size_t smem, const CplbInstParams* Q,
-                                    cudaStream_t st)
+                                    const CplbParamTile& PT, cudaStream_t st)
 {
     constexpr int T = 32 / LPI;
     auto kern = eval_instance_major<ENV, LPI, WARPS, FLAGS, PERINST>;
@@ -617,24 +648,63 @@ static cudaError_t launch_im_kernel(const CplbParams& P, const CplbIo& io, unsig
     const long long want = (tiles + WARPS - 1) / WARPS;
     const unsigned blocks = (unsigned)(want < cfg.resident ? want : cfg.resident);
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    const int aligned16 = al16(io.x) && al16(io.g) && al16(io.jac) && al16(io.grad) && (T % 2 == 0);
-    return launch_pdl(kern, blocks, WARPS * 32, smem, st, P, io, flags, aligned16, Q ? *Q : kNoInstParams);
+    int aligned16 = al16(io.x) && al16(io.g) && al16(io.jac) && al16(io.grad) && (T % 2 == 0);
+    if (Q) {
+        const double* const parr[CPLB_NUM_INST_ARRAYS] = {Q->mass, Q->wrench, Q->mu, Q->F_thr, Q->ground_z, Q->com_ref, Q->W_com,
+                                                           Q->p_ref, Q->F_ref, Q->W_p, Q->W_F};
+        for (int a = 0; a < CPLB_NUM_INST_ARRAYS; a++)
+            if (PT.off[a] >= 0) aligned16 = aligned16 && al16(parr[a]);
+    }
+    return launch_pdl(kern, blocks, WARPS * 32, smem, st, P, io, flags, aligned16, Q ? *Q : kNoInstParams, PT);
+}
+
+// Which per-instance arrays the instance-major kernel stages for the requested outputs, and where (CplbParamTile).
+static CplbParamTile make_param_tile(const CplbParams& P, const CplbInstParams* Q, unsigned flags, int T)
+{
+    CplbParamTile PT = {};
+    const int nc = P.nc;
+    const int lens[CPLB_NUM_INST_ARRAYS] = {1, 6, 1, nc, 1, 3, 1, 3 * nc, 3 * nc, nc, nc};
+    for (int a = 0; a < CPLB_NUM_INST_ARRAYS; a++) {
+        PT.off[a] = -1;
+        PT.len[a] = lens[a];
+    }
+    if (!Q) return PT;
+    const double* const parr[CPLB_NUM_INST_ARRAYS] = {Q->mass, Q->wrench, Q->mu, Q->F_thr, Q->ground_z, Q->com_ref, Q->W_com,
+                                                       Q->p_ref, Q->F_ref, Q->W_p, Q->W_F};
+    // Staged for constraint-only evaluations: what the constraint rows read (9 + nc doubles per instance; measured 55 -> 61 %
+    // of the roofline at 65,536 x 4 contacts, 69 -> 75 % at 1,048,576).  With the cost or the gradient requested nothing is
+    // staged and every array is read with read-only global loads as before: that variant is bound by the cost lane's
+    // critical path and by resident warps, and both staging everything (39 %) and staging only the constraint arrays (32 %)
+    // measured below the plain loads (43 %).
+    // Ground problems only: without an environment the extra 1.5 KB per warp costs a resident CTA (59 vs 53 KB: 70 -> 62 % at
+    // 1,048,576 x 4 contacts) and the Superquadric rows are bound by their arithmetic (48 vs 45 %, 51 vs 52 %).
+    if (flags & (CPLB_WANT_COST | CPLB_WANT_GRAD)) return PT;
+    if (P.env != CPLB_ENV_GROUND_K) return PT;
+    const bool GJ = flags & (CPLB_WANT_G | CPLB_WANT_J), C = false;
+    const bool need[CPLB_NUM_INST_ARRAYS] = {GJ, GJ, GJ, GJ, GJ && P.env == CPLB_ENV_GROUND_K, C, C, C, C, C, C};
+    for (int a = 0; a < CPLB_NUM_INST_ARRAYS; a++)
+        if (parr[a] && need[a]) {
+            PT.off[a] = PT.total;
+            PT.total += T * lens[a];
+        }
+    return PT;
 }
 
 template <int ENV, int LPI>
 static cudaError_t launch_im_cfg(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
     constexpr int T = 32 / LPI;
-    const size_t per_warp = tile_doubles(T, P.n, P.m, P.nnz, flags & 15u) * sizeof(double) + 2 * sizeof(uint64_t);
+    const CplbParamTile PT = make_param_tile(P, Q, flags & 15u, T);
+    const size_t per_warp = (tile_doubles(T, P.n, P.m, P.nnz, flags & 15u) + 2 * (size_t)PT.total) * sizeof(double) + 2 * sizeof(uint64_t);
     const unsigned gj = CPLB_WANT_G | CPLB_WANT_J;
     if (4 * per_warp <= 72 * 1024) {  // the common shapes: 4 warps per CTA, 3 CTAs per SM
-        if (Q) return launch_im_kernel<ENV, LPI, 4, 0u, true>(P, io, flags, 4 * per_warp, Q, st);
-        if ((flags & 15u) == gj) return launch_im_kernel<ENV, LPI, 4, gj, false>(P, io, flags, 4 * per_warp, Q, st);
-        return launch_im_kernel<ENV, LPI, 4, 0u, false>(P, io, flags, 4 * per_warp, Q, st);
+        if (Q) return launch_im_kernel<ENV, LPI, 4, 0u, true>(P, io, flags, 4 * per_warp, Q, PT, st);
+        if ((flags & 15u) == gj) return launch_im_kernel<ENV, LPI, 4, gj, false>(P, io, flags, 4 * per_warp, Q, PT, st);
+        return launch_im_kernel<ENV, LPI, 4, 0u, false>(P, io, flags, 4 * per_warp, Q, PT, st);
     }
     if (per_warp > 227 * 1024) return cudaErrorInvalidConfiguration;
-    if (Q) return launch_im_kernel<ENV, LPI, 1, 0u, true>(P, io, flags, per_warp, Q, st);
-    return launch_im_kernel<ENV, LPI, 1, 0u, false>(P, io, flags, per_warp, Q, st);  // many contacts: one warp per CTA
+    if (Q) return launch_im_kernel<ENV, LPI, 1, 0u, true>(P, io, flags, per_warp, Q, PT, st);
+    return launch_im_kernel<ENV, LPI, 1, 0u, false>(P, io, flags, per_warp, Q, PT, st);  // many contacts: one warp per CTA
 }
 
 template <int ENV>

@@ -67,6 +67,16 @@ struct CplbInstParams {
     const double* W_F;       // nc
 };
 
+// Instance-major kernel, per-instance parameter mode: where each staged parameter array's slice of a warp tile sits in the
+// shared-memory parameter buffer (doubles from the buffer start; -1 = not staged: absent, or not needed by the requested
+// outputs).  Array order = the member order of CplbInstParams.
+#define CPLB_NUM_INST_ARRAYS 11
+struct CplbParamTile {
+    int off[CPLB_NUM_INST_ARRAYS];
+    int len[CPLB_NUM_INST_ARRAYS];  // doubles per instance of each array
+    int total;                      // doubles per buffer (one warp tile)
+};
+
 // Pointers of one evaluation (device memory), see cplb_eval_args in include/cpl_batched.h.
 struct CplbIo {
     const double* x;
