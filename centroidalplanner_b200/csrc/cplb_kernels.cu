@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
         // ---- compute: lane (inst, s) handles contacts s, s+LPI, ... and statics rows s, s+LPI, ... ----
         // The body is instantiated per parameter source: shared block, staged per-instance tiles, or per-instance arrays read
         // with read-only global loads (kept free of any shared-memory alternative so that the compiler can hoist and batch them).
+        const unsigned live = __ballot_sync(0xffffffffu, inst < cnt);  // lanes that hold an instance of this tile (shuffle mask)
         auto compute_instance = [&](const auto& ps) {
             const double* xi = xs + (size_t)inst * n;
             TileEmitter em{gs ? gs + (size_t)inst * m : nullptr, js ? js + (size_t)inst * nnz : nullptr,
@@ -499,19 +500,32 @@ __global__ void __launch_bounds__(WARPS * 32) eval_instance_major(const __grid_c
                     }
                 }
             }
-            if (s == 0) {
-                if (flags & CPLB_WANT_COST) {  // MinimizeCentroidalVariables.cpp:126-147, sorted order
-                    double cost = 0.0;
-                    for (int j = 0; j < nc; j++) {
+            if (flags & CPLB_WANT_COST) {  // MinimizeCentroidalVariables.cpp:126-147, sorted order
+                // every lane evaluates the terms of its own contacts; lane 0 of the instance collects them with shuffles
+                // in sorted order j = 0, 1, ... -- the same running sum as the reference's loop (0.0 + t0 is exact)
+                double cost = 0.0;
+                for (int r = 0; r * LPI < nc; r++) {
+                    const int j = r * LPI + s;
+                    double t = 0.0;
+                    if (j < nc) {
                         const int k = P.perm[j];
                         const double* xk = xi + 3 + 9 * k;
                         const double F[3] = {xk[0], xk[1], xk[2]};
                         const double p[3] = {xk[3], xk[4], xk[5]};
-                        cost += contact_cost(ps, P.reduction_order, k, F, p);
+                        t = contact_cost(ps, P.reduction_order, k, F, p);
                     }
+#pragma unroll
+                    for (int q = 0; q < LPI; q++) {
+                        const double tq = __shfl_sync(live, t, inst * LPI + q);
+                        if (r * LPI + q < nc) cost += tq;
+                    }
+                }
+                if (s == 0) {
                     cost += com_cost(ps, P.reduction_order, c);
                     costs[inst] = cost;
                 }
+            }
+            if (s == 0) {
                 if (flags & CPLB_WANT_GRAD) {
 #pragma unroll
                     for (int q = 0; q < 3; q++) em.grad(q, ps.W_com() * (c[q] - ps.com_ref(q)));
