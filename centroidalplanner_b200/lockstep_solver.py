@@ -211,7 +211,6 @@ class LockStepInteriorPoint:
         x_lo_f, x_hi_f, s_lo_f, s_hi_f = x_lo.to(f64), x_hi.to(f64), s_lo.to(f64), s_hi.to(f64)
         delta_last = torch.zeros(N, dtype=f64, device=dev)
         delta_lm = torch.zeros(N, dtype=f64, device=dev)
-        soc_used = torch.zeros(N, dtype=torch.int64, device=dev)
         polish = torch.zeros(N, dtype=torch.bool, device=dev)
         eyeK = torch.eye(n + m, dtype=f64, device=dev)
 
@@ -430,7 +429,6 @@ class LockStepInteriorPoint:
                     x_new = torch.where(takec[:, None], xc, x_new)
                     s_new = torch.where(takec[:, None], stc, s_new)
                     dlam_used = torch.where(takec[:, None], dlam_c, dlam_used)
-                    soc_used = soc_used + takec.to(torch.int64)
                     accepted = accepted | takec
                     if bool(accepted.all()):
                         break

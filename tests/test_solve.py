@@ -250,3 +250,28 @@ def test_com_planner_facade_solve(cuda_device):
     assert np.abs(F_sum - [0.0, 0.0, -MASS * G]).max() < 1e-6
     assert np.abs(T_sum).max() < 1e-4
     assert np.abs(sol["contact_values_map"]["contact4"]["force_value"]).max() == 0.0   # lifting contact carries nothing
+
+
+@pytest.mark.gpu
+def test_instances_that_are_different_problems(cuda_device):
+    """INTEGRATION §4b through the solve driver: every instance has its own manipulation wrench and robot mass (per-instance
+    parameter arrays forwarded to every evaluation, including the widened Hessian-difference launches); each solution must
+    balance ITS wrench and weight (the equilibrium lines of TEST_F testGroundEnv, tests/TestBasic.cpp:131-136)."""
+    prob, names, par = product_problem("ground")
+    N = 48
+    rng = np.random.default_rng(5)
+    wrench = np.tile(par["wrench"], (N, 1)) + rng.normal(0.0, 20.0, (N, 6)) * np.array([1, 1, 1, 0.2, 0.2, 1.0])
+    mass = rng.uniform(60.0, 140.0, N)
+    per_instance = {"wrench": torch.as_tensor(wrench, device=cuda_device), "mass": torch.as_tensor(mass, device=cuda_device)}
+    x0 = starts(prob, N, seed=3, device=cuda_device)
+    res = LockStepInteriorPoint().Solve(prob, x0, per_instance=per_instance)
+    assert (res.status == SUCCESS).all(), (res.status.tolist(), res.iterations.tolist())
+    for i, (com, cmap) in enumerate(solution_maps(names, res.x.cpu().numpy())):
+        F_sum, T_sum = np.zeros(3), np.zeros(3)
+        for F, p, n in cmap.values():
+            F_sum += F
+            T_sum += np.cross(p - com, F)
+            assert abs(p[2] - par["ground_z"]) < 1e-6 and abs(n[2] - 1.0) < 1e-6
+            assert -F.dot(n) <= RELAX and np.linalg.norm(F - n.dot(F) * n) - par["mu"] * F.dot(n) <= RELAX
+        assert np.abs(F_sum - (wrench[i, :3] - mass[i] * np.array([0.0, 0.0, G]))).max() < 1e-6
+        assert np.abs(T_sum - wrench[i, 3:]).max() < 1e-5
