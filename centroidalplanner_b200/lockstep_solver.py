@@ -239,6 +239,14 @@ class LockStepInteriorPoint:
                                 ((gsl * vsl - mu_t[:, None]) * s_lo_f).abs().amax(1), ((gsu * vsu - mu_t[:, None]) * s_hi_f).abs().amax(1)]).amax(0) / sd
             return dual, prim, comp
 
+        eq_f = is_eq.to(f64)
+        cu_s, cl_s = dc * cu, dc * cl                     # scaled ORIGINAL row bounds (sl / su are the relaxed ones)
+
+        def polish_residual(cc):
+            """What the feasibility polish drives to zero: equality residuals and excess over the original inequality bounds."""
+            exc = torch.clamp(cc - cu_s, min=0.0) * s_hi_f + torch.clamp(cl_s - cc, min=0.0) * s_lo_f
+            return torch.maximum(((cc - sl) * eq_f).abs().amax(1), exc.amax(1))
+
         def reset_slack(st, ct, mu, nu):
             """Slack reset (Nocedal & Wright 2006, §19.3): for the x just tried, the slack of a one-sided row that minimises
             barrier + penalty is the constraint value itself, kept mu/nu away from its bound."""
@@ -365,12 +373,16 @@ class LockStepInteriorPoint:
             merit0 = phi0 + nu * h1
             pol = active & polish
             if bool(pol.any()):
-                # feasibility polish: minimum-norm Newton step on the equality rows, x only (multipliers stay)
-                eq_f = is_eq.to(f64)
-                Je = Jf * eq_f[None, :, None]
-                M = Je @ Je.transpose(1, 2) + torch.diag_embed((1.0 - eq_f).expand(N, m) + 1e-14)
+                # feasibility polish: minimum-norm Newton step, x only (multipliers stay), on the equality rows and on the
+                # inequality rows that sit beyond their ORIGINAL bound (pulled back onto it; the relaxed bound is the test)
+                over = ineq & s_hi & (c > cu_s)
+                under = ineq & s_lo & (c < cl_s)
+                act_f = (is_eq | over | under).to(f64)
+                r_p = torch.where(over, c - cu_s, torch.where(under, c - cl_s, (c - sl) * eq_f))
+                Je = Jf * act_f[:, :, None]
+                M = Je @ Je.transpose(1, 2) + torch.diag_embed((1.0 - act_f) + 1e-14)
                 M = torch.where(torch.isfinite(M).all(2).all(1)[:, None, None], M, torch.eye(m, dtype=f64, device=dev))
-                y = torch.linalg.solve(M, (h * eq_f)[:, :, None])
+                y = torch.linalg.solve(M, r_p[:, :, None])
                 dx_p = -(Je.transpose(1, 2) @ y)[:, :, 0] * free_f
                 dx_p = torch.where(torch.isfinite(dx_p).all(1)[:, None], dx_p, torch.zeros_like(dx_p))
                 a_pp = torch.stack([max_step(gxl, dx_p, x_lo_f), max_step(gxu, -dx_p, x_hi_f)]).amin(0).clamp(max=1.0)
@@ -379,7 +391,7 @@ class LockStepInteriorPoint:
                 dlam = torch.where(pol[:, None], torch.zeros_like(dlam), dlam)
                 a_p = torch.where(pol, a_pp, a_p)
                 a_d = torch.where(pol, torch.zeros_like(a_d), a_d)
-            hE0 = (h * is_eq.to(f64)).abs().amax(1)
+            R0 = polish_residual(c)
             alpha = torch.where(active, a_p, torch.zeros_like(a_p))
             tiny = (dx.abs() / (1.0 + x.abs())).amax(1) < 1e-13          # tiny_step_tol: below rounding the merit test is noise
             accepted = ~active
@@ -396,7 +408,7 @@ class LockStepInteriorPoint:
                 # equality residual shrinks
                 inside = (~s_lo | (ct > sl)) & (~s_hi | (ct < su))
                 st_p = torch.where(ineq & inside, ct, s)
-                ok_p = torch.isfinite(ct).all(1) & (((ct - st_p) * is_eq.to(f64)).abs().amax(1) < hE0)
+                ok_p = torch.isfinite(ct).all(1) & (polish_residual(ct) < R0)
                 st = torch.where(pol[:, None], st_p, st)
                 ok = torch.where(pol, ok_p, ok)
                 return ok, st, ct
