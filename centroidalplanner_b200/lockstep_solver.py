@@ -61,7 +61,7 @@ class LockStepInteriorPoint:
 
     def __init__(self, tol=1e-3, max_iter=500, mu_init=0.1, bound_push=1e-2, bound_frac=1e-2,
                  nlp_scaling_max_gradient=100.0, constr_viol_tol=1e-4, polish_viol_tol=1e-9, bound_relax_factor=1e-8,
-                 max_backtracks=30, verbose=False):
+                 max_backtracks=30, compact=True, compact_min=64, verbose=False):
         self.tol = float(tol)
         self.max_iter = int(max_iter)
         self.mu_init = float(mu_init)
@@ -72,6 +72,8 @@ class LockStepInteriorPoint:
         self.polish_viol_tol = float(polish_viol_tol)
         self.bound_relax = float(bound_relax_factor)
         self.max_backtracks = int(max_backtracks)
+        self.compact = bool(compact)
+        self.compact_min = int(compact_min)
         self.verbose = verbose
 
     # ---- helpers -----------------------------------------------------------------------------------------------
@@ -151,11 +153,15 @@ class LockStepInteriorPoint:
             out = on_dev(problem.eval(xx, g=True, jac=True, cost=True, grad=True, **kw1))
             return out["cost"], torch.where(fixed, torch.zeros_like(out["grad"]), out["grad"]), out["g"], dense(out["jac"], N)
 
-        def trial_eval(xx):
+        kw_rep = {1: kw1}
+
+        def trial_eval(xx, K=1):
             nonlocal evaluations, instance_evals
             evaluations += 1
-            instance_evals += N
-            out = on_dev(problem.eval(xx, g=True, jac=False, cost=True, grad=False, **kw1))
+            instance_evals += N * K
+            if K not in kw_rep:
+                kw_rep[K] = repeat_params(K)
+            out = on_dev(problem.eval(xx, g=True, jac=False, cost=True, grad=False, **kw_rep[K]))
             return out["cost"], out["g"]
 
         f, df, c, J = full_eval(x)
@@ -226,7 +232,11 @@ class LockStepInteriorPoint:
             lb = (torch.log(gxl) * x_lo_f + torch.log(gxu) * x_hi_f).sum(1) + (torch.log(gsl) * s_lo_f + torch.log(gsu) * s_hi_f).sum(1)
             return f - mu * lb
 
-        def errors(df, c, J, s, lam, vxl, vxu, vsl, vsu, x, mu_t):
+        comp_mask = torch.cat([x_lo_f, x_hi_f, s_lo_f, s_hi_f])
+
+        def kkt_residuals(df, c, J, s, lam, vxl, vxu, vsl, vsu, x):
+            """Scaled optimality error of Waechter & Biegler eq. (5) without its mu-dependent part: dual and primal
+            infeasibility, the multiplier scaling s_d, and the gap x multiplier products the complementarity error is made of."""
             gxl, gxu, gsl, gsu = gaps(x, s)
             rx = (df + torch.einsum("nij,ni->nj", J, lam) - vxl + vxu) * free_f
             rs = (-lam - vsl + vsu) * ineq_f
@@ -235,9 +245,11 @@ class LockStepInteriorPoint:
             sd = torch.clamp((lam.abs().sum(1) + vxl.sum(1) + vxu.sum(1) + vsl.sum(1) + vsu.sum(1)) / nmul, min=100.0) / 100.0
             dual = torch.maximum(rx.abs().amax(1), rs.abs().amax(1)) / sd
             prim = h.abs().amax(1)
-            comp = torch.stack([((gxl * vxl - mu_t[:, None]) * x_lo_f).abs().amax(1), ((gxu * vxu - mu_t[:, None]) * x_hi_f).abs().amax(1),
-                                ((gsl * vsl - mu_t[:, None]) * s_lo_f).abs().amax(1), ((gsu * vsu - mu_t[:, None]) * s_hi_f).abs().amax(1)]).amax(0) / sd
-            return dual, prim, comp
+            prods = torch.cat([gxl * vxl, gxu * vxu, gsl * vsl, gsu * vsu], dim=1)
+            return dual, prim, sd, prods
+
+        def complementarity(prods, sd, mu_t):
+            return ((prods - mu_t[:, None]) * comp_mask).abs().amax(1) / sd
 
         eq_f = is_eq.to(f64)
         cu_s, cl_s = dc * cu, dc * cl                     # scaled ORIGINAL row bounds (sl / su are the relaxed ones)
@@ -247,20 +259,27 @@ class LockStepInteriorPoint:
             exc = torch.clamp(cc - cu_s, min=0.0) * s_hi_f + torch.clamp(cl_s - cc, min=0.0) * s_lo_f
             return torch.maximum(((cc - sl) * eq_f).abs().amax(1), exc.amax(1))
 
-        def reset_slack(st, ct, mu, nu):
-            """Slack reset (Nocedal & Wright 2006, §19.3): for the x just tried, the slack of a one-sided row that minimises
-            barrier + penalty is the constraint value itself, kept mu/nu away from its bound."""
-            keep = (mu / nu)[:, None]
-            up_only = s_hi & ~s_lo
-            lo_only = s_lo & ~s_hi
-            st = torch.where(up_only, torch.minimum(ct, su - keep), st)
-            st = torch.where(lo_only, torch.maximum(ct, sl + keep), st)
-            return st
+        N0 = N
+        orig = torch.arange(N0, device=dev)            # original index of every instance still in the working set
+        out = {"x": torch.empty(N0, n, dtype=f64, device=dev), "status": torch.empty(N0, dtype=torch.int64, device=dev),
+               "iters": torch.empty(N0, dtype=torch.int64, device=dev), "cost": torch.empty(N0, dtype=f64, device=dev),
+               "viol": torch.empty(N0, dtype=f64, device=dev), "dual": torch.empty(N0, dtype=f64, device=dev),
+               "lam": torch.empty(N0, m, dtype=f64, device=dev)}
+
+        def flush():
+            """Current state of the working set -> the full-size result buffers."""
+            out["x"][orig] = torch.minimum(torch.maximum(x, x_orig_lo), x_orig_hi)          # honor_original_bounds
+            out["status"][orig] = status
+            out["iters"][orig] = iters
+            out["cost"][orig] = f / dobj
+            out["viol"][orig] = ((torch.clamp(sl - c, min=0) + torch.clamp(c - su, min=0)) / dc).amax(1)
+            out["dual"][orig] = kkt_residuals(df, c, J, s, lam, vxl, vxu, vsl, vsu, x)[0]
+            out["lam"][orig] = lam * dc / dobj[:, None]
 
         rounds = 0
         for it in range(self.max_iter + 1):
-            zero_mu = torch.zeros_like(mu)
-            dual0, prim0, comp0 = errors(df, c, J, s, lam, vxl, vxu, vsl, vsu, x, zero_mu)
+            dual0, prim0, sd0, prods0 = kkt_residuals(df, c, J, s, lam, vxl, vxu, vsl, vsu, x)
+            comp0 = complementarity(prods0, sd0, torch.zeros_like(mu))
             E0 = torch.stack([dual0, prim0, comp0]).amax(0)
             viol = (torch.clamp(sl - c, min=0) + torch.clamp(c - su, min=0)) / dc                           # unscaled row violation (relaxed bounds)
             vmax = viol.amax(1)
@@ -276,15 +295,33 @@ class LockStepInteriorPoint:
                 i0 = 0
                 print(f"it {it:3d} active {int(active.sum()):5d} | inst0: f {float(f[i0] / dobj[i0]):.6e} prim {float(prim0[i0]):.2e} dual {float(dual0[i0]):.2e} "
                       f"comp {float(comp0[i0]):.2e} mu {float(mu[i0]):.1e}")
-            if not bool(active.any()) or it == self.max_iter:
+            n_active = int(active.sum())
+            if n_active == 0 or it == self.max_iter:
                 break
+            if self.compact and N >= self.compact_min and 2 * n_active <= N:
+                # Lock-step rounds cost the same whether an instance is still iterating or not: once half of the working set
+                # has finished, the finished ones are written out and dropped (instances are independent, so the others'
+                # iterates do not change).
+                flush()
+                keep = torch.nonzero(active).flatten()
+                (x, s, lam, vxl, vxu, vsl, vsu, mu, status, iters, delta_last, delta_lm, polish, f, df, c, J, dc, dobj, sl, su,
+                 cu_s, cl_s, orig, dual0, prim0, sd0, prods0, active) = (
+                    t[keep] for t in (x, s, lam, vxl, vxu, vsl, vsu, mu, status, iters, delta_last, delta_lm, polish, f, df, c, J,
+                                      dc, dobj, sl, su, cu_s, cl_s, orig, dual0, prim0, sd0, prods0, active))
+                N = n_active
+                if per_instance is not None:
+                    per_instance = {k: torch.as_tensor(v, device=dev)[keep] for k, v in per_instance.items()}
+                    kw1 = {"per_instance": per_instance}
+                    kwh = repeat_params(nf + 1)
+                    kw_rep.clear()
+                    kw_rep[1] = kw1
             rounds += 1
             iters += active.to(torch.int64)
 
             # monotone barrier update (Waechter & Biegler eq. 7): shrink mu while the barrier problem is solved to kappa_eps * mu
+            dp0 = torch.maximum(dual0, prim0)
             for _ in range(4):
-                d_mu, p_mu, c_mu = errors(df, c, J, s, lam, vxl, vxu, vsl, vsu, x, mu)
-                Emu = torch.stack([d_mu, p_mu, c_mu]).amax(0)
+                Emu = torch.maximum(dp0, complementarity(prods0, sd0, mu))
                 shrink = active & (Emu <= 10.0 * mu) & (mu > self.tol / 10.0)
                 mu = torch.where(shrink, torch.clamp(torch.minimum(0.2 * mu, mu ** 1.5), min=self.tol / 10.0), mu)
             tau = torch.clamp(1.0 - mu, min=0.99)
@@ -398,53 +435,91 @@ class LockStepInteriorPoint:
             x_new, s_new = x, s
             dlam_used = dlam
 
-            def try_point(xt, st_lin, al):
-                ft, ct = trial_eval(xt)
-                ft, ct = dobj * ft, dc * ct
-                st = reset_slack(st_lin, ct, mu, nu)
-                mt = barrier(ft, xt, st, mu) + nu * (ct - st).abs().sum(1)
-                ok = torch.isfinite(mt) & (mt <= merit0 + 1e-4 * al * Dm + 10.0 * 2.2e-16 * merit0.abs())
+            def try_points(X, S_lin, AL):
+                """Merit test of K candidate points per instance in ONE widened evaluation: X (N, K, n), S_lin (N, K, m) the
+                linearly stepped slacks, AL (N, K) the step lengths -> ok (N, K), slacks (N, K, m), row values (N, K, m)."""
+                K = X.shape[1]
+                ft, ct = trial_eval(X.reshape(N * K, n), K)
+                ft, ct = dobj[:, None] * ft.view(N, K), dc[:, None, :] * ct.view(N, K, m)
+                keep = (mu / nu)[:, None, None]
+                st = torch.where(s_hi & ~s_lo, torch.minimum(ct, su[:, None, :] - keep), S_lin)      # slack reset (Nocedal & Wright 2006, §19.3): the row value itself, mu/nu inside its bound
+                st = torch.where(s_lo & ~s_hi, torch.maximum(ct, sl[:, None, :] + keep), st)
+                gxl = torch.where(x_lo, X - xl, one)
+                gxu = torch.where(x_hi, xu - X, one)
+                gsl = torch.where(s_lo, st - sl[:, None, :], one)
+                gsu = torch.where(s_hi, su[:, None, :] - st, one)
+                lb = (torch.log(gxl) * x_lo_f + torch.log(gxu) * x_hi_f).sum(2) + (torch.log(gsl) * s_lo_f + torch.log(gsu) * s_hi_f).sum(2)
+                mt = (ft - mu[:, None] * lb) + nu[:, None] * (ct - st).abs().sum(2)
+                ok = torch.isfinite(mt) & (mt <= (merit0 + 10.0 * 2.2e-16 * merit0.abs())[:, None] + 1e-4 * AL * Dm[:, None])
                 # polishing instances: the slack of a strictly satisfied inequality row is the row value; accept when the
-                # equality residual shrinks
-                inside = (~s_lo | (ct > sl)) & (~s_hi | (ct < su))
-                st_p = torch.where(ineq & inside, ct, s)
-                ok_p = torch.isfinite(ct).all(1) & (polish_residual(ct) < R0)
-                st = torch.where(pol[:, None], st_p, st)
-                ok = torch.where(pol, ok_p, ok)
+                # polish residual shrinks
+                inside = (~s_lo | (ct > sl[:, None, :])) & (~s_hi | (ct < su[:, None, :]))
+                st_p = torch.where(ineq & inside, ct, s[:, None, :])
+                exc = torch.clamp(ct - cu_s[:, None, :], min=0.0) * s_hi_f + torch.clamp(cl_s[:, None, :] - ct, min=0.0) * s_lo_f
+                R_t = torch.maximum(((ct - sl[:, None, :]) * eq_f).abs().amax(2), exc.amax(2))
+                ok_p = torch.isfinite(ct).all(2) & (R_t < R0[:, None])
+                st = torch.where(pol[:, None, None], st_p, st)
+                ok = torch.where(pol[:, None], ok_p, ok)
                 return ok, st, ct
 
-            for _ls in range(self.max_backtracks):
-                xt = x + alpha[:, None] * dx
-                ok, st, ct = try_point(xt, s + alpha[:, None] * ds, alpha)
-                ok = ok | (tiny & torch.isfinite(ct).all(1))
-                take = ok & ~accepted
-                x_new = torch.where(take[:, None], xt, x_new)
-                s_new = torch.where(take[:, None], st, s_new)
-                accepted = accepted | ok
+            # Candidates alpha0 * 2^-k are tried four at a time (one widened launch instead of four round trips); the first
+            # acceptable one in the order full step, second-order correction, 1/2, 1/4, ... is taken, as a sequential
+            # backtracking search would.
+            KC = 4
+            scale = 0.5 ** torch.arange(KC, device=dev, dtype=f64)
+            base = alpha.clone()                                  # alpha0 * 2^-(4 g) of the current group
+            tried = 0
+            _ls = 0
+            while tried < self.max_backtracks:
+                AL = base[:, None] * scale[None, :]
+                X = x[:, None, :] + AL[:, :, None] * dx[:, None, :]
+                ok, st, ct = try_points(X, s[:, None, :] + AL[:, :, None] * ds[:, None, :], AL)
+                ok = ok | (tiny[:, None] & torch.isfinite(ct).all(2))
+                if tried + KC > self.max_backtracks:
+                    ok[:, self.max_backtracks - tried:] = False
+                if tried == 0:
+                    first_ok = ok[:, 0]
+                    take = first_ok & ~accepted
+                    x_new = torch.where(take[:, None], X[:, 0], x_new)
+                    s_new = torch.where(take[:, None], st[:, 0], s_new)
+                    accepted = accepted | first_ok
+                    if not bool(accepted.all()):
+                        # second-order correction (Waechter & Biegler 2006, §2.4): same matrix, constraint residual of the
+                        # rejected trial point added to the right-hand side -- removes the Maratos effect on the bilinear
+                        # moment rows and the friction cones
+                        h_soc = alpha[:, None] * h + (ct[:, 0] - (s + alpha[:, None] * ds))
+                        rhs_c = torch.cat([-r_x, -h_soc - D * r_s], dim=1)
+                        sol_c = torch.linalg.lu_solve(LU, piv, torch.where(okK[:, None], rhs_c, torch.zeros_like(rhs_c))[:, :, None])[:, :, 0]
+                        dx_c, dlam_c = sol_c[:, :n] * free_f, sol_c[:, n:]
+                        ds_c = (D * (dlam_c - r_s)) * ineq_f
+                        fin_c = torch.isfinite(sol_c).all(1)
+                        a_c = torch.stack([max_step(gxl, dx_c, x_lo_f), max_step(gxu, -dx_c, x_hi_f),
+                                           max_step(gsl, ds_c, s_lo_f), max_step(gsu, -ds_c, s_hi_f)]).amin(0).clamp(max=1.0)
+                        xc = torch.where(fin_c[:, None], x + a_c[:, None] * dx_c, x)
+                        okc, stc, _ = try_points(xc[:, None, :], (s + a_c[:, None] * ds_c)[:, None, :], alpha[:, None])
+                        takec = okc[:, 0] & fin_c & ~accepted & ~pol
+                        x_new = torch.where(takec[:, None], xc, x_new)
+                        s_new = torch.where(takec[:, None], stc[:, 0], s_new)
+                        dlam_used = torch.where(takec[:, None], dlam_c, dlam_used)
+                        accepted = accepted | takec
+                # the first acceptable candidate of this group (for the first group: among 1/2, 1/4, 1/8)
+                okg = ok.clone()
+                if tried == 0:
+                    okg[:, 0] = False
+                any_ok = okg.any(1)
+                kfirst = torch.argmax(okg.to(torch.int8), dim=1)
+                take = any_ok & ~accepted
+                idx = kfirst[:, None, None]
+                x_new = torch.where(take[:, None], torch.gather(X, 1, idx.expand(N, 1, n))[:, 0], x_new)
+                s_new = torch.where(take[:, None], torch.gather(st, 1, idx.expand(N, 1, m))[:, 0], s_new)
+                alpha = torch.where(take, torch.gather(AL, 1, kfirst[:, None])[:, 0], alpha)
+                accepted = accepted | any_ok
+                tried += KC
+                _ls = tried
                 if bool(accepted.all()):
                     break
-                if _ls == 0:
-                    # second-order correction (Waechter & Biegler 2006, §2.4): same matrix, constraint residual of the
-                    # rejected trial point added to the right-hand side -- removes the Maratos effect on the bilinear
-                    # moment rows and the friction cones
-                    h_soc = alpha[:, None] * h + (ct - (s + alpha[:, None] * ds))
-                    rhs_c = torch.cat([-r_x, -h_soc - D * r_s], dim=1)
-                    sol_c = torch.linalg.lu_solve(LU, piv, torch.where(okK[:, None], rhs_c, torch.zeros_like(rhs_c))[:, :, None])[:, :, 0]
-                    dx_c, dlam_c = sol_c[:, :n] * free_f, sol_c[:, n:]
-                    ds_c = (D * (dlam_c - r_s)) * ineq_f
-                    fin_c = torch.isfinite(sol_c).all(1)
-                    a_c = torch.stack([max_step(gxl, dx_c, x_lo_f), max_step(gxu, -dx_c, x_hi_f),
-                                       max_step(gsl, ds_c, s_lo_f), max_step(gsu, -ds_c, s_hi_f)]).amin(0).clamp(max=1.0)
-                    xc = x + a_c[:, None] * dx_c
-                    okc, stc, _ = try_point(torch.where(fin_c[:, None], xc, x), s + a_c[:, None] * ds_c, alpha)
-                    takec = okc & fin_c & ~accepted & ~pol
-                    x_new = torch.where(takec[:, None], xc, x_new)
-                    s_new = torch.where(takec[:, None], stc, s_new)
-                    dlam_used = torch.where(takec[:, None], dlam_c, dlam_used)
-                    accepted = accepted | takec
-                    if bool(accepted.all()):
-                        break
-                alpha = torch.where(accepted, alpha, 0.5 * alpha)
+                base = base * scale[-1] * 0.5
+            alpha = torch.where(accepted, alpha, a_p * 0.5 ** self.max_backtracks)
             dlam = dlam_used
             # Levenberg-Marquardt damping of the next step: a search that had to backtrack asks for a shorter step next
             # time, a full step relaxes the damping again (directions the cost is flat in -- ForceWeight 0 -- otherwise
@@ -481,12 +556,10 @@ class LockStepInteriorPoint:
             vsu = torch.minimum(torch.maximum(vsu, mu_c / (ks * gsu)), ks * mu_c / gsu) * s_hi_f
 
         status = torch.where(status < 0, torch.full_like(status, MAX_ITER), status)
-        viol = ((torch.clamp(sl - c, min=0) + torch.clamp(c - su, min=0)) / dc).amax(1)
-        dual0, _, _ = errors(df, c, J, s, lam, vxl, vxu, vsl, vsu, x, torch.zeros_like(mu))
-        x = torch.minimum(torch.maximum(x, x_orig_lo), x_orig_hi)          # honor_original_bounds
-        return SolveResult(x=x, status=status, iterations=iters, cost=f / dobj, constr_viol=viol, dual_inf=dual0,
-                           rounds=rounds, evaluations=evaluations, instance_evaluations=instance_evals,
-                           lam=lam * dc / dobj[:, None])
+        flush()
+        return SolveResult(x=out["x"], status=out["status"], iterations=out["iters"], cost=out["cost"], constr_viol=out["viol"],
+                           dual_inf=out["dual"], rounds=rounds, evaluations=evaluations, instance_evaluations=instance_evals,
+                           lam=out["lam"])
 
 
 def default_start(problem, N=1, device=None):

@@ -186,6 +186,19 @@ def test_solver_agrees_with_scipy_slsqp_on_a_nondegenerate_problem():
     assert abs(float(res.cost[0]) - r.fun) < 1e-6 * abs(r.fun)
 
 
+def test_dropping_finished_instances_does_not_change_the_others():
+    """Working-set compaction (finished instances leave the lock-step batch) is invisible in the results: instances are
+    independent, so every iterate, iteration count and solution is bit-identical with and without it."""
+    op, _, _ = oracle_problem("ground")
+    x0 = starts(op, 12, seed=7)
+    a = LockStepInteriorPoint(compact=False).Solve(op, x0)
+    b = LockStepInteriorPoint(compact_min=2).Solve(op, x0)
+    assert a.ok() and b.ok() and a.rounds == b.rounds
+    assert (a.iterations == b.iterations).all()
+    assert (a.x.numpy().view(np.int64) == b.x.numpy().view(np.int64)).all()
+    assert b.instance_evaluations < a.instance_evaluations
+
+
 def test_start_at_zero_is_reported_as_invalid_number():
     """x = 0 is the reference's start (Variable3D.cpp:8-10); the friction Jacobian there is 0/0 and the driver
     says so instead of iterating on NaNs."""
@@ -264,7 +277,7 @@ def test_instances_that_are_different_problems(cuda_device):
     mass = rng.uniform(60.0, 140.0, N)
     per_instance = {"wrench": torch.as_tensor(wrench, device=cuda_device), "mass": torch.as_tensor(mass, device=cuda_device)}
     x0 = starts(prob, N, seed=3, device=cuda_device)
-    res = LockStepInteriorPoint().Solve(prob, x0, per_instance=per_instance)
+    res = LockStepInteriorPoint(compact_min=8).Solve(prob, x0, per_instance=per_instance)   # the parameter arrays are compacted too
     assert (res.status == SUCCESS).all(), (res.status.tolist(), res.iterations.tolist())
     for i, (com, cmap) in enumerate(solution_maps(names, res.x.cpu().numpy())):
         F_sum, T_sum = np.zeros(3), np.zeros(3)
