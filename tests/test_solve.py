@@ -10,6 +10,10 @@ parameters and its EXPECT lines, asserted for EVERY instance of a small batch of
     no-environment problems every output of the CUDA path is bit-identical to the oracle's, so with the linear algebra on
     the same device the two solves must walk the SAME iterates bit for bit (`test_gpu_solve_trajectory_is_the_oracle_s`).
 
+The two scenarios of the reference's Python example (examples/python/test.py: a two-contact planner with every default, a
+CoMPlanner with two lifting contacts and a CoM reference) run through the same machinery; the example asserts nothing, so
+they are held to TestBasic's equilibrium and friction lines.
+
 Where the reference asserts a strict `<= 0.0` on a quantity an interior-point method only drives to its bound within the
 bound relaxation (IPOPT bound_relax_factor = 1e-8), the tolerance is written out.
 """
@@ -24,6 +28,7 @@ from helpers import OracleEvalProblem
 G = -9.81
 MASS = 100.0
 NAMES = ["contact1", "contact2", "contact3", "contact4"]
+MASSES = {"example_planner": 20.0}
 RELAX = 1e-8  # IPOPT bound_relax_factor
 
 
@@ -78,13 +83,35 @@ def setup_com_planner(problem, env):                # TestBasic.cpp:225-292 with
     return dict(mu=0.5, wrench=np.zeros(6))
 
 
+def setup_example_planner(problem, env):           # examples/python/test.py:7-18: two contacts, mass 20, everything else default
+    env.SetGroundZ(0.1)
+    return dict(ground_z=0.1, mu=0.5, wrench=np.zeros(6), mass=20.0)   # mu default: Environment.h:46
+
+
+def setup_example_com_planner(problem, env):       # examples/python/test.py:21-42: two of four contacts lifting, CoM reference set
+    problem.SetPosWeight(0.0)
+    problem.SetForceWeight(0.0)
+    problem.SetMu(0.5)
+    problem.SetCoMRef([0.2, 0.2, 1.0])
+    pts = {"c_1": [1.0, 1.0, 0.0], "c_2": [-1.0, 1.0, 0.0], "c_3": [1.0, -1.0, 0.0], "c_4": [-1.0, -1.0, 0.0]}
+    for nm, p in pts.items():
+        problem.SetNormalBounds(nm, [0, 0, 1.0], [0, 0, 1.0])
+        problem.SetPosBounds(nm, p, p)
+    for nm in ("c_3", "c_4"):                      # SetLiftingContact
+        problem.SetForceBounds(nm, [0, 0, 0], [0, 0, 0])
+        problem.SetForceThreshold(nm, 0.0)
+    return dict(mu=0.5, wrench=np.zeros(6))
+
+
 SETUPS = {"simple": (["contact1"], "ground", setup_simple), "ground": (NAMES, "ground", setup_ground),
-          "superquadric": (NAMES, "superquadric", setup_superquadric), "com_planner": (NAMES, "none", setup_com_planner)}
+          "superquadric": (NAMES, "superquadric", setup_superquadric), "com_planner": (NAMES, "none", setup_com_planner),
+          "example_planner": (["micio", "miao"], "ground", setup_example_planner),
+          "example_com_planner": (["c_1", "c_2", "c_3", "c_4"], "none", setup_example_com_planner)}
 
 
 def oracle_problem(case):
     names, env_name, setup = SETUPS[case]
-    op = OracleEvalProblem(names, env_name, MASS)
+    op = OracleEvalProblem(names, env_name, MASSES.get(case, MASS))
     return op, names, setup(op, op)
 
 
@@ -92,7 +119,7 @@ def product_problem(case):
     names, env_name, setup = SETUPS[case]
     env = {"none": None, "ground": cpl.Ground, "superquadric": cpl.Superquadric}[env_name]
     env = env() if env is not None else None
-    prob = cpl.BatchedCplProblem(names, MASS, env)
+    prob = cpl.BatchedCplProblem(names, MASSES.get(case, MASS), env)
     return prob, names, setup(prob, env)
 
 
@@ -127,7 +154,7 @@ def check_expectations(case, names, par, x):
         for F, p, n in cmap.values():
             F_sum += F
             T_sum += np.cross(p - com, F)
-            if case in ("simple", "ground"):
+            if case in ("simple", "ground", "example_planner"):
                 assert abs(p[2] - par["ground_z"]) < 1e-6            # :53,119
                 assert abs(np.linalg.norm(n) - 1.0) < 1e-6           # :54,120
                 assert abs(n[2] - 1.0) < 1e-6                        # :55,121
@@ -144,9 +171,10 @@ def check_expectations(case, names, par, x):
             assert abs(F_sum[2] - (-MASS * G)) < 1e-6                # :59
             continue
         w = par["wrench"]
+        mass = par.get("mass", MASS)
         tol_t = 1e-5 if case == "ground" else 1e-4
         assert abs(F_sum[0] - w[0]) < 1e-6 and abs(F_sum[1] - w[1]) < 1e-6   # :131-132
-        assert abs(F_sum[2] - (-MASS * G + w[2])) < 1e-6             # :133
+        assert abs(F_sum[2] - (-mass * G + w[2])) < 1e-6             # :133
         assert np.abs(T_sum - w[3:6]).max() < tol_t                  # :134-136
 
 
