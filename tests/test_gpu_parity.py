@@ -368,6 +368,51 @@ def test_per_instance_parameters(case, layout, path, cuda_device):
             assert same_bits(g_sub[i][:6], o2.eval(x[i])["g"][:6])
 
 
+@pytest.mark.parametrize("misaligned", [False, True])
+@pytest.mark.parametrize("want", [dict(g=True, jac=True), dict(g=True, jac=False), dict(g=False, jac=True)])
+@pytest.mark.parametrize("case,N", [("ground4", 4096), ("ground4", 301), ("ground4", 5), ("ground8", 1023), ("ground1", 777), ("ground12", 130)])
+def test_per_instance_constraint_only_evaluations(case, N, want, misaligned, cuda_device):
+    """Constraint-only evaluations of Ground problems are the ones whose per-instance parameter slices the instance-major
+    kernel stages in shared memory with the x tile (bulk copies; plain copies for ragged tiles and for arrays that are not
+    16-byte aligned): every instance, every output, both layouts, against N oracle problems."""
+    import torch
+
+    prob, o, gen = make_pair(case)
+    nc = o.nc
+    x = gen(N)
+    rng = np.random.default_rng(N)
+    pi = {"mass": rng.uniform(20, 150, N), "wrench": rng.uniform(-50, 50, (N, 6)), "mu": rng.uniform(0.2, 1.2, N),
+          "force_threshold": rng.uniform(0, 30, (N, nc)), "ground_z": rng.uniform(-0.2, 0.4, N)}
+    ref = {"g": np.zeros((N, o.m)), "jac": np.zeros((N, o.nnz))}
+    for i in range(N):
+        o.set_mass(pi["mass"][i])
+        o.set_wrench(pi["wrench"][i])
+        o.set_mu(pi["mu"][i])
+        o.set_ground_z(pi["ground_z"][i])
+        for k, nm in enumerate(o.names):
+            o.set_force_threshold(nm, pi["force_threshold"][i, k])
+        e = o.eval(x[i], want=("g", "jac"))
+        ref["g"][i], ref["jac"][i] = e["g"], e["jac"]
+
+    def dev(a):
+        a = np.ascontiguousarray(a)
+        if not misaligned:
+            return torch.from_numpy(a).to(cuda_device)
+        pad = torch.empty(a.size + 1, dtype=torch.float64, device=cuda_device)       # 8 bytes off a 16-byte boundary
+        view = pad[1:].view(a.shape)
+        view.copy_(torch.from_numpy(a))
+        assert view.data_ptr() % 16 == 8
+        return view
+
+    for layout in LAYOUTS:
+        lay = (lambda a: a.T) if layout == cpl.COMPONENT_MAJOR else (lambda a: a)
+        pid = {k: dev(lay(v) if v.ndim == 2 else v) for k, v in pi.items()}
+        out = prob.eval(torch.from_numpy(np.ascontiguousarray(lay(x))).to(cuda_device), layout=layout, per_instance=pid, **want)
+        torch.cuda.synchronize()
+        got = {k: (None if v is None else to_instance_major(v.cpu().numpy(), layout)) for k, v in out.items()}
+        assert_parity(got, {k: (ref[k] if want.get(k) else None) for k in ref}, o, f"per-instance-constraints/{case}/{N}/layout{layout}", x)
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("want", [dict(g=True, jac=False), dict(g=False, jac=True), dict(g=False, jac=False, cost=True),
