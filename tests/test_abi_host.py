@@ -56,6 +56,34 @@ def test_layout_matches_oracle_structure(case):
     assert np.array_equal(lb, lbo) and np.array_equal(ub, ubo)
 
 
+def test_layout_of_random_name_sets_matches_oracle_structure():
+    """The closed-form layout (csrc/cplb_layout.hpp) against the structure the oracle DISCOVERS by emulating ifopt's assembly,
+    for 60 random contact-name sets: 1..32 names with shared prefixes, digits, upper case and underscores (std::map orders
+    them bytewise: 'Z' < '_' < 'a', 'c10' < 'c2'), in random vector order, every environment kind."""
+    rng = np.random.default_rng(2024)
+    alphabet = list("abcXYZ_019")
+    for trial in range(60):
+        nc = int(rng.integers(1, 33))
+        names = set()
+        while len(names) < nc:
+            names.add("".join(rng.choice(alphabet, size=int(rng.integers(1, 6)))))
+        names = list(names)
+        rng.shuffle(names)
+        kind = ["none", "ground", "superquadric"][trial % 3]
+        env = {"none": None, "ground": cpl.Ground, "superquadric": cpl.Superquadric}[kind]
+        prob = cpl.BatchedCplProblem(names, 50.0, env() if env else None)
+        o = orc.Oracle(names, {"none": orc.ENV_NONE, "ground": orc.ENV_GROUND, "superquadric": orc.ENV_SUPERQUADRIC}[kind], 50.0)
+        assert (prob.n, prob.m, prob.nnz) == (o.n, o.m, o.nnz), names
+        r, c = prob.GetJacobianStructure()
+        ro, co = o.structure()
+        assert np.array_equal(r, ro) and np.array_equal(c, co), names
+        assert np.array_equal(prob.GetSortedOrder(), o.sorted_order()), names
+        assert [names[k] for k in prob.GetSortedOrder()] == sorted(names)            # bytewise, like std::string operator<
+        for nm in names:
+            j = sorted(names).index(nm)
+            assert prob.GetContactRow(nm) == 6 + (6 if kind != "none" else 2) * j
+
+
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_layout_matches_reference_golden_structure(case):
     """(iRow, jCol) and bounds as the reference's own CplProblem + ifopt-style assembly report them
