@@ -36,32 +36,51 @@ def main():
     ap.add_argument("--no-gpu", action="store_true")
     a = ap.parse_args()
     out = {"metric": "end-to-end solves/s (lock-step interior-point stand-in, NOT IPOPT)", "case": a.case, "instances": a.instances}
+    # one process per GPU under torchrun: instances shard by index (no collective on the solve path), time = max over ranks
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     op, names, par = ts.oracle_problem(a.case)
     op.nthreads = len(os.sched_getaffinity(0))
     x0 = ts.starts(op, a.instances, seed=2025)
     solver = LockStepInteriorPoint()
 
     if not a.no_gpu:
+        from centroidalplanner_b200 import sharding
         prob, _, _ = ts.product_problem(a.case)
-        dev = torch.device("cuda:0")
-        xg = x0.to(dev)
+        dev = torch.device("cuda", local)
+        lo, hi = sharding.local_range(a.instances, rank, world)
+        xg = x0[lo:hi].to(dev)
         solver.Solve(prob, xg[:64])          # warm-up: cuSOLVER/cuBLAS handles, kernels
         best = None
         for _ in range(a.repeats):
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             l0 = prob.launch_count()
             t = time.perf_counter()
             res = solver.Solve(prob, xg)
             torch.cuda.synchronize()
-            dt = time.perf_counter() - t
+            dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt = float(dt.item())
             best = dt if best is None else min(best, dt)
-        ok = int((res.status == SUCCESS).sum())
+        ok = torch.tensor([int((res.status == SUCCESS).sum())], device=dev)
+        if world > 1:
+            dist.all_reduce(ok)
+        ok = int(ok.item())
         ts.check_expectations(a.case, names, par, res.x[res.status == SUCCESS].cpu().numpy())
-        out["gpu"] = {"solves_per_s": a.instances / best, "seconds": best, "succeeded": ok, "rounds": res.rounds,
+        out["gpu"] = {"n_gpus": world, "solves_per_s": a.instances / best, "seconds": best, "succeeded": ok, "rounds": res.rounds,
                       "kernel_launches": prob.launch_count() - l0, "instance_evaluations": res.instance_evaluations,
                       "iterations_median": float(res.iterations.double().median()), "iterations_max": int(res.iterations.max()),
                       "max_constr_viol": float(res.constr_viol[res.status == SUCCESS].max())}
 
+    if rank != 0:
+        return
     n_cpu = min(a.cpu_sample, a.instances)
     t = time.perf_counter()
     rc = solver.Solve(op, x0[:n_cpu])
