@@ -4,17 +4,10 @@
 // path in this library: without a CUDA device every evaluation fails with CPLB_CUDA_ERROR.
 #include <cuda_runtime.h>
 
-#ifdef __linux__
-#include <sys/syscall.h>
-#include <unistd.h>
-#endif
-
 #include <atomic>
-#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -977,49 +970,11 @@ cplb_status cplb_eval_host(cplb_problem* p, const cplb_eval_args* args)
     return CPLB_OK;
 }
 
-// NUMA node the current CUDA device hangs off (sysfs), -1 if unknown.
-static int current_device_numa_node()
-{
-    int dev = 0;
-    char bus[32] = {0};
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) != cudaSuccess) {
-        cudaGetLastError();
-        return -1;
-    }
-    for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
-    char path[96];
-    std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
-    FILE* f = std::fopen(path, "r");
-    if (!f) return -1;
-    int node = -1;
-    if (std::fscanf(f, "%d", &node) != 1) node = -1;
-    std::fclose(f);
-    return (node >= 0 && node < 64) ? node : -1;
-}
-
 cplb_status cplb_host_alloc(size_t bytes, void** out)
 {
     CPLB_REQUIRE(out);
     *out = nullptr;
-    // Pinned pages PREFERABLY on the memory node of the current device: on a multi-socket box the DMA of the GPUs on the
-    // far socket otherwise crosses the inter-socket link for every transfer (profiles/r01_scaling.md).  MPOL_PREFERRED
-    // falls back to any allowed node, a refused syscall (containers) leaves the default policy; CPLB_NUMA_LOCAL=0 disables.
-    bool policy_set = false;
-#ifdef __linux__
-    static const bool numa_local = [] { const char* e = std::getenv("CPLB_NUMA_LOCAL"); return !(e && e[0] == '0'); }();
-    const int node = numa_local ? current_device_numa_node() : -1;
-    if (node >= 0) {
-        const unsigned long mask = 1UL << node;
-        policy_set = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 8 * sizeof(mask)) == 0;
-    }
-    static const bool numa_verbose = [] { const char* e = std::getenv("CPLB_NUMA_LOCAL"); return e && e[0] == 'v'; }();
-    if (numa_verbose) std::fprintf(stderr, "cplb_host_alloc: %zu bytes, device node %d, preferred-node policy %s\n", bytes, node, policy_set ? "set" : "not set");
-#endif
-    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
-#ifdef __linux__
-    if (policy_set) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
-#endif
-    CPLB_CUDA(e);
+    CPLB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
     return CPLB_OK;
 }
 cplb_status cplb_host_free(void* ptr)
