@@ -9,13 +9,18 @@ views of `cplb/ifopt_views.hpp` in lock-step mode.  This mo
 solver written out, so that the batched evaluator can be exercised -- and the reference's own post-solve assertions
 (tests/TestBasic.cpp) checked -- by a real NLP solve without IPOPT:
 
-  * the four IpoptAdapter callbacks become ONE `problem.eval(x, g, jac, cost, grad)` per iteration for all N instances
-    plus one `eval(g, cost)` per line-search trial;
+  * the four IpoptAdapter callbacks become ONE `problem.eval(x, g, jac, cost, grad)` per iteration for all N instances,
+    one widened `eval(jac, grad)` of N (n_free + 1) points for the Hessian differences and one widened `eval(g, cost)` per
+    group of four line-search candidates;
   * the algorithm is the textbook primal-dual interior-point method IPOPT implements (Waechter & Biegler 2006, §2-3:
     slack reformulation of inequality rows, log barrier on bounds, fraction-to-boundary rule, monotone barrier update,
-    gradient-based scaling with nlp_scaling_max_gradient = 100, bound_push / bound_frac initialisation, kappa_sigma
-    safeguard of the bound multipliers, fixed variables removed), with a damped dense BFGS approximation of the
-    Lagrangian Hessian in place of IPOPT's L-BFGS and an l1 merit backtracking line search in place of the filter.
+    gradient-based scaling with nlp_scaling_max_gradient = 100, bound_push / bound_frac initialisation, bound relaxation,
+    kappa_sigma safeguard of the bound multipliers, fixed variables removed, second-order correction, `tol = 1e-3` as
+    ifopt sets it).  Where it departs from IPOPT: the Lagrangian Hessian is a forward difference of the batched gradient
+    and Jacobian instead of L-BFGS (the reference runs `limited-memory`), with an inertia-free curvature test and
+    Levenberg-Marquardt damping for the directions the cost is flat in (ForceWeight 0); an l1 merit backtracking line
+    search with slack reset replaces the filter; and a minimum-norm feasibility polish takes the constraints from
+    IPOPT's constr_viol_tol (1e-4) to 1e-9 after the optimality test has passed.
     It is NOT IPOPT: iterates differ, solutions agree to the tolerance (local minima of the same NLP).
 
 Everything is torch on the device of `x0` (fp64): the evaluation kernels read x where the linear algebra left it, so a
