@@ -94,6 +94,23 @@ static void run(bool with_env, int N)
         for (int c = 0; c < n; c++) EXPECT(same(gr(c), grad[c]), "grad[%d][%d]", i, c);
     }
     EXPECT(batch->evaluations() == ev0 + 1, "lock-step use must cost one batched evaluation, took %lld", batch->evaluations() - ev0);
+    // CplProblem::GetSolution (src/CplProblem.cpp:85-106): what finalize_solution left in the variables, keyed by name
+    {
+        const int i = N / 2;
+        const double* x = &X[(size_t)i * n];
+        cplb::solver::Solution sol;
+        probs[i]->GetSolution(sol);
+        EXPECT(sol.contact_values_map.size() == names.size() && sol.contact_values_map.begin()->first == "l_foot", "solution map order");
+        for (int c = 0; c < 3; c++) EXPECT(same(sol.com_sol[c], x[c]), "com_sol[%d]", c);
+        for (size_t k = 0; k < names.size(); k++) {
+            const auto& v = sol.contact_values_map.at(names[k]);
+            for (int c = 0; c < 3; c++) {
+                EXPECT(same(v.force_value[c], x[3 + 9 * k + c]), "force_value %s[%d]", names[k].c_str(), c);
+                EXPECT(same(v.position_value[c], x[6 + 9 * k + c]), "position_value %s[%d]", names[k].c_str(), c);
+                EXPECT(same(v.normal_value[c], x[9 + 9 * k + c]), "normal_value %s[%d]", names[k].c_str(), c);
+            }
+        }
+    }
     // bounds as IpoptAdapter::get_bounds_info reads them
     auto bg = probs[0]->GetBoundsOnConstraints();
     std::vector<double> gl(m), gu(m);
