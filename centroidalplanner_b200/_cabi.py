@@ -92,6 +92,8 @@ PROTOTYPES = {
     "cplb_get_contact_force_weight": (C.c_int, [C.c_void_p, C.c_char_p, dp]),
     "cplb_eval_device": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs), C.c_void_p]),
     "cplb_eval_host": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs)]),
+    "cplb_eval_host_begin": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs), C.POINTER(C.c_int32)]),
+    "cplb_eval_host_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "cplb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cplb_host_free": (C.c_int, [C.c_void_p]),
     "cplb_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

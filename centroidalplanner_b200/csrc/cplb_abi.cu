@@ -49,6 +49,7 @@ cplb_status cuda_fail(cudaError_t e, const char* what)
     } while (0)
 
 constexpr int kHostStreams = 3;
+constexpr int kHostTickets = 4;  // asynchronous host calls that may be outstanding at once
 
 struct DeviceGuard {
     int prev = -1;
@@ -90,6 +91,10 @@ struct cplb_problem {
     size_t bounce_bytes = 0;
     size_t stage_bytes = 0;
     bool streams_ready = false;
+    // cplb_eval_host_begin / _wait: completion events of the outstanding asynchronous calls (ring of tickets)
+    cudaEvent_t host_done[kHostTickets][kHostStreams] = {};
+    bool host_done_ready = false;
+    int next_ticket = 0;
 
     int find(const char* name) const
     {
@@ -207,6 +212,9 @@ void cplb_destroy(cplb_problem* p)
             cudaEventDestroy(ev.first);
             cudaEventDestroy(ev.second);
         }
+        if (p->host_done_ready)
+            for (int t = 0; t < kHostTickets; t++)
+                for (int s = 0; s < kHostStreams; s++) cudaEventDestroy(p->host_done[t][s]);
         if (p->streams_ready) {
             for (int s = 0; s < kHostStreams; s++) {
                 cudaStreamSynchronize(p->streams[s]);
@@ -867,10 +875,13 @@ static cplb_status eval_host_bounced(cplb_problem* p, const cplb_eval_args* args
     return CPLB_OK;
 }
 
-cplb_status cplb_eval_host(cplb_problem* p, const cplb_eval_args* args)
+// ticket == nullptr: synchronous (returns when the outputs have landed).  Otherwise the work is only enqueued, a completion
+// event per stream is recorded into the next ticket slot and its index returned; pinned buffers are required then.
+static cplb_status eval_host_impl(cplb_problem* p, const cplb_eval_args* args, int32_t* ticket)
 {
     CPLB_REQUIRE(p);
     CPLB_REQUIRE(args);
+    if (ticket) *ticket = -1;
     unsigned flags = 0;
     long long ld = 0;
     cplb_status st = check_args(p, args, &flags, &ld);
@@ -903,8 +914,15 @@ cplb_status cplb_eval_host(cplb_problem* p, const cplb_eval_args* args)
     bool all_pinned = is_pinned(args->x) && is_pinned(args->g) && is_pinned(args->jac) && is_pinned(args->cost) && is_pinned(args->grad);
     if (args->per_instance)
         for (const auto& f : kInstFields) all_pinned = all_pinned && is_pinned(args->per_instance->*(f.src));
-    if (!all_pinned)
+    if (!all_pinned) {
+        if (ticket) return fail(CPLB_INVALID_ARGUMENT, "cplb_eval_host_begin needs pinned host buffers (cplb_host_alloc)");
         return eval_host_bounced(p, args, flags, ld, chunk, per_inst * (size_t)chunk * sizeof(double));
+    }
+    if (ticket && !p->host_done_ready) {
+        for (int t = 0; t < kHostTickets; t++)
+            for (int q = 0; q < kHostStreams; q++) CPLB_CUDA(cudaEventCreateWithFlags(&p->host_done[t][q], cudaEventDisableTiming));
+        p->host_done_ready = true;
+    }
 
     const bool cm = args->layout == CPLB_COMPONENT_MAJOR;
     const bool skip_const = (args->host_flags & CPLB_HOST_JAC_CONSTANTS_PRESENT) != 0;
@@ -966,7 +984,34 @@ cplb_status cplb_eval_host(cplb_problem* p, const cplb_eval_args* args)
         }
         if (dc) CPLB_CUDA(cudaMemcpyAsync(args->cost + i0, dc, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
-    for (int t = 0; t < kHostStreams; t++) CPLB_CUDA(cudaStreamSynchronize(p->streams[t]));
+    if (!ticket) {
+        for (int t = 0; t < kHostStreams; t++) CPLB_CUDA(cudaStreamSynchronize(p->streams[t]));
+        return CPLB_OK;
+    }
+    const int slot = p->next_ticket;
+    p->next_ticket = (slot + 1) % kHostTickets;
+    // the slot's previous use must be over before its events are re-recorded (the caller waited for it or never will)
+    for (int t = 0; t < kHostStreams; t++) CPLB_CUDA(cudaEventRecord(p->host_done[slot][t], p->streams[t]));
+    *ticket = slot;
+    return CPLB_OK;
+}
+
+cplb_status cplb_eval_host(cplb_problem* p, const cplb_eval_args* args) { return eval_host_impl(p, args, nullptr); }
+
+cplb_status cplb_eval_host_begin(cplb_problem* p, const cplb_eval_args* args, int32_t* ticket)
+{
+    CPLB_REQUIRE(ticket);
+    return eval_host_impl(p, args, ticket);
+}
+
+cplb_status cplb_eval_host_wait(cplb_problem* p, int32_t ticket)
+{
+    CPLB_REQUIRE(p);
+    if (ticket == -1) return CPLB_OK;  // an empty call (no instances / no outputs) completed at once
+    if (ticket < 0 || ticket >= kHostTickets || !p->host_done_ready) return fail(CPLB_INVALID_ARGUMENT, "unknown ticket %d", (int)ticket);
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(CPLB_CUDA_ERROR, "cudaSetDevice(%d) failed", p->device);
+    for (int t = 0; t < kHostStreams; t++) CPLB_CUDA(cudaEventSynchronize(p->host_done[ticket][t]));
     return CPLB_OK;
 }
 

@@ -396,7 +396,17 @@ class BatchedCplProblem:
         _check(self._lib.cplb_eval_device(self._h, C.byref(args), C.c_void_p(s)))
         return res
 
-    def _eval_host(self, x, g, jac, cost, grad, layout, out, jac_constants_present=False, per_instance=None):
+    def eval_host_begin(self, x, out, g=True, jac=True, cost=False, grad=False, layout=_cabi.INSTANCE_MAJOR,
+                        jac_constants_present=False, per_instance=None):
+        """cplb_eval_host_begin: enqueue one host-buffer evaluation and return (ticket, outputs) without waiting.  `x` and
+        every array in `out` must be PINNED NumPy arrays (cplb_host_alloc) that stay alive and untouched until
+        `eval_host_wait(ticket)`; with two buffer sets (begin k+1, wait k) consecutive batches keep the PCIe link busy."""
+        return self._eval_host(x, g, jac, cost, grad, layout, dict(out), jac_constants_present, per_instance, begin=True)
+
+    def eval_host_wait(self, ticket):
+        _check(self._lib.cplb_eval_host_wait(self._h, int(ticket)))
+
+    def _eval_host(self, x, g, jac, cost, grad, layout, out, jac_constants_present=False, per_instance=None, begin=False):
         is_t = _is_torch(x)
         xa = x.numpy() if is_t else np.asarray(x, dtype=np.float64)
         xa = np.ascontiguousarray(xa)
@@ -420,6 +430,10 @@ class BatchedCplProblem:
         args = _cabi.EvalArgs(N, layout, hflags, N, xa.ctypes.data, *[None if res[k] is None else res[k].ctypes.data
                                                                      for k in ("g", "jac", "cost", "grad")],
                               C.pointer(pi) if pi is not None else None)
+        if begin:
+            ticket = C.c_int32(-1)
+            _check(self._lib.cplb_eval_host_begin(self._h, C.byref(args), C.byref(ticket)))
+            return ticket.value, res
         _check(self._lib.cplb_eval_host(self._h, C.byref(args)))
         return res
 

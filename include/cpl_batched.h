@@ -240,6 +240,15 @@ cplb_status cplb_eval_device(cplb_problem *p, const cplb_eval_args *args, void *
  * after every output has landed in the host buffers. */
 cplb_status cplb_eval_host(cplb_problem *p, const cplb_eval_args *args);
 
+/* The same call for a QUEUE of batches (several IPOPT callback rounds or planner requests in flight): _begin only
+ * enqueues the chunked copies and kernels and hands back a ticket, _wait returns once that call's outputs have landed.
+ * With two sets of host buffers (begin k+1, wait k) the device -> host link, which bounds the synchronous call, never
+ * idles between batches.  Host buffers must be pinned (cplb_host_alloc; CPLB_INVALID_ARGUMENT otherwise) and stay
+ * untouched until the wait; at most 4 calls may be outstanding (a ticket is reused after 4 more begins).
+ * Replaces: N x the reference's Problem::Evaluate* calls per batch (ifopt), as cplb_eval_host. */
+cplb_status cplb_eval_host_begin(cplb_problem *p, const cplb_eval_args *args, int32_t *ticket);
+cplb_status cplb_eval_host_wait(cplb_problem *p, int32_t ticket);
+
 /* Structural Jacobian slots whose value does not depend on x: the 1.0 identities of CentroidalStatics
  * (CentroidalStatics.cpp:93-95) and EnvironmentNormal (EnvironmentNormal.cpp:66-68) and, for Ground, its explicit
  * zeros and the (0,0,1) gradient (Ground.cpp:33-34,49).  IPOPT keeps one values[] array per problem, so a consumer

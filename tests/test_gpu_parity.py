@@ -530,3 +530,53 @@ def test_full_size_configs(case, N, cuda_device):
     w = torch.tensor(synthetic.TESTBASIC["wrench"][:3], device=cuda_device, dtype=torch.float64)
     mg = torch.tensor([0.0, 0.0, -981.0], device=cuda_device, dtype=torch.float64)
     assert float((a["g"][:, :3] - (F - w + mg)).abs().max()) <= 1e-9
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_asynchronous_host_calls_queue_of_batches(layout, cuda_device):
+    """cplb_eval_host_begin / _wait: three batches in flight on two buffer sets (begin k+1, wait k); every batch's outputs
+    equal the synchronous call's bit for bit; pageable buffers are refused; an empty call completes at once."""
+    import ctypes as C
+
+    from centroidalplanner_b200 import _cabi
+
+    prob, o, gen = make_pair("ground4")
+    lib = _cabi.load()
+    N = 40000          # three chunks, the last one ragged
+    shape = (lambda L: (N, L)) if layout == cpl.INSTANCE_MAJOR else (lambda L: (L, N))
+
+    def pinned(shp):
+        ptr = C.c_void_p()
+        assert lib.cplb_host_alloc(int(np.prod(shp)) * 8, C.byref(ptr)) == 0
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(int(np.prod(shp)),)).reshape(shp), ptr
+
+    keep, sets = [], []
+    for _ in range(2):
+        bufs = {}
+        for key, L in (("x", prob.n), ("g", prob.m), ("jac", prob.nnz)):
+            bufs[key], ptr = pinned(shape(L))
+            keep.append(ptr)
+        sets.append(bufs)
+    batches = [gen(N) * (1.0 + 0.01 * b) for b in range(3)]
+    want = [prob.eval(np.ascontiguousarray(xb if layout == cpl.INSTANCE_MAJOR else xb.T), g=True, jac=True, layout=layout) for xb in batches]
+    got, pending = [], None
+    for b, xb in enumerate(batches):
+        bufs = sets[b % 2]
+        bufs["x"][...] = xb if layout == cpl.INSTANCE_MAJOR else xb.T
+        bufs["g"][...] = np.nan
+        bufs["jac"][...] = np.nan
+        ticket, _ = prob.eval_host_begin(bufs["x"], {"g": bufs["g"], "jac": bufs["jac"]}, g=True, jac=True, layout=layout)
+        if pending is not None:
+            prob.eval_host_wait(pending[0])
+            got.append({k: pending[1][k].copy() for k in ("g", "jac")})
+        pending = (ticket, bufs)
+    prob.eval_host_wait(pending[0])
+    got.append({k: pending[1][k].copy() for k in ("g", "jac")})
+    for b in range(3):
+        assert same_bits(got[b]["g"], want[b]["g"]) and same_bits(got[b]["jac"], want[b]["jac"]), b
+    with pytest.raises(ValueError, match="pinned"):
+        prob.eval_host_begin(np.zeros(shape(prob.n)), {"g": np.zeros(shape(prob.m))}, g=True, jac=False, layout=layout)
+    with pytest.raises(ValueError, match="unknown ticket"):
+        prob.eval_host_wait(17)
+    for ptr in keep:
+        lib.cplb_host_free(ptr)
