@@ -95,6 +95,7 @@ struct cplb_problem {
     cudaEvent_t host_done[kHostTickets][kHostStreams] = {};
     bool host_done_ready = false;
     int next_ticket = 0;
+    int next_stream = 0;
 
     int find(const char* name) const
     {
@@ -897,7 +898,8 @@ static cplb_status eval_host_impl(cplb_problem* p, const cplb_eval_args* args, i
     const int n = p->layout.n, m = p->layout.m, nnz = p->layout.nnz;
     // chunk: big enough for efficient PCIe bursts (several MB per copy), small enough that three
     // chunks in flight overlap H2D, kernel and D2H
-    long long chunk = 16384;
+    // (a queued call does not need an early first download: larger chunks, fewer and longer copies)
+    long long chunk = ticket ? 32768 : 16384;
     if (chunk > N) chunk = N;
     chunk = (chunk + 31) & ~31LL;  // keeps every chunk's slices 16-byte aligned and tile-aligned
     size_t per_inst = (size_t)n;
@@ -926,7 +928,9 @@ static cplb_status eval_host_impl(cplb_problem* p, const cplb_eval_args* args, i
 
     const bool cm = args->layout == CPLB_COMPONENT_MAJOR;
     const bool skip_const = (args->host_flags & CPLB_HOST_JAC_CONSTANTS_PRESENT) != 0;
-    int s = 0;
+    // the round robin over the streams continues across calls: the first chunk of a queued call then lands on the stream
+    // whose previous work finished longest ago instead of behind the previous call's last download
+    int s = p->next_stream;
     for (long long i0 = 0; i0 < N; i0 += chunk, s = (s + 1) % kHostStreams) {
         const long long cnt = (N - i0) < chunk ? (N - i0) : chunk;
         cudaStream_t stream = p->streams[s];
@@ -984,6 +988,7 @@ static cplb_status eval_host_impl(cplb_problem* p, const cplb_eval_args* args, i
         }
         if (dc) CPLB_CUDA(cudaMemcpyAsync(args->cost + i0, dc, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
+    p->next_stream = s;
     if (!ticket) {
         for (int t = 0; t < kHostStreams; t++) CPLB_CUDA(cudaStreamSynchronize(p->streams[t]));
         return CPLB_OK;
