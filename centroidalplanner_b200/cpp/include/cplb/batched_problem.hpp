@@ -330,6 +330,25 @@ public:
         a.per_instance = per_instance;
         check(cplb_eval_host(_p, &a));
     }
+    // the same for a queue of batches: Begin enqueues and returns a ticket, Wait returns when that batch's outputs have landed
+    // (pinned host buffers, untouched in between; cplb_eval_host_begin / cplb_eval_host_wait)
+    int32_t EvaluateHostBegin(int64_t N, const double* x, double* g, double* jac, double* cost, double* grad,
+                              const cplb_instance_params* per_instance = nullptr)
+    {
+        cplb_eval_args a{};
+        a.num_instances = N;
+        a.layout = CPLB_INSTANCE_MAJOR;
+        a.x = x;
+        a.g = g;
+        a.jac = jac;
+        a.cost = cost;
+        a.grad = grad;
+        a.per_instance = per_instance;
+        int32_t ticket = -1;
+        check(cplb_eval_host_begin(_p, &a, &ticket));
+        return ticket;
+    }
+    void EvaluateHostWait(int32_t ticket) { check(cplb_eval_host_wait(_p, ticket)); }
     // device buffers, either layout, asynchronous on `stream`
     void EvaluateDevice(int64_t N, cplb_layout layout, int64_t ld, const double* x, double* g, double* jac, double* cost,
                         double* grad, void* stream, const cplb_instance_params* per_instance = nullptr)
