@@ -284,6 +284,26 @@ def test_eval_argument_checks_happen_before_any_device_work():
     assert lib.cplb_eval_host(None, None) == _cabi.NULL_POINTER
 
 
+def test_queued_host_call_argument_checks():
+    """cplb_eval_host_begin / _wait validate before any device work, like cplb_eval_host: NULL ticket pointer, unknown tickets,
+    and (without a CUDA device) the same loud failure instead of a CPU evaluation."""
+    import torch
+
+    prob = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, cpl.Ground())
+    lib = _cabi.load()
+    x = np.zeros((4, prob.n))
+    args = _cabi.EvalArgs(4, cpl.INSTANCE_MAJOR, 0, 4, x.ctypes.data, None, None, None, None, None)
+    assert lib.cplb_eval_host_begin(prob._h, C.byref(args), None) == _cabi.NULL_POINTER
+    with pytest.raises(ValueError, match="unknown ticket"):
+        prob.eval_host_wait(3)                     # nothing was ever begun
+    prob.eval_host_wait(-1)                        # the ticket of an empty call
+    ticket, _ = prob.eval_host_begin(np.zeros((0, prob.n)), {}, g=False, jac=False)   # no instances, no outputs: completes at once
+    assert ticket == -1
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no usable CUDA device"):
+            prob.eval_host_begin(x, {"g": np.zeros((4, prob.m))}, g=True, jac=False)
+
+
 def test_header_is_valid_c99_and_usable_from_plain_c(tmp_path):
     """include/cpl_batched.h compiled by gcc as strict C99 and driven from a C program (no C++, no Python, no GPU)."""
     import shutil
