@@ -898,8 +898,9 @@ static cplb_status eval_host_impl(cplb_problem* p, const cplb_eval_args* args, i
     const int n = p->layout.n, m = p->layout.m, nnz = p->layout.nnz;
     // chunk: big enough for efficient PCIe bursts (several MB per copy), small enough that three
     // chunks in flight overlap H2D, kernel and D2H
-    // (a queued call does not need an early first download: larger chunks, fewer and longer copies)
-    long long chunk = ticket ? 32768 : 16384;
+    // 32,768-instance chunks (few, long copies: the download engine is the bound).  A synchronous call starts with one
+    // short chunk so that its first download begins early; a queued call is preceded by the previous call's downloads anyway.
+    long long chunk = 32768;
     if (chunk > N) chunk = N;
     chunk = (chunk + 31) & ~31LL;  // keeps every chunk's slices 16-byte aligned and tile-aligned
     size_t per_inst = (size_t)n;
@@ -931,8 +932,10 @@ static cplb_status eval_host_impl(cplb_problem* p, const cplb_eval_args* args, i
     // the round robin over the streams continues across calls: the first chunk of a queued call then lands on the stream
     // whose previous work finished longest ago instead of behind the previous call's last download
     int s = p->next_stream;
-    for (long long i0 = 0; i0 < N; i0 += chunk, s = (s + 1) % kHostStreams) {
-        const long long cnt = (N - i0) < chunk ? (N - i0) : chunk;
+    const long long first = (!ticket && N > chunk) ? chunk / 4 : chunk;
+    for (long long i0 = 0, cnt = 0; i0 < N; i0 += cnt, s = (s + 1) % kHostStreams) {
+        const long long want = (i0 == 0) ? first : chunk;
+        cnt = (N - i0) < want ? (N - i0) : want;
         cudaStream_t stream = p->streams[s];
         double* d = p->stage[s];
         double* dx = d;
