@@ -16,6 +16,7 @@ ENV_NONE, ENV_GROUND, ENV_SUPERQUADRIC = 0, 1, 2
 INSTANCE_MAJOR, COMPONENT_MAJOR = 0, 1
 HOST_JAC_CONSTANTS_PRESENT = 1
 DEVICE_INPUTS_READY = 2
+KERNEL_AUTO, KERNEL_PER_CONTACT, KERNEL_PER_INSTANCE = 0, 1, 2
 BLOCK_COM, BLOCK_FORCE, BLOCK_POSITION, BLOCK_NORMAL = 0, 1, 2, 3
 
 dp = C.POINTER(C.c_double)
@@ -96,6 +97,8 @@ PROTOTYPES = {
     "cplb_eval_host_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "cplb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cplb_host_free": (C.c_int, [C.c_void_p]),
+    "cplb_set_component_major_kernel": (C.c_int, [C.c_void_p, C.c_int32]),
+    "cplb_get_device": (C.c_int, [C.c_void_p, ip]),
     "cplb_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "cplb_timing_begin": (C.c_int, [C.c_void_p]),
     "cplb_timing_end": (C.c_int, [C.c_void_p, dp, C.POINTER(C.c_int64)]),

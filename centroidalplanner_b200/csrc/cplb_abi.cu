@@ -77,6 +77,7 @@ struct cplb_problem {
     CplbParams P{};
     std::vector<double> x_lb, x_ub;
     std::atomic<long long> launches{0};
+    int cm_kernel = CPLB_CM_AUTO;  // cplb_set_component_major_kernel
 
     // kernel timing (cplb_timing_begin/end)
     std::mutex timing_mu;
@@ -371,6 +372,25 @@ cplb_status cplb_set_reduction_order(cplb_problem* p, int32_t order)
     CPLB_REQUIRE(p);
     if (order != 0 && order != 1) return fail(CPLB_INVALID_ARGUMENT, "reduction order must be 0 ((v0+v1)+v2) or 1 (v0+(v1+v2))");
     p->P.reduction_order = order;
+    return CPLB_OK;
+}
+
+cplb_status cplb_set_component_major_kernel(cplb_problem* p, int32_t kernel)
+{
+    CPLB_REQUIRE(p);
+    if (kernel != CPLB_KERNEL_AUTO && kernel != CPLB_KERNEL_PER_CONTACT && kernel != CPLB_KERNEL_PER_INSTANCE)
+        return fail(CPLB_INVALID_ARGUMENT, "unknown component-major kernel choice %d", (int)kernel);
+    if (kernel == CPLB_KERNEL_PER_INSTANCE && p->layout.nc != 4 && p->layout.nc != 8)
+        return fail(CPLB_INVALID_ARGUMENT, "the thread-per-instance kernel exists for 4 and 8 contacts only (this problem has %d)", p->layout.nc);
+    p->cm_kernel = kernel == CPLB_KERNEL_AUTO ? CPLB_CM_AUTO : (kernel == CPLB_KERNEL_PER_CONTACT ? CPLB_CM_SPLIT : CPLB_CM_WHOLE);
+    return CPLB_OK;
+}
+
+cplb_status cplb_get_device(const cplb_problem* p, int32_t* device)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(device);
+    *device = p->device;
     return CPLB_OK;
 }
 
@@ -690,7 +710,7 @@ static bool any_instance_param(const cplb_instance_params* q)
 static cplb_status launch(cplb_problem* p, const CplbIo& io, int layout, unsigned flags, cudaStream_t st,
                           const CplbInstParams* q = nullptr)
 {
-    cudaError_t e = layout == CPLB_COMPONENT_MAJOR ? cplb::launch_component_major(p->P, io, flags, q, st)
+    cudaError_t e = layout == CPLB_COMPONENT_MAJOR ? cplb::launch_component_major(p->P, io, flags, q, p->cm_kernel, st)
                                                    : cplb::launch_instance_major(p->P, io, flags, q, st);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     p->launches.fetch_add(1, std::memory_order_relaxed);

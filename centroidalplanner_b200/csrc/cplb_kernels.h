@@ -9,8 +9,13 @@
 namespace cplb {
 
 // per_instance: optional per-instance parameter arrays (device pointers), nullptr = the shared parameter block.
-// buf[e*ld + i]: one thread per (instance, contact), fully coalesced.
-cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* per_instance, cudaStream_t st);
+// buf[e*ld + i]: fully coalesced; cm_kernel picks the kernel: auto (by shape and batch size), one thread per
+// (instance, contact) ["split"], or one thread per instance ["whole"; 4- and 8-contact shared-parameter batches only].
+#define CPLB_CM_AUTO 0
+#define CPLB_CM_SPLIT 1
+#define CPLB_CM_WHOLE 2
+cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* per_instance, int cm_kernel,
+                                   cudaStream_t st);
 // buf[i*len + e]: warp tiles staged through shared memory with bulk async (TMA) copies.
 cudaError_t launch_instance_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* per_instance, cudaStream_t st);
 

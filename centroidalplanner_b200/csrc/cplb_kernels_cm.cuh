@@ -216,8 +216,11 @@ __global__ void __launch_bounds__(128) eval_component_major_whole(const __grid_c
     }
 }
 
+// cm_kernel: CPLB_CM_AUTO (pick by shape and batch size, below), CPLB_CM_SPLIT, CPLB_CM_WHOLE (cplb_set_component_major_kernel:
+// parity tests and dispatch measurements run BOTH kernels on the same inputs; a forced `whole` silently stays with the split
+// kernel where the one-thread-per-instance kernel does not exist: per-instance parameters, contact counts other than 4 / 8).
 template <int ENV>
-cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
+cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, int cm_kernel, cudaStream_t st)
 {
     // two 32-instance sub-blocks per CTA when they fit in 256 threads (measured: 22.1 vs 22.5 us on config 2)
     const int subs = (P.nc <= 4) ? 2 : 1;
@@ -232,10 +235,7 @@ cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned flags,
     // closed-form normal Jacobian needs 250 registers and 320 B of local memory (2 CTAs per SM) and measures 64-65 % of the
     // roofline at 65,536 and 1,048,576 instances (profiles/r01_variants.md).
     const long long whole_from = P.nc == 4 ? 90112 : 49152;
-    static const int forced = [] {  // CPLB_CM_KERNEL=split|whole: dispatch experiments only (tools/variant_table.py)
-        const char* e = std::getenv("CPLB_CM_KERNEL");
-        return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'w' ? 2 : 0));
-    }();
+    const int forced = cm_kernel;
     const bool whole_ok = !Q && (P.nc == 4 || P.nc == 8);
     const bool whole_auto = io.N >= whole_from && !(ENV == CPLB_ENV_SUPERQUADRIC_K && P.nc == 8);
     if (whole_ok && (forced == 2 || (forced == 0 && whole_auto))) {
@@ -248,8 +248,10 @@ cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned flags,
         return launch_pdl(eval_component_major_whole<ENV, 8, 0u>, wb, 128u, 0, st, P, io, flags);
     }
     if (smem > 48 * 1024) {  // more than ~26 contacts: opt in to the larger dynamic shared memory (57 KB at 32 contacts)
-        cudaError_t e = cudaFuncSetAttribute(eval_component_major_split<ENV, 0u, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_component_major_split<ENV, 0u, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // the attribute is process-wide per device and must never shrink under a concurrent launch: always the 32-contact size
+        const int max_smem = (int)((size_t)CPLB_KMAX_CONTACTS * (192 + 32) * sizeof(double));
+        cudaError_t e = cudaFuncSetAttribute(eval_component_major_split<ENV, 0u, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eval_component_major_split<ENV, 0u, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) return e;
     }
     if (Q) {  // per-instance parameter arrays

@@ -2,5 +2,5 @@
 #include "cplb_kernels_cm.cuh"
 
 namespace cplb {
-template cudaError_t launch_cm_env<CPLB_ENV_GROUND_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, cudaStream_t);
+template cudaError_t launch_cm_env<CPLB_ENV_GROUND_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, int, cudaStream_t);
 }  // namespace cplb

@@ -3,9 +3,14 @@
 #ifndef CPLB_KERNELS_IM_CUH
 #define CPLB_KERNELS_IM_CUH
 
+#include <mutex>
+#include <vector>
+
 #include "cplb_launch.cuh"
 
 namespace cplb {
+
+constexpr int kMaxDevices = 64;
 
 // ================================================================================================
 // instance-major (AoS): warp tile, LPI lanes per instance, bulk async copies in and out
@@ -304,27 +309,43 @@ cudaError_t launch_im_kernel(const CplbParams& P, const CplbIo& io, unsigned fla
 {
     constexpr int T = 32 / LPI;
     auto kern = eval_instance_major<ENV, LPI, WARPS, FLAGS, PERINST>;
-    // resident CTAs per SM and the SM count are fixed per (kernel, smem, device): looked up once
-    struct Cfg { int device = -1; size_t smem = 0; int resident = 0; };
-    static thread_local Cfg cfg;
+    // Per kernel instantiation, process-wide: the opt-in dynamic shared memory limit of each device (only ever RAISED -- the
+    // attribute belongs to the function on a device, not to a thread, so lowering it for a smaller request would make a
+    // concurrent larger launch of another host thread fail) and the grid size that is resident at once per (device, smem).
+    struct Cfg {
+        std::mutex mu;
+        size_t limit[kMaxDevices] = {};
+        struct Entry { int device; size_t smem; int resident; };
+        std::vector<Entry> seen;
+    };
+    static Cfg cfg;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (cfg.device != dev || cfg.smem != smem) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0, sms = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        cfg.device = dev;
-        cfg.smem = smem;
-        cfg.resident = (per_sm > 0 ? per_sm : 1) * sms;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    int resident = 0;
+    {
+        std::lock_guard<std::mutex> lk(cfg.mu);
+        if (smem > cfg.limit[dev]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            cfg.limit[dev] = smem;
+        }
+        for (const auto& s : cfg.seen)
+            if (s.device == dev && s.smem == smem) resident = s.resident;
+        if (resident == 0) {
+            int per_sm = 0, sms = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+            if (e != cudaSuccess) return e;
+            e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+            resident = (per_sm > 0 ? per_sm : 1) * sms;
+            cfg.seen.push_back({dev, smem, resident});
+        }
     }
     const long long tiles = (io.N + T - 1) / T;
     const long long want = (tiles + WARPS - 1) / WARPS;
-    const unsigned blocks = (unsigned)(want < cfg.resident ? want : cfg.resident);
+    const unsigned blocks = (unsigned)(want < resident ? want : resident);
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     int aligned16 = al16(io.x) && al16(io.g) && al16(io.jac) && al16(io.grad) && (T % 2 == 0);
     if (Q) {

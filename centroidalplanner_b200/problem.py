@@ -317,6 +317,16 @@ class BatchedCplProblem:
     def SetMass(self, mass):
         _check(self._lib.cplb_set_mass(self._h, float(mass)))
 
+    def SetComponentMajorKernel(self, kernel):
+        """cplb_set_component_major_kernel: KERNEL_AUTO / KERNEL_PER_CONTACT / KERNEL_PER_INSTANCE (or 'auto', 'split', 'whole')."""
+        kernel = {"auto": _cabi.KERNEL_AUTO, "split": _cabi.KERNEL_PER_CONTACT, "whole": _cabi.KERNEL_PER_INSTANCE}.get(kernel, kernel)
+        _check(self._lib.cplb_set_component_major_kernel(self._h, int(kernel)))
+
+    def GetDevice(self):
+        d = C.c_int32()
+        _check(self._lib.cplb_get_device(self._h, C.byref(d)))
+        return d.value
+
     # ---- evaluation --------------------------------------------------------------------------
     def _shape(self, length, N, layout):
         return (N, length) if layout == _cabi.INSTANCE_MAJOR else (length, N)
@@ -332,13 +342,16 @@ class BatchedCplProblem:
         """Write the constant slots of a host jac buffer once; later host evaluations into the same buffer may then
         pass jac_constants_present=True and skip transferring them."""
         a = jac_host.numpy() if _is_torch(jac_host) else jac_host
-        assert a.dtype == np.float64 and a.flags.c_contiguous
+        if a.dtype != np.float64 or not a.flags.c_contiguous or a.ndim != 2:
+            raise ValueError("jac_host must be a C-contiguous 2-D float64 array")
         N = a.shape[0] if layout == _cabi.INSTANCE_MAJOR else a.shape[1]
+        if tuple(a.shape) != self._shape(self.nnz, N, layout):
+            raise ValueError(f"jac_host has shape {tuple(a.shape)}, expected {self._shape(self.nnz, N, layout)}")
         _check(self._lib.cplb_fill_jacobian_constants(self._h, N, layout, N, a.ctypes.data_as(_cabi.dp)))
 
     def _instance_params(self, per_instance, N, layout, on_device):
         """dict name -> array (cplb_instance_params fields) -> (ctypes struct, keep-alive list); shapes follow x's
-        layout: (N,) / (N, len) instance-major, (len, N) component-major."""
+        layout: (N,) / (N, len) instance-major, (len, N) component-major.  on_device: x's torch device, or None (host)."""
         if not per_instance:
             return None, []
         lens = {"mass": 1, "wrench": 6, "mu": 1, "force_threshold": len(self._names), "ground_z": 1, "com_ref": 3, "com_weight": 1,
@@ -349,12 +362,20 @@ class BatchedCplProblem:
             if name not in lens:
                 raise ValueError(f"unknown per-instance parameter '{name}'")
             L = lens[name]
-            if on_device:
-                assert arr.is_cuda and arr.is_contiguous() and arr.numel() == N * L, name
+            if on_device is not None:
+                import torch
+
+                if not (_is_torch(arr) and arr.is_cuda and arr.dtype == torch.float64 and arr.is_contiguous()):
+                    raise ValueError(f"per-instance array '{name}' must be a contiguous float64 CUDA tensor")
+                if arr.device != on_device:
+                    raise ValueError(f"per-instance array '{name}' lives on {arr.device}, x on {on_device}")
+                if arr.numel() != N * L:
+                    raise ValueError(f"per-instance array '{name}' has {arr.numel()} elements, expected {N} x {L}")
                 setattr(st, name, arr.data_ptr())
             else:
-                arr = np.ascontiguousarray(arr.numpy() if _is_torch(arr) else np.asarray(arr, dtype=np.float64))
-                assert arr.size == N * L, name
+                arr = np.ascontiguousarray(arr.numpy() if _is_torch(arr) else np.asarray(arr, dtype=np.float64), dtype=np.float64)
+                if arr.size != N * L:
+                    raise ValueError(f"per-instance array '{name}' has {arr.size} elements, expected {N} x {L}")
                 setattr(st, name, arr.ctypes.data)
             keep.append(arr)
         return st, keep
@@ -372,28 +393,40 @@ class BatchedCplProblem:
     def _eval_device(self, x, g, jac, cost, grad, layout, out, stream, per_instance=None, inputs_ready=False):
         import torch
 
-        assert x.dtype == torch.float64 and x.is_contiguous() and x.dim() == 2
+        if x.dtype != torch.float64 or not x.is_contiguous() or x.dim() != 2:
+            raise ValueError("x must be a contiguous 2-D float64 tensor")
         N = x.shape[0] if layout == _cabi.INSTANCE_MAJOR else x.shape[1]
-        assert tuple(x.shape) == self._shape(self.n, N, layout), (tuple(x.shape), self.n)
+        if tuple(x.shape) != self._shape(self.n, N, layout):
+            raise ValueError(f"x has shape {tuple(x.shape)}, expected {self._shape(self.n, N, layout)} for this layout")
+        bound = self.GetDevice()
+        if bound >= 0 and bound != x.device.index:
+            raise ValueError(f"this problem evaluates on cuda:{bound}; x lives on {x.device}")
 
         def buf(key, want, length):
             if not want:
                 return None
+            shape = (N,) if length is None else self._shape(length, N, layout)
             t = out.get(key)
             if t is None:
-                shape = (N,) if length is None else self._shape(length, N, layout)
-                t = torch.empty(shape, dtype=torch.float64, device=x.device)
-            assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+                return torch.empty(shape, dtype=torch.float64, device=x.device)
+            if not (_is_torch(t) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+                raise ValueError(f"out['{key}'] must be a contiguous float64 CUDA tensor")
+            if t.device != x.device:
+                raise ValueError(f"out['{key}'] lives on {t.device}, x on {x.device}")
+            if tuple(t.shape) != shape:
+                raise ValueError(f"out['{key}'] has shape {tuple(t.shape)}, expected {shape}")
             return t
 
         res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self.nnz), "cost": buf("cost", cost, None),
                "grad": buf("grad", grad, self.n)}
-        pi, keep = self._instance_params(per_instance, N, layout, True)
+        pi, keep = self._instance_params(per_instance, N, layout, x.device)
         args = _cabi.EvalArgs(N, layout, _cabi.DEVICE_INPUTS_READY if inputs_ready else 0, N, x.data_ptr(), *[None if res[k] is None else res[k].data_ptr()
                                                               for k in ("g", "jac", "cost", "grad")],
                               C.pointer(pi) if pi is not None else None)
         s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
-        _check(self._lib.cplb_eval_device(self._h, C.byref(args), C.c_void_p(s)))
+        # a problem created without a device binds to the calling thread's CURRENT device at its first evaluation: make that x's
+        with torch.cuda.device(x.device):
+            _check(self._lib.cplb_eval_device(self._h, C.byref(args), C.c_void_p(s)))
         return res
 
     def eval_host_begin(self, x, out, g=True, jac=True, cost=False, grad=False, layout=_cabi.INSTANCE_MAJOR,
@@ -410,23 +443,30 @@ class BatchedCplProblem:
         is_t = _is_torch(x)
         xa = x.numpy() if is_t else np.asarray(x, dtype=np.float64)
         xa = np.ascontiguousarray(xa)
+        if xa.ndim != 2:
+            raise ValueError("x must be 2-D")
         N = xa.shape[0] if layout == _cabi.INSTANCE_MAJOR else xa.shape[1]
-        assert xa.shape == self._shape(self.n, N, layout), (xa.shape, self.n)
+        if xa.shape != self._shape(self.n, N, layout):
+            raise ValueError(f"x has shape {xa.shape}, expected {self._shape(self.n, N, layout)} for this layout")
 
         def buf(key, want, length):
             if not want:
                 return None
+            shape = (N,) if length is None else self._shape(length, N, layout)
             t = out.get(key)
             if t is None:
-                return np.empty((N,) if length is None else self._shape(length, N, layout))
+                return np.empty(shape)
             t = t.numpy() if _is_torch(t) else t
-            assert t.dtype == np.float64 and t.flags.c_contiguous
+            if not isinstance(t, np.ndarray) or t.dtype != np.float64 or not t.flags.c_contiguous:
+                raise ValueError(f"out['{key}'] must be a C-contiguous float64 array")
+            if tuple(t.shape) != shape:
+                raise ValueError(f"out['{key}'] has shape {tuple(t.shape)}, expected {shape}")
             return t
 
         res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self.nnz), "cost": buf("cost", cost, None),
                "grad": buf("grad", grad, self.n)}
         hflags = _cabi.HOST_JAC_CONSTANTS_PRESENT if jac_constants_present else 0
-        pi, keep = self._instance_params(per_instance, N, layout, False)
+        pi, keep = self._instance_params(per_instance, N, layout, None)
         args = _cabi.EvalArgs(N, layout, hflags, N, xa.ctypes.data, *[None if res[k] is None else res[k].ctypes.data
                                                                      for k in ("g", "jac", "cost", "grad")],
                               C.pointer(pi) if pi is not None else None)

@@ -264,6 +264,20 @@ cplb_status cplb_fill_jacobian_constants(const cplb_problem *p, int64_t num_inst
 cplb_status cplb_host_alloc(size_t bytes, void **out);
 cplb_status cplb_host_free(void *ptr);
 
+/* Which of the two COMPONENT_MAJOR kernels evaluates this problem.  AUTO (default) picks by shape and batch size: one thread
+ * per (instance, contact) for small batches, one thread per instance once several waves of CTAs are in flight (4- and 8-contact
+ * problems with shared parameters; measured crossovers in DESIGN.md 4.1b).  The two kernels run the same arithmetic in the
+ * same order and must return the same bits: the parity tests force each of them on the same inputs, and dispatch
+ * measurements time both.  PER_INSTANCE on a problem with another contact count -> CPLB_INVALID_ARGUMENT; evaluations with
+ * per-instance parameter arrays always take the per-contact kernel.  No reference counterpart (the reference has one code path:
+ * src/Constraints/CentroidalStatics.cpp:37-61,75-138 et al.). */
+#define CPLB_KERNEL_AUTO 0
+#define CPLB_KERNEL_PER_CONTACT 1
+#define CPLB_KERNEL_PER_INSTANCE 2
+cplb_status cplb_set_component_major_kernel(cplb_problem *p, int32_t kernel);
+/* CUDA ordinal this problem evaluates on; -1 while a problem created with device = -1 has not evaluated yet. */
+cplb_status cplb_get_device(const cplb_problem *p, int32_t *device);
+
 /* Number of kernels this problem has launched so far (bench.py's gpu_launches). */
 cplb_status cplb_get_launch_count(const cplb_problem *p, int64_t *launches);
 /* Average device time (ms, CUDA events on the launch stream) of the kernels launched by

@@ -304,6 +304,18 @@ def test_queued_host_call_argument_checks():
             prob.eval_host_begin(x, {"g": np.zeros((4, prob.m))}, g=True, jac=False)
 
 
+def test_kernel_choice_validation():
+    """cplb_set_component_major_kernel: unknown choices and the thread-per-instance kernel on a problem it does not exist for
+    are refused (CPLB_INVALID_ARGUMENT -> ValueError); host-only, no GPU needed for the check itself."""
+    prob, _, _ = make_pair("ground5")
+    with pytest.raises(ValueError, match="4 and 8 contacts"):
+        prob.SetComponentMajorKernel("whole")
+    with pytest.raises(ValueError, match="unknown"):
+        prob.SetComponentMajorKernel(7)
+    prob.SetComponentMajorKernel(_cabi.KERNEL_PER_CONTACT)
+    prob.SetComponentMajorKernel(_cabi.KERNEL_AUTO)
+
+
 def test_header_is_valid_c99_and_usable_from_plain_c(tmp_path):
     """include/cpl_batched.h compiled by gcc as strict C99 and driven from a C program (no C++, no Python, no GPU)."""
     import shutil
