@@ -9,18 +9,22 @@ launch) of BASELINE.json configs[1]: 65,536 synthetic 4-contact flat-ground inst
 Instances shard by index across ranks with no collective on the data path (weak scaling: every
 rank evaluates its own 65,536-instance shard).  Prints ONE JSON line (rank 0).
 
-  value     instances/s, inputs resident in HBM, K back-to-back launches bracketed by CUDA events
-            on the launch stream; successive steps rotate through buffer sets whose total size
+  value     instances/s, inputs resident in HBM: K back-to-back launches bracketed by CUDA events on the
+            launch stream, max over ranks; the region is repeated (`timed_regions`) and the MEDIAN region
+            is reported, min/max beside it.  Successive steps rotate through buffer sets whose total size
             is >> L2, so every step reads and writes HBM, not L2.
+  plain_order   the same measurement without CPLB_DEVICE_INPUTS_READY (x may be the preceding kernel's output).
+  configs   the other BASELINE.json configurations in the same run: config 3 (65,536 x 4-contact Superquadric)
+            with its own roofline, config 4 (1,048,576 x 8 contacts, permuted names, STRONG scaling: N/G per rank).
   e2e       the same metric through the host-buffer API: HOST (pinned) buffers in, host buffers out, every
-            step's H2D and D2H copies inside the timed region; a queue of batches (cplb_eval_host_begin /
-            _wait), with the one-batch-at-a-time cplb_eval_host figure beside it.
+            step's H2D and D2H copies inside the timed region; next to it the raw PCIe ceiling of the same
+            bytes measured on all ranks at once.
   roofline  algorithmic bytes per launch (8*(n+m+nnz) per instance) / average launch
             duration over the timed region, against MEASURED_PEAKS.json's HBM copy bandwidth.
-  cpu_baseline  the CPU oracle (port of the reference's evaluation) timed on this box's host cores.
+  cpu_baseline  the reference's own CPU evaluation and the lean C port, timed on this box's host cores.
 
 --impl reference times the reference's own CPU evaluation (oracle/_ref when it was built from the
-reference sources, else the oracle port) on all host cores, same config/metric.
+reference sources, else the oracle port) on all host cores: same config, all 65,536 instances per step.
 """
 from __future__ import annotations
 
@@ -41,8 +45,13 @@ import numpy as np  # noqa: E402
 
 N_PER_GPU = 65536
 NC = 4
+N_CONFIG4 = 1 << 20
 WORKLOAD = "configs[1]: 65,536 synthetic 4-contact flat-ground instances per GPU, fused g+Jacobian eval"
+# identical in both arms (--impl ours / --impl reference): what is evaluated, not how
+CONFIG = {"workload": WORKLOAD, "num_contacts": NC, "env": "Ground", "instances_per_gpu": N_PER_GPU, "outputs": "g+jac",
+          "params": "shared (TestBasic.cpp:64-99 parameter set)", "inputs": "synthetic.ground_batch(65536, 4, seed 1002 + 7919*rank)"}
 L2_BYTES = 126 * 1024 * 1024
+METRIC = "constraint+Jacobian evals/sec (instances/s)"
 
 
 def algorithmic_bytes_per_instance(n, m, nnz):
@@ -68,7 +77,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed regions run (B200_PROFILING.md recipe)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index):
         self.index = index
@@ -91,27 +100,40 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, busy, reasons = [], [], [], set()
         for line in out.splitlines():
             f = [t.strip() for t in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                busy.append(float(f[9]) > 0.0)
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        # "under load" = samples with non-zero GPU utilisation: the run alternates device-bound legs with host-bound ones
+        # (pinned allocations, input generation) during which an idle GPU drops its clocks
+        hot = [v for v, b in zip(sm, busy) if b] or sm
+        return {"sm_mhz": statistics.median(hot) if hot else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(hot), "sm_mhz_all_samples_median": statistics.median(sm) if sm else None}
 
 
 def make_inputs(rank):
     from centroidalplanner_b200 import synthetic
 
     return synthetic.ground_batch(N_PER_GPU, NC, seed=1002 + 7919 * rank)
+
+
+def config4_shard(lo, hi):
+    """Instances [lo, hi) of config 4's 1,048,576 x 8-contact batch; seeded per 65,536-instance block so the batch does not
+    depend on how many ranks share it."""
+    from centroidalplanner_b200 import synthetic
+
+    blocks = [synthetic.ground_batch(65536, 8, seed=1004 + b) for b in range(lo // 65536, (hi + 65535) // 65536)]
+    return np.concatenate(blocks)[lo - (lo // 65536) * 65536:][:hi - lo]
 
 
 def configure(problem_like, env_like):
@@ -132,62 +154,61 @@ def oracle_problem():
     return op.o
 
 
-def time_cpu(o, x, threads, budget_s=10.0, want=("g", "jac")):
-    """Bounded CPU sample: repeat the 65,536-instance batch until ~budget_s of wall time is spent."""
-    out = {"g": np.empty((x.shape[0], o.m)), "jac": np.empty((x.shape[0], o.nnz))}
-    o.eval_batch(x[:4096], want=want, nthreads=threads)  # warm-up
-    t0 = time.perf_counter()
-    o.eval_batch(x, want=want, nthreads=threads, out=out)
-    one = time.perf_counter() - t0
-    reps = max(1, min(50, int(budget_s / max(one, 1e-6))))
-    best = one
-    for _ in range(reps):
+def time_cpu(fn, n_instances, budget_s, max_passes=50):
+    """Bounded CPU sample: repeat fn() (one pass over n_instances) until ~budget_s of wall time is spent.  Returns
+    (instances/s over all timed passes -- the way --impl reference computes its value --, passes, best-pass instances/s)."""
+    fn()  # warm-up pass (page faults of the output arrays, thread start-up)
+    best, spent, passes = 1e30, 0.0, 0
+    while passes < 2 or (spent < budget_s and passes < max_passes):
         t0 = time.perf_counter()
-        o.eval_batch(x, want=want, nthreads=threads, out=out)
-        best = min(best, time.perf_counter() - t0)
-    return x.shape[0] / best, reps + 1
+        fn()
+        dt = time.perf_counter() - t0
+        best, spent, passes = min(best, dt), spent + dt, passes + 1
+    return n_instances * passes / spent, passes, n_instances / best
+
+
+def reference_callable(x, cores):
+    """The reference's CPU evaluation of the whole batch x into preallocated outputs -> (fn, kind, description)."""
+    from centroidalplanner_b200 import synthetic
+
+    from oracle import cpl_ref_py
+
+    N = x.shape[0]
+    if cpl_ref_py.available():
+        r = cpl_ref_py.RefProblem(synthetic.NAMES4, "ground", 100.0)
+        configure(r, r)
+        out = {"g": np.empty((N, r.m)), "jac": np.empty((N, r.nnz))}
+        return (lambda: r.eval_batch(x, want=("g", "jac"), nthreads=cores, out=out), "reference",
+                f"all {N} instances per step through the reference's own sources (CplProblem + its IFOPT components, "
+                "Problem::EvaluateConstraints + EvalNonzerosOfJacobian per instance) compiled in place against stand-in Eigen/ifopt "
+                f"headers (oracle/_ref; sparse blocks = sorted inner vectors like Eigen's), one CplProblem per thread, {cores} threads")
+    o = oracle_problem()
+    out = {"g": np.empty((N, o.m)), "jac": np.empty((N, o.nnz))}
+    return (lambda: o.eval_batch(x, want=("g", "jac"), nthreads=cores, out=out), "port",
+            f"all {N} instances per step through the C oracle port (oracle/_ref was not built), {cores} threads")
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU evaluation on the host cores, rank 0 only."""
+    """--impl reference: the reference's CPU evaluation on the host cores, rank 0 only; same config as the GPU arm
+    (all 65,536 instances per step), --steps and --warmup honoured."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
     x = make_inputs(0)
-    kind, sample = "port", ""
-    ref_lib = os.path.join(ROOT, "oracle", "_ref", "libcpl_ref.so")
-    per_step = []
-    if os.path.exists(ref_lib):
-        from oracle import cpl_ref_py
-
-        r = cpl_ref_py.RefProblem(__import__("centroidalplanner_b200").synthetic.NAMES4, "ground", 100.0)
-        configure(r, r)
-        kind = "reference"
-        n_s = min(N_PER_GPU, 8192)
-        fn = lambda: r.eval_batch(x[:n_s], nthreads=cores)  # noqa: E731
-        sample = (f"{n_s} of the 65,536 instances per step through the reference's own ifopt components "
-                  f"(oracle/_ref: reference sources compiled against stand-in Eigen/ifopt headers), {cores} threads")
-    else:
-        o = oracle_problem()
-        n_s = N_PER_GPU
-        buf = {"g": np.empty((n_s, o.m)), "jac": np.empty((n_s, o.nnz))}
-        fn = lambda: o.eval_batch(x, want=("g", "jac"), nthreads=cores, out=buf)  # noqa: E731
-        sample = f"all 65,536 instances per step through the C oracle port, {cores} threads"
-    for _ in range(max(1, min(args.warmup, 3))):
+    fn, kind, sample = reference_callable(x, cores)
+    W, K = max(0, args.warmup), max(1, args.steps)
+    for _ in range(W):
         fn()
-    steps = max(1, min(args.steps, 20))
     t_all = time.perf_counter()
-    for _ in range(steps):
-        t0 = time.perf_counter()
+    for _ in range(K):
         fn()
-        per_step.append(time.perf_counter() - t0)
     total = time.perf_counter() - t_all
-    value = n_s * steps / total
-    line = {"impl": "reference", "metric": "constraint+Jacobian evals/sec (instances/s)", "value": value, "unit": "instances/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * total / steps,
+    value = N_PER_GPU * K / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "instances/s",
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * total / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "num_contacts": NC, "env": "Ground"},
+            "config": dict(CONFIG),
             "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -209,7 +230,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import centroidalplanner_b200 as cpl
-    from centroidalplanner_b200 import _cabi, synthetic
+    from centroidalplanner_b200 import _cabi, sharding, synthetic
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the evaluator has no CPU fallback (use --impl reference for the CPU arm)")
@@ -220,48 +241,50 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    env = cpl.Ground()
-    prob = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, env, device=local)
-    configure(prob, env)
-    n, m, nnz = prob.n, prob.m, prob.nnz
-    N = N_PER_GPU
-    bytes_per_launch = algorithmic_bytes_per_instance(n, m, nnz) * N
-    layout = cpl.INSTANCE_MAJOR if args.layout == "instance" else cpl.COMPONENT_MAJOR
-
-    x_host = make_inputs(rank)
     stream = torch.cuda.current_stream(dev)
-    W, K = max(3, args.warmup), args.steps
-    # buffer sets: total footprint >> L2 so no step finds its lines in L2
-    sets = max(4, int(np.ceil(8 * L2_BYTES / bytes_per_launch)))
+    W, K = max(3, args.warmup), max(1, args.steps)
+    R = max(1, args.regions)
+    peak, peak_src = measured_peak()
+    lname = {cpl.INSTANCE_MAJOR: "instance-major", cpl.COMPONENT_MAJOR: "component-major"}
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def time_layout(lay):
-        """W warm-up + K timed back-to-back evaluations in one buffer layout; returns (ms_per_step, launches, ...)."""
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure(prob, x_im, lay, ready, regions, use_graph=True, event_pairs=False):
+        """W warm-up steps, then `regions` timed regions of EXACTLY K back-to-back g+Jacobian evaluations each (CUDA events on the
+        launch stream, barrier + synchronize on both sides, max over ranks per region).  Steps rotate through buffer sets
+        whose total footprint is >> L2.  Returns dict(ms=[per-region ms/step], launches=..., sets=..., launch=..., ev_ms, ev_k)."""
+        N = x_im.shape[0]
+        n, m, nnz = prob.n, prob.m, prob.nnz
+        per_launch = algorithmic_bytes_per_instance(n, m, nnz) * N
+        sets = max(3, int(np.ceil(8 * L2_BYTES / per_launch)))
         shp = (lambda length: (N, length)) if lay == cpl.INSTANCE_MAJOR else (lambda length: (length, N))
-        base = torch.from_numpy(x_host if lay == cpl.INSTANCE_MAJOR else np.ascontiguousarray(x_host.T)).to(dev)
-        xs = [base.clone() for _ in range(sets)]
+        base = torch.from_numpy(x_im if lay == cpl.INSTANCE_MAJOR else np.ascontiguousarray(x_im.T)).to(dev)
+        xs = [base] + [base.clone() for _ in range(sets - 1)]
         gs = [torch.empty(shp(m), dtype=torch.float64, device=dev) for _ in range(sets)]
         js = [torch.empty(shp(nnz), dtype=torch.float64, device=dev) for _ in range(sets)]
 
         def step(i):
             s = i % sets
-            # inputs_ready: the x buffers are resident and never written by a kernel (the metric's "inputs already in HBM")
-            prob.eval(xs[s], g=True, jac=True, layout=lay, out={"g": gs[s], "jac": js[s]}, inputs_ready=not args.no_inputs_ready)
+            prob.eval(xs[s], g=True, jac=True, layout=lay, out={"g": gs[s], "jac": js[s]}, inputs_ready=ready)
 
         for i in range(W):
             step(i)
         barrier()
-        # The K timed steps are issued as replays of a CUDA graph holding one rotation over the buffer sets
-        # (`sets` evaluation kernels, captured from the same cplb_eval_device calls) plus a plain-launch remainder:
-        # at ~20 us per kernel the per-launch host path and inter-kernel launch gap would otherwise be >10% of the step.
+        # The K timed steps are issued as replays of a CUDA graph holding one rotation over the buffer sets (`sets`
+        # evaluation kernels, captured from the same cplb_eval_device calls) plus a plain-launch remainder: at ~20 us per
+        # kernel the per-launch host path of the Python caller would otherwise be inside the step.
         graph = None
         gsteps = min(K, sets)
-        if not args.no_graph and gsteps >= 2:
+        if use_graph and not args.no_graph and gsteps >= 2:
             side = torch.cuda.Stream(dev)
             side.wait_stream(stream)
             with torch.cuda.stream(side):
@@ -273,104 +296,250 @@ def run_ours(args):
             graph.replay()  # one untimed replay (upload / first-run cost)
             barrier()
         reps, rem = (K // gsteps, K % gsteps) if graph is not None else (0, K)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(reps):
-            graph.replay()
-        for i in range(rem):
-            step(W + i)
-        e1.record(stream)
-        barrier()
-        ms_total = e0.elapsed_time(e1)
-        n_launch = reps * gsteps + rem  # evaluation kernels executed inside the timed region
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # per-launch device time with an event pair around every launch (same stream), second pass
-        prob.timing_begin()
-        for i in range(min(K, 200)):
-            step(W + K + i)
-        torch.cuda.synchronize(dev)
-        ev_ms, ev_k = prob.timing_end()
-        del xs, gs, js
-        return float(t.item()) / K, n_launch, ev_ms, ev_k
+        ms = []
+        for _ in range(regions):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                graph.replay()
+            for i in range(rem):
+                step(W + i)
+            e1.record(stream)
+            barrier()
+            ms.append(max_over_ranks(e0.elapsed_time(e1)) / K)
+        ev_ms = ev_k = None
+        if event_pairs:  # per-launch device time with an event pair around every launch (same stream), separate pass
+            prob.timing_begin()
+            for i in range(min(K, 200)):
+                step(W + K + i)
+            torch.cuda.synchronize(dev)
+            ev_ms, ev_k = prob.timing_end()
+        del xs, gs, js, base, graph
+        torch.cuda.empty_cache()
+        launch = ("plain launches" if reps == 0 else
+                  f"CUDA graph of {gsteps} evaluation kernels replayed {reps}x + {rem} plain launches")
+        return {"ms": ms, "launches": reps * gsteps + rem, "sets": sets, "launch": launch, "ev_ms": ev_ms, "ev_k": ev_k,
+                "bytes_per_launch": per_launch}
+
+    def spread(ms):
+        return {"n": len(ms), "min": min(ms), "median": statistics.median(ms), "max": max(ms)}
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
 
-    ms_per_step, launches, ev_ms, ev_k = time_layout(layout)
+    # ---- config 2 (the headline): 65,536 x 4-contact Ground per GPU -----------------------------------------------
+    env = cpl.Ground()
+    prob = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, env, device=local)
+    configure(prob, env)
+    n, m, nnz = prob.n, prob.m, prob.nnz
+    N = N_PER_GPU
+    layout = cpl.INSTANCE_MAJOR if args.layout == "instance" else cpl.COMPONENT_MAJOR
     other = cpl.COMPONENT_MAJOR if layout == cpl.INSTANCE_MAJOR else cpl.INSTANCE_MAJOR
-    other_ms, _, other_ev_ms, _ = time_layout(other)
-    value = world * N / (ms_per_step * 1e-3)
-    lname = {cpl.INSTANCE_MAJOR: "instance-major", cpl.COMPONENT_MAJOR: "component-major"}
     kname = {cpl.INSTANCE_MAJOR: "eval_instance_major", cpl.COMPONENT_MAJOR: "eval_component_major_split"}
-    shape = (lambda length: (N, length))  # the e2e leg below uses instance-major host buffers
+    x_host = make_inputs(rank)
+    ready = not args.no_inputs_ready
+    launches0 = prob.launch_count()
+    head = measure(prob, x_host, layout, ready, R, event_pairs=True)
+    bytes_per_launch = head["bytes_per_launch"]
+    ms_per_step = statistics.median(head["ms"])
+    value = world * N / (ms_per_step * 1e-3)
+    plain = measure(prob, x_host, layout, False, R)
+    oth = measure(prob, x_host, other, ready, min(R, 3))
+    oth_plain = measure(prob, x_host, other, False, min(R, 3))
 
-    # ---- e2e: host buffers through cplb_eval_host -------------------------------------------
+    def frac(ms, bytes_=bytes_per_launch, gpus=1):
+        return bytes_ / (ms * 1e-3) / 1e9 / (gpus * peak)
+
+    # ---- config 3: 65,536 x 4-contact Superquadric (TestBasic.cpp:150-157 shape), same measurement -------------------
+    sq_env = cpl.Superquadric()
+    sq = synthetic.SUPERQUADRIC
+    sq_env.SetParameters(sq["C"], sq["R"], sq["P"])
+    sq_env.SetMu(sq["mu"])
+    sq_prob = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, sq_env, device=local)
+    sq_prob.SetManipulationWrench(synthetic.TESTBASIC["wrench"])
+    x3 = synthetic.superquadric_batch(N, NC, seed=1003 + 7919 * rank)
+    c3 = {lay: measure(sq_prob, x3, lay, ready, min(R, 3)) for lay in (cpl.COMPONENT_MAJOR, cpl.INSTANCE_MAJOR)}
+    c3_plain = measure(sq_prob, x3, cpl.COMPONENT_MAJOR, False, min(R, 3))
+    del x3
+
+    # ---- config 4: 1,048,576 x 8-contact Ground, names permuted, STRONG scaling (N/G instances per rank) ------------
+    env8 = cpl.Ground()
+    env8.SetGroundZ(synthetic.TESTBASIC["ground_z"])
+    env8.SetMu(synthetic.TESTBASIC["mu"])
+    prob8 = cpl.BatchedCplProblem(synthetic.NAMES8, 100.0, env8, device=local)
+    prob8.SetManipulationWrench(synthetic.TESTBASIC["wrench"])
+    lo, hi = sharding.local_range(N_CONFIG4, rank, world)
+    x4 = config4_shard(lo, hi)
+    c4 = measure(prob8, x4, cpl.COMPONENT_MAJOR, ready, min(R, 3), use_graph=False)
+    c4_plain = measure(prob8, x4, cpl.COMPONENT_MAJOR, False, min(R, 3), use_graph=False)
+    c4_im = measure(prob8, x4, cpl.INSTANCE_MAJOR, ready, min(R, 3), use_graph=False)
+    bytes4_total = algorithmic_bytes_per_instance(prob8.n, prob8.m, prob8.nnz) * N_CONFIG4
+    del x4
+    launches_total = prob.launch_count() - launches0 + sq_prob.launch_count() + prob8.launch_count()
+
+    # ---- e2e: host buffers through cplb_eval_host[_begin/_wait] -------------------------------------------------------
     lib = _cabi.load()
-    hx, px = pinned_array(lib, shape(n))
-    hg, pg = pinned_array(lib, shape(m))
-    hj, pj = pinned_array(lib, shape(nnz))
+    shape = (lambda length: (N, length))  # instance-major: what an IPOPT thread consumes (x[n] -> g[m], values[nnz] slices)
+    pinned = []
+
+    def pin(shp):
+        a, p = pinned_array(lib, shp)
+        pinned.append(p)
+        return a
+
+    hx, hg, hj = pin(shape(n)), pin(shape(m)), pin(shape(nnz))
+    hx2, hg2, hj2 = pin(shape(n)), pin(shape(m)), pin(shape(nnz))
     hx[...] = x_host
-    e2e_steps = max(3, min(K, 20))
-    e2e_layout = cpl.INSTANCE_MAJOR  # what an IPOPT thread consumes: its instance's x[n] -> g[m], values[nnz] slices
-    for _ in range(2):
-        prob.eval(hx, g=True, jac=True, layout=e2e_layout, out={"g": hg, "jac": hj})
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        prob.eval(hx, g=True, jac=True, layout=e2e_layout, out={"g": hg, "jac": hj})  # synchronous: outputs landed
-    torch.cuda.synchronize(dev)
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_check = float(np.abs(hg).sum())  # touch the result on the host
-    # the same call for a queue of batches (cplb_eval_host_begin / _wait, two pinned buffer sets: begin k+1, wait k) -- the
-    # host-side counterpart of the device-side `value`, which also runs a queue of independent batches back to back
-    hx2, px2 = pinned_array(lib, shape(n))
-    hg2, pg2 = pinned_array(lib, shape(m))
-    hj2, pj2 = pinned_array(lib, shape(nnz))
     hx2[...] = x_host
+    e2e_steps = max(3, min(K, 20))
+    e2e_layout = cpl.INSTANCE_MAJOR
+
+    def wall(fn, regions=3):
+        """`regions` wall-clock regions of e2e_steps calls each (barrier + synchronize on both sides), max over ranks; median."""
+        t = []
+        for _ in range(regions):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(dev)
+            t.append(max_over_ranks((time.perf_counter() - t0) / e2e_steps))
+        return statistics.median(t), t
+
+    def sync_calls():
+        for _ in range(e2e_steps):
+            prob.eval(hx, g=True, jac=True, layout=e2e_layout, out={"g": hg, "jac": hj})  # returns when the outputs have landed
+
     bufsets = [(hx, {"g": hg, "jac": hj}), (hx2, {"g": hg2, "jac": hj2})]
-    for b in range(2):
-        prob.eval_host_wait(prob.eval_host_begin(bufsets[b][0], bufsets[b][1], g=True, jac=True, layout=e2e_layout)[0])
-    barrier()
-    t0 = time.perf_counter()
-    pending = None
-    for k in range(e2e_steps):
-        ticket, _ = prob.eval_host_begin(bufsets[k % 2][0], bufsets[k % 2][1], g=True, jac=True, layout=e2e_layout)
-        if pending is not None:
-            prob.eval_host_wait(pending)     # batch k-1 has landed in its host buffers
-        pending = ticket
-    prob.eval_host_wait(pending)
-    e2e_q_s = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_q_s], dtype=torch.float64, device=dev)
+
+    def queued_calls():
+        pending = None
+        for k in range(e2e_steps):
+            ticket, _ = prob.eval_host_begin(bufsets[k % 2][0], bufsets[k % 2][1], g=True, jac=True, layout=e2e_layout)
+            if pending is not None:
+                prob.eval_host_wait(pending)     # batch k-1 has landed in its host buffers
+            pending = ticket
+        prob.eval_host_wait(pending)
+
+    # packed Jacobian slices (CPLB_JAC_PACKED): only the x-dependent slots travel; what the IFOPT views consume
+    nv = len(prob.GetPackedJacobianMap())
+    hjp, hjp2 = pin((N, nv)), pin((N, nv))
+    pk_sets = [(hx, {"g": hg, "jac": hjp}), (hx2, {"g": hg2, "jac": hjp2})]
+
+    def packed_calls():
+        pending = None
+        for k in range(e2e_steps):
+            ticket, _ = prob.eval_host_begin(pk_sets[k % 2][0], pk_sets[k % 2][1], g=True, jac=True, layout=e2e_layout, jac_packed=True)
+            if pending is not None:
+                prob.eval_host_wait(pending)
+            pending = ticket
+        prob.eval_host_wait(pending)
+
+    def packed_sync_calls():
+        for _ in range(e2e_steps):
+            prob.eval(hx, g=True, jac=True, layout=e2e_layout, out={"g": hg, "jac": hjp}, jac_packed=True)
+
+    sync_calls()
+    e2e_s, _ = wall(sync_calls)
+    e2e_check = float(np.abs(hg).sum())  # touch the result on the host
+    queued_calls()
+    e2e_q_s, e2e_q_all = wall(queued_calls)
+    assert float(np.abs(hg2).sum()) == e2e_check, "queued host evaluation differs from the synchronous one"
+    packed_calls()
+    e2e_p_s, e2e_p_all = wall(packed_calls)
+    # the packed slices are the same bits as the same slots of the full rows, and unpack to the full rows
+    pmap = prob.GetPackedJacobianMap()
+    assert np.array_equal(hjp2.view(np.int64), hj2[:, pmap].view(np.int64)), "packed Jacobian slices differ from the full rows"
+    assert np.array_equal(prob.UnpackJacobian(hjp2[:512]).view(np.int64), hj2[:512].view(np.int64))
+    packed_sync_calls()
+    e2e_ps_s, _ = wall(packed_sync_calls)
+    h2d_bytes, d2h_bytes = 8 * n * N, 8 * (m + nnz) * N
+    d2h_packed = 8 * (m + nv) * N
+
+    # raw PCIe ceiling of exactly these bytes, ALL ranks at once: one D2H copy of the g + Jacobian bytes and one H2D copy of the
+    # x bytes per step on two streams, pinned buffers, nothing else -- what the host side of this box can move when every GPU asks
+    def pcie_ceiling(d2h_bytes):
+        d_out = torch.empty(d2h_bytes // 8, dtype=torch.float64, device=dev)
+        d_in = torch.empty(h2d_bytes // 8, dtype=torch.float64, device=dev)
+        h_out = torch.empty(d2h_bytes // 8, dtype=torch.float64).pin_memory()
+        h_in = torch.empty(h2d_bytes // 8, dtype=torch.float64).pin_memory()
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def steps():
+            for _ in range(e2e_steps):
+                with torch.cuda.stream(s1):
+                    h_out.copy_(d_out, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    d_in.copy_(h_in, non_blocking=True)
+            s1.synchronize()
+            s2.synchronize()
+
+        steps()
+        med, _ = wall(steps)
+        return med
+
+    ceil_s = pcie_ceiling(d2h_bytes)
+    ceil_p_s = pcie_ceiling(d2h_packed)
+
+    # the same queue of packed batches driven IN ONE PROCESS over all GPUs of the run through a sharded problem
+    # (cplb_create_sharded: one set of host buffers for world x 65,536 instances, every device's pipeline driven by the calling
+    # thread); rank 0 only, the other ranks idle at the barrier meanwhile
+    sharded = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_q_s = float(t.item())
-    e2e_q_check = float(np.abs(hg2).sum())
-    assert e2e_q_check == e2e_check, "queued host evaluation differs from the synchronous one"
+        barrier()
+        if rank == 0:
+            env_s = cpl.Ground()
+            shp = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, env_s, devices=list(range(world)))
+            configure(shp, env_s)
+            NT = world * N
+            sx = [pin((NT, n)), pin((NT, n))]
+            sg = [pin((NT, m)), pin((NT, m))]
+            sj = [pin((NT, nv)), pin((NT, nv))]
+            for b in range(2):
+                for r in range(world):
+                    sx[b][r * N:(r + 1) * N] = x_host
+
+            def sharded_calls():
+                pending = None
+                for k in range(e2e_steps):
+                    ticket, _ = shp.eval_host_begin(sx[k % 2], {"g": sg[k % 2], "jac": sj[k % 2]}, g=True, jac=True, layout=e2e_layout, jac_packed=True)
+                    if pending is not None:
+                        shp.eval_host_wait(pending)
+                    pending = ticket
+                shp.eval_host_wait(pending)
+
+            sharded_calls()
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                sharded_calls()
+                ts.append((time.perf_counter() - t0) / e2e_steps)
+            assert np.array_equal(sj[1][:N].view(np.int64), hjp2.view(np.int64)) and np.array_equal(sj[1][-N:].view(np.int64), hjp2.view(np.int64))
+            t_sh = statistics.median(ts)
+            sharded = {"value": NT / t_sh, "ms_per_step": 1e3 * t_sh, "instances_per_step": NT, "devices": world,
+                       "h2d_bytes_per_step": 8 * n * NT, "d2h_bytes_per_step": 8 * (m + nv) * NT,
+                       "api": "cplb_create_sharded + cplb_eval_host_begin / _wait with CPLB_JAC_PACKED: ONE process, one set of pinned host "
+                              f"buffers for {world} x 65,536 instances, contiguous index ranges per GPU, no collective"}
+        barrier()
+
     # component-major host buffers, x-independent Jacobian slots (whole rows there) pre-filled once and not re-transferred
     cmask, _ = prob.GetJacobianConstants()
     n_var = int((~cmask).sum())
     hxc, hgc, hjc = hx.reshape(n, N), hg.reshape(m, N), hj.reshape(nnz, N)
     hxc[...] = x_host.T
     prob.FillJacobianConstants(hjc, layout=cpl.COMPONENT_MAJOR)
-    prob.eval(hxc, g=True, jac=True, layout=cpl.COMPONENT_MAJOR, out={"g": hgc, "jac": hjc}, jac_constants_present=True)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        prob.eval(hxc, g=True, jac=True, layout=cpl.COMPONENT_MAJOR, out={"g": hgc, "jac": hjc}, jac_constants_present=True)
-    torch.cuda.synchronize(dev)
-    e2e_cm_s = (time.perf_counter() - t0) / e2e_steps
+
+    def cm_calls():
+        for _ in range(e2e_steps):
+            prob.eval(hxc, g=True, jac=True, layout=cpl.COMPONENT_MAJOR, out={"g": hgc, "jac": hjc}, jac_constants_present=True)
+
+    cm_calls()
+    e2e_cm_s, _ = wall(cm_calls)
 
     # optional final gather of the per-rank output slices (NCCL all_gather over NVLink), timed apart from the evaluation
     gather = None
     if world > 1:
-        from centroidalplanner_b200 import sharding
-
         gl = {"g": torch.empty((N, m), dtype=torch.float64, device=dev), "jac": torch.empty((N, nnz), dtype=torch.float64, device=dev)}
         sharding.gather_outputs(gl, world * N)
         barrier()
@@ -380,93 +549,134 @@ def run_ours(args):
             full = sharding.gather_outputs(gl, world * N)
         g1.record(stream)
         barrier()
-        tg = torch.tensor([g0.elapsed_time(g1) / 5], dtype=torch.float64, device=dev)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(tg.item()), "bytes_per_rank_out": 8 * (m + nnz) * N * world,
+        gather = {"ms": max_over_ranks(g0.elapsed_time(g1) / 5), "bytes_per_rank_out": 8 * (m + nnz) * N * world,
                   "note": "all_gather of g and jac slices to every rank; NOT part of value/ms_per_step"}
         del full, gl
 
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+        plain_ms = statistics.median(plain["ms"])
+        oth_ms, oth_plain_ms = statistics.median(oth["ms"]), statistics.median(oth_plain["ms"])
+        c3_ms = {lay: statistics.median(c3[lay]["ms"]) for lay in c3}
+        c3_plain_ms = statistics.median(c3_plain["ms"])
+        c4_ms, c4_plain_ms, c4_im_ms = (statistics.median(c["ms"]) for c in (c4, c4_plain, c4_im))
         line = {
-            "metric": "constraint+Jacobian evals/sec (instances/s)", "value": value, "unit": "instances/s",
+            "metric": METRIC, "value": value, "unit": "instances/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "num_contacts": NC, "env": "Ground", "instances_per_gpu": N,
-                       "layout": lname[layout],
-                       "outputs": "g+jac", "params": "shared",
-                       "inputs_ready": (not args.no_inputs_ready) and "x buffers are resident and not produced by the preceding kernel: "
-                                       "CPLB_DEVICE_INPUTS_READY lets each kernel load x before waiting for the previous one (outputs still in stream order)",
-                       "launch": "plain launches" if args.no_graph or min(K, sets) < 2 else
-                       f"CUDA graph of {min(K, sets)} evaluation kernels replayed {K // min(K, sets)}x + {K % min(K, sets)} plain launches",
-                       "l2": f"inputs larger than L2: steps rotate through {sets} buffer sets, {sets * bytes_per_launch / 2**20:.0f} MiB total vs 126 MiB L2"},
-            "e2e": {"value": world * N / e2e_q_s, "unit": "instances/s", "h2d_bytes_per_step": world * 8 * n * N,
-                    "d2h_bytes_per_step": world * 8 * (m + nnz) * N, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_q_s,
-                    "api": "cplb_eval_host_begin / cplb_eval_host_wait: a queue of batches on two sets of instance-major pinned host "
-                           "buffers (begin k+1, wait k); every step uploads its x and downloads its g + Jacobian; chunked "
-                           "H2D/kernel/D2H on 3 streams",
-                    "synchronous_call": {"value": world * N / e2e_s, "ms_per_step": 1e3 * e2e_s,
-                                         "api": "cplb_eval_host: one batch at a time, returns when its outputs have landed"},
+            "config": dict(CONFIG),
+            "timing": {"layout": lname[layout],
+                       "timed_regions": dict(spread(head["ms"]), unit="ms_per_step", all=head["ms"],
+                                             note=f"{R} timed regions of exactly {K} steps each; value/ms_per_step = the median region"),
+                       "inputs_ready": ready and "x buffers are resident and not produced by the preceding kernel: CPLB_DEVICE_INPUTS_READY lets "
+                                       "each kernel load x before waiting for the previous one (outputs still in stream order); "
+                                       "plain_order below is the same measurement without it",
+                       "launch": head["launch"],
+                       "l2": f"inputs larger than L2: steps rotate through {head['sets']} buffer sets, "
+                             f"{head['sets'] * bytes_per_launch / 2**20:.0f} MiB total vs 126 MiB L2"},
+            "plain_order": dict(spread(plain["ms"]), unit="ms_per_step", value=world * N / (plain_ms * 1e-3), roofline_frac=frac(plain_ms),
+                                note="plain stream order (x may be produced by the kernel launched just before): what a solver loop sees"),
+            "e2e": {"value": world * N / e2e_p_s, "unit": "instances/s", "h2d_bytes_per_step": world * h2d_bytes,
+                    "d2h_bytes_per_step": world * d2h_packed, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_p_s,
+                    "regions_ms_per_step": [1e3 * t for t in e2e_p_all],
+                    "api": "cplb_eval_host_begin / cplb_eval_host_wait with CPLB_JAC_PACKED: a queue of batches on two sets of instance-major "
+                           "pinned host buffers (begin k+1, wait k); every step uploads its x and downloads its g and the x-dependent Jacobian "
+                           f"slots ({nv} of {nnz} per instance; the others are constants the consumer holds: cplb_get_jacobian_constants, "
+                           "cplb_unpack_jacobian; the IFOPT views read packed batches through the slot map); chunked H2D/kernel/D2H on 3 streams",
+                    "packed_equals_full_rows": True,
+                    "pcie_ceiling": {"ms_per_step": 1e3 * ceil_p_s, "value": world * N / ceil_p_s,
+                                     "d2h_GBps_per_gpu": d2h_packed / ceil_p_s / 1e9, "h2d_GBps_per_gpu": h2d_bytes / ceil_p_s / 1e9,
+                                     "aggregate_GBps": world * (d2h_packed + h2d_bytes) / ceil_p_s / 1e9,
+                                     "note": f"raw pinned copies of the same bytes per step (one D2H + one H2D on two streams), all {world} "
+                                             "rank(s) at once, max over ranks: the host-side ceiling of e2e on this box"},
+                    "frac_of_pcie_ceiling": ceil_p_s / e2e_p_s,
+                    "synchronous_call": {"value": world * N / e2e_ps_s, "ms_per_step": 1e3 * e2e_ps_s,
+                                         "api": "cplb_eval_host with CPLB_JAC_PACKED: one batch at a time, returns when its outputs have landed"},
+                    "full_rows": {"value": world * N / e2e_q_s, "ms_per_step": 1e3 * e2e_q_s, "d2h_bytes_per_step": world * d2h_bytes,
+                                  "regions_ms_per_step": [1e3 * t for t in e2e_q_all],
+                                  "api": "the same queue with full values[nnz] rows per instance (constants re-transferred every step)",
+                                  "synchronous_call": {"value": world * N / e2e_s, "ms_per_step": 1e3 * e2e_s},
+                                  "pcie_ceiling": {"ms_per_step": 1e3 * ceil_s, "value": world * N / ceil_s,
+                                                   "d2h_GBps_per_gpu": d2h_bytes / ceil_s / 1e9,
+                                                   "aggregate_GBps": world * (d2h_bytes + h2d_bytes) / ceil_s / 1e9},
+                                  "frac_of_pcie_ceiling": ceil_s / e2e_q_s},
                     "component_major_constants_skipped": {
-                        "value": N / e2e_cm_s, "ms_per_step": 1e3 * e2e_cm_s, "d2h_bytes_per_step": 8 * (m + n_var) * N,
-                        "note": f"rank 0 only; component-major host buffers, the {nnz - n_var} x-independent of {nnz} Jacobian slot rows pre-filled once"},
+                        "value": world * N / e2e_cm_s, "ms_per_step": 1e3 * e2e_cm_s, "d2h_bytes_per_step": world * 8 * (m + n_var) * N,
+                        "note": f"component-major host buffers, the {nnz - n_var} x-independent of {nnz} Jacobian slot rows pre-filled once"},
                     "checksum": e2e_check},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(head["launches"]),
+            "gpu_launches_whole_run": int(launches_total),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
                          "kernel": kname[layout],
-                         "avg_launch_ms": ms_per_step, "avg_launch_ms_event_pairs": ev_ms, "event_pair_launches": ev_k},
-            "other_layout": {"layout": lname[other], "kernel": kname[other], "ms_per_step": other_ms,
-                             "value": world * N / (other_ms * 1e-3), "roofline_frac": bytes_per_launch / (other_ms * 1e-3) / 1e9 / peak,
-                             "avg_launch_ms_event_pairs": other_ev_ms},
+                         "avg_launch_ms": ms_per_step, "avg_launch_ms_event_pairs": head["ev_ms"], "event_pair_launches": head["ev_k"]},
+            "other_layout": {"layout": lname[other], "kernel": kname[other], "ms_per_step": oth_ms,
+                             "value": world * N / (oth_ms * 1e-3), "roofline_frac": frac(oth_ms),
+                             "plain_order": {"ms_per_step": oth_plain_ms, "roofline_frac": frac(oth_plain_ms)}},
+            "configs": {
+                "config3": {"workload": "configs[2]: 65,536 4-contact instances per GPU with Superquadric environment contacts "
+                                        "(C=(0,0,1), R=(0.3,0.3,10), P=(10,10,10); TestBasic.cpp:150-157), fused g+Jacobian eval",
+                            "scaling": "weak", "ms_per_step": c3_ms[cpl.COMPONENT_MAJOR], "value": world * N / (c3_ms[cpl.COMPONENT_MAJOR] * 1e-3),
+                            "unit": "instances/s", "layout": "component-major", "timed_regions": spread(c3[cpl.COMPONENT_MAJOR]["ms"]),
+                            "roofline": {"bound": "hbm", "achieved": bytes_per_launch / (c3_ms[cpl.COMPONENT_MAJOR] * 1e-3) / 1e9, "peak": peak,
+                                         "unit": "GB/s", "frac": frac(c3_ms[cpl.COMPONENT_MAJOR]), "bytes_per_launch": bytes_per_launch,
+                                         "kernel": "eval_component_major_split<SUPERQUADRIC>"},
+                            "plain_order": {"ms_per_step": c3_plain_ms, "roofline_frac": frac(c3_plain_ms)},
+                            "instance_major": {"ms_per_step": c3_ms[cpl.INSTANCE_MAJOR], "roofline_frac": frac(c3_ms[cpl.INSTANCE_MAJOR])}},
+                "config4": {"workload": "configs[3]: 1,048,576 8-contact (hands+feet) flat-ground instances IN TOTAL, names given r_* first "
+                                        "(vector order != sorted order), sharded by index: contiguous N/G instances per GPU",
+                            "scaling": "strong", "instances_total": N_CONFIG4, "instances_per_gpu": hi - lo, "ms_per_step": c4_ms,
+                            "value": N_CONFIG4 / (c4_ms * 1e-3), "unit": "instances/s", "layout": "component-major",
+                            "timed_regions": spread(c4["ms"]), "launch": c4["launch"],
+                            "roofline": {"bound": "hbm", "achieved": bytes4_total / (c4_ms * 1e-3) / 1e9, "peak": world * peak, "unit": "GB/s",
+                                         "frac": frac(c4_ms, bytes4_total, world), "bytes_per_step_all_gpus": bytes4_total,
+                                         "note": "peak = n_gpus x the measured single-GPU copy bandwidth",
+                                         "kernel": "eval_component_major_whole<GROUND,8>"},
+                            "plain_order": {"ms_per_step": c4_plain_ms, "roofline_frac": frac(c4_plain_ms, bytes4_total, world)},
+                            "instance_major": {"ms_per_step": c4_im_ms, "roofline_frac": frac(c4_im_ms, bytes4_total, world)}},
+            },
             "clocks": clocks,
         }
+        if sharded is not None:
+            line["e2e"]["in_process_sharded"] = sharded
         if gather is not None:
             line["gather"] = gather
         traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(traffic_file):
             try:
                 line["roofline"]["traffic"] = json.load(open(traffic_file)).get(line["roofline"]["kernel"])
+                line["roofline"]["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE cold, serialised launch under ncu "
+                                                    "--set full (profiles/): below the algorithmic bytes because ~57 MB of the output is still "
+                                                    "dirty in the 126 MB L2 when that launch ends and drains during the next one; it is not a "
+                                                    "measurement of the timed region")
             except Exception:
                 pass
         if world == 1 and not args.no_cpu:
-            from oracle import cpl_oracle_py, cpl_ref_py  # noqa: F401  (cpu_baseline leg: the CPU path as the timed baseline)
+            from oracle import cpl_oracle_py  # noqa: F401  (cpu_baseline leg: the CPU path as the timed baseline)
 
             cores = host_cores()
             o = oracle_problem()
             o.set_call_all_pairs(0)
-            v_port, reps = time_cpu(o, x_host, cores, budget_s=args.cpu_seconds / 2)
-            port = {"value": v_port, "unit": "instances/s", "cores": cores, "kind": "port",
-                    "sample": f"{reps} passes over the same 65,536 instances, best pass; C oracle (-O2), {cores} threads, "
+            pout = {"g": np.empty((N, o.m)), "jac": np.empty((N, o.nnz))}
+            v_port, reps, v_port_best = time_cpu(lambda: o.eval_batch(x_host, want=("g", "jac"), nthreads=cores, out=pout), N, args.cpu_seconds / 2)
+            port = {"value": v_port, "best_pass": v_port_best, "unit": "instances/s", "cores": cores, "kind": "port",
+                    "sample": f"{reps} passes over the same 65,536 instances after a warm-up pass; C oracle (-O2), {cores} threads, "
                               "(set, variable-set) pairs that produce no Jacobian entry skipped -- a lean port, faster than "
-                              "the reference's own ifopt assembly"}
-            if cpl_ref_py.available():
-                from centroidalplanner_b200 import synthetic as syn
-
-                r = cpl_ref_py.RefProblem(syn.NAMES4, "ground", 100.0)
-                configure(r, r)
-                n_s = 16384
-                r.eval_batch(x_host[:2048], want=("g", "jac"), nthreads=cores)
-                best, t_spent, passes = 1e9, 0.0, 0
-                while t_spent < args.cpu_seconds / 2 and passes < 50:
-                    t0 = time.perf_counter()
-                    r.eval_batch(x_host[:n_s], want=("g", "jac"), nthreads=cores)
-                    dt = time.perf_counter() - t0
-                    best, t_spent, passes = min(best, dt), t_spent + dt, passes + 1
-                line["cpu_baseline"] = {
-                    "value": n_s / best, "unit": "instances/s", "cores": cores, "kind": "reference",
-                    "sample": f"{passes} passes over the first {n_s} of the 65,536 instances, best pass; the reference's own sources "
-                              "(CplProblem + its IFOPT components) compiled in place against stand-in Eigen/ifopt headers "
-                              f"(oracle/_ref; std::map-based sparse blocks, so indicative), one CplProblem per thread, {cores} threads",
-                    "lean_port": port}
+                              "the reference's own ifopt assembly",
+                    "lean_port_ratio": {"value": value / v_port, "e2e": line["e2e"]["value"] / v_port}}
+            fn, kind, sample = reference_callable(x_host, cores)
+            if kind == "reference":
+                v_ref, passes, v_ref_best = time_cpu(fn, N, args.cpu_seconds / 2)
+                line["cpu_baseline"] = {"value": v_ref, "best_pass": v_ref_best, "unit": "instances/s", "cores": cores, "kind": "reference",
+                                        "sample": f"{passes} passes after a warm-up pass; " + sample, "lean_port": port,
+                                        "lean_port_ratio": port["lean_port_ratio"]}
             else:
                 line["cpu_baseline"] = port
         print(json.dumps(line), flush=True)
 
-    for p in (px, pg, pj):
+    for p in pinned:
         lib.cplb_host_free(p)
     if world > 1:
         dist.destroy_process_group()
@@ -477,6 +687,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--regions", type=int, default=5, help="timed regions of --steps steps each (median reported, spread beside it)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default="component", choices=["instance", "component"],
                     help="buffer layout of the headline number (the other one is timed too and reported under other_layout)")
@@ -484,7 +695,7 @@ def main():
     ap.add_argument("--no-inputs-ready", action="store_true",
                     help="do not tell the evaluator that x is independent of the preceding kernel (CPLB_DEVICE_INPUTS_READY)")
     ap.add_argument("--no-graph", action="store_true", help="issue every timed step as a separate launch instead of CUDA-graph replays")
-    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -16,7 +16,9 @@ ENV_NONE, ENV_GROUND, ENV_SUPERQUADRIC = 0, 1, 2
 INSTANCE_MAJOR, COMPONENT_MAJOR = 0, 1
 HOST_JAC_CONSTANTS_PRESENT = 1
 DEVICE_INPUTS_READY = 2
+JAC_PACKED = 4
 KERNEL_AUTO, KERNEL_PER_CONTACT, KERNEL_PER_INSTANCE = 0, 1, 2
+KERNEL_WARP_TILE, KERNEL_CTA_TILE = 1, 2
 BLOCK_COM, BLOCK_FORCE, BLOCK_POSITION, BLOCK_NORMAL = 0, 1, 2, 3
 
 dp = C.POINTER(C.c_double)
@@ -50,6 +52,10 @@ class EvalArgs(C.Structure):
 # name -> (restype, argtypes); every symbol include/cpl_batched.h declares
 PROTOTYPES = {
     "cplb_create": (C.c_int, [C.c_int32, C.POINTER(C.c_char_p), C.c_int, C.c_double, C.c_int32, C.POINTER(C.c_void_p)]),
+    "cplb_create_sharded": (C.c_int, [C.c_int32, C.POINTER(C.c_char_p), C.c_int, C.c_double, C.c_int32, ip, C.POINTER(C.c_void_p)]),
+    "cplb_get_num_shards": (C.c_int, [C.c_void_p, ip]),
+    "cplb_get_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, ip, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "cplb_eval_device_shard": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(EvalArgs), C.c_void_p]),
     "cplb_destroy": (None, [C.c_void_p]),
     "cplb_last_error": (C.c_char_p, []),
     "cplb_abi_version": (C.c_int32, []),
@@ -60,6 +66,8 @@ PROTOTYPES = {
     "cplb_get_contact_row": (C.c_int, [C.c_void_p, C.c_char_p, ip]),
     "cplb_get_jacobian_constants": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8), dp]),
     "cplb_fill_jacobian_constants": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, dp]),
+    "cplb_get_packed_jacobian_map": (C.c_int, [C.c_void_p, ip, ip]),
+    "cplb_unpack_jacobian": (C.c_int, [C.c_void_p, C.c_int64, dp, dp]),
     "cplb_get_variable_bounds": (C.c_int, [C.c_void_p, dp, dp]),
     "cplb_get_constraint_bounds": (C.c_int, [C.c_void_p, dp, dp]),
     "cplb_set_mass": (C.c_int, [C.c_void_p, C.c_double]),
@@ -98,6 +106,7 @@ PROTOTYPES = {
     "cplb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cplb_host_free": (C.c_int, [C.c_void_p]),
     "cplb_set_component_major_kernel": (C.c_int, [C.c_void_p, C.c_int32]),
+    "cplb_set_instance_major_kernel": (C.c_int, [C.c_void_p, C.c_int32]),
     "cplb_get_device": (C.c_int, [C.c_void_p, ip]),
     "cplb_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "cplb_timing_begin": (C.c_int, [C.c_void_p]),

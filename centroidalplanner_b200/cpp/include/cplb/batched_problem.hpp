@@ -216,6 +216,21 @@ public:
         if (!_env) _ground_fake = std::make_shared<env::Ground>();  // CplProblem.cpp:14
         (_env ? _env : env::EnvironmentClass::Ptr(_ground_fake))->Attach(_p);
     }
+    // The same problem sharded over several GPUs of this box (cplb_create_sharded): EvaluateHost / EvaluateHostBegin then cut the
+    // batch into one contiguous range per device and drive all of them from the calling thread; device-resident buffers go through
+    // EvaluateDeviceShard.
+    BatchedProblem(std::vector<std::string> contact_names, double robot_mass, env::EnvironmentClass::Ptr env, const std::vector<int>& devices)
+        : _contact_names(std::move(contact_names)), _env(std::move(env))
+    {
+        std::vector<const char*> names;
+        for (auto& s : _contact_names) names.push_back(s.c_str());
+        std::vector<int32_t> devs(devices.begin(), devices.end());
+        check(cplb_create_sharded((int32_t)names.size(), names.data(), _env ? _env->Kind() : CPLB_ENV_NONE, robot_mass, (int32_t)devs.size(),
+                                  devs.data(), &_p));
+        check(cplb_get_dims(_p, &_n, &_m, &_nnz));
+        if (!_env) _ground_fake = std::make_shared<env::Ground>();  // CplProblem.cpp:14
+        (_env ? _env : env::EnvironmentClass::Ptr(_ground_fake))->Attach(_p);
+    }
     ~BatchedProblem()
     {
         (_env ? _env : env::EnvironmentClass::Ptr(_ground_fake))->Detach(_p);
@@ -229,6 +244,19 @@ public:
     int GetNumberOfOptimizationVariables() const { return _n; }
     int GetNumberOfConstraints() const { return _m; }
     int GetNumberOfJacobianNonzeros() const { return _nnz; }
+    int GetNumberOfShards() const
+    {
+        int32_t v = 1;
+        check(cplb_get_num_shards(_p, &v));
+        return v;
+    }
+    // device ordinal and instance range [begin, end) of one shard for a batch of N instances
+    void GetShard(int shard, int64_t N, int& device, int64_t& begin, int64_t& end) const
+    {
+        int32_t d = -1;
+        check(cplb_get_shard(_p, shard, N, &d, &begin, &end));
+        device = d;
+    }
     bool has_environment() const { return (bool)_env; }
 
     void GetJacobianStructure(std::vector<int32_t>& iRow, std::vector<int32_t>& jCol) const
@@ -236,6 +264,21 @@ public:
         iRow.resize(_nnz);
         jCol.resize(_nnz);
         check(cplb_get_jacobian_structure(_p, iRow.data(), jCol.data()));
+    }
+    // the x-dependent Jacobian slots in slot order (element q of a CPLB_JAC_PACKED slice is slot map[q]) and the values of the others
+    std::vector<int32_t> GetPackedJacobianMap() const
+    {
+        int32_t nv = 0;
+        check(cplb_get_packed_jacobian_map(_p, &nv, nullptr));
+        std::vector<int32_t> map((size_t)nv);
+        check(cplb_get_packed_jacobian_map(_p, &nv, map.data()));
+        return map;
+    }
+    void GetJacobianConstants(std::vector<uint8_t>& is_constant, std::vector<double>& value) const
+    {
+        is_constant.resize(_nnz);
+        value.resize(_nnz);
+        check(cplb_get_jacobian_constants(_p, is_constant.data(), value.data()));
     }
     std::vector<int32_t> GetSortedOrder() const
     {
@@ -316,11 +359,13 @@ public:
 
     // ---- evaluation (host buffers, instance-major: instance i owns x[i*n..], g[i*m..], jac[i*nnz..]) ----
     // per_instance: optional per-instance parameter arrays (host pointers, instance-major), nullptr = shared parameters
+    // host_flags: 0 or CPLB_JAC_PACKED (jac then holds GetPackedJacobianMap().size() doubles per instance: the x-dependent slots only)
     void EvaluateHost(int64_t N, const double* x, double* g, double* jac, double* cost, double* grad,
-                      const cplb_instance_params* per_instance = nullptr)
+                      const cplb_instance_params* per_instance = nullptr, int32_t host_flags = 0)
     {
         cplb_eval_args a{};
         a.num_instances = N;
+        a.host_flags = host_flags;
         a.layout = CPLB_INSTANCE_MAJOR;
         a.x = x;
         a.g = g;
@@ -333,10 +378,11 @@ public:
     // the same for a queue of batches: Begin enqueues and returns a ticket, Wait returns when that batch's outputs have landed
     // (pinned host buffers, untouched in between; cplb_eval_host_begin / cplb_eval_host_wait)
     int32_t EvaluateHostBegin(int64_t N, const double* x, double* g, double* jac, double* cost, double* grad,
-                              const cplb_instance_params* per_instance = nullptr)
+                              const cplb_instance_params* per_instance = nullptr, int32_t host_flags = 0)
     {
         cplb_eval_args a{};
         a.num_instances = N;
+        a.host_flags = host_flags;
         a.layout = CPLB_INSTANCE_MAJOR;
         a.x = x;
         a.g = g;
@@ -364,6 +410,23 @@ public:
         a.grad = grad;
         a.per_instance = per_instance;
         check(cplb_eval_device(_p, &a, stream));
+    }
+
+    // one shard's device-resident buffers (its instances only) on that shard's device and stream
+    void EvaluateDeviceShard(int shard, int64_t N, cplb_layout layout, int64_t ld, const double* x, double* g, double* jac, double* cost,
+                             double* grad, void* stream, const cplb_instance_params* per_instance = nullptr)
+    {
+        cplb_eval_args a{};
+        a.num_instances = N;
+        a.layout = layout;
+        a.ld = ld;
+        a.x = x;
+        a.g = g;
+        a.jac = jac;
+        a.cost = cost;
+        a.grad = grad;
+        a.per_instance = per_instance;
+        check(cplb_eval_device_shard(_p, shard, &a, stream));
     }
 
 private:

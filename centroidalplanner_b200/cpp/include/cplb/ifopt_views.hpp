@@ -22,6 +22,7 @@
 
 #include <condition_variable>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -33,21 +34,33 @@
 namespace cplb {
 namespace solver {
 
-// Host buffers of N instances (instance-major) plus the lazily refreshed outputs.
+// Host buffers of N instances (instance-major) plus the lazily refreshed outputs.  The Jacobian buffer is PACKED
+// (CPLB_JAC_PACKED): only the x-dependent slots travel device -> host; a view's FillJacobianBlock reads a slot through the
+// slot map and takes the x-independent ones (the 1.0 identities, a Ground's zeros: CentroidalStatics.cpp:93-95,
+// EnvironmentNormal.cpp:66-68, Ground.cpp:33-34,49) from cplb_get_jacobian_constants.  The problem may be sharded over
+// several GPUs (BatchedProblem's device-list constructor): the batch is then evaluated by all of them at once.
 class InstanceBatch {
 public:
     typedef std::shared_ptr<InstanceBatch> Ptr;
     struct Entry {
         int r, c, slot;
+        int packed;     // index into the instance's packed Jacobian slice, or -1: x-independent
+        double constant;  // its value then
     };
 
     InstanceBatch(BatchedProblem::Ptr problem, int64_t num_instances)
         : _prob(std::move(problem)), _N(num_instances), _n(_prob->GetNumberOfOptimizationVariables()),
           _m(_prob->GetNumberOfConstraints()), _nnz(_prob->GetNumberOfJacobianNonzeros())
     {
+        const std::vector<int32_t> map = _prob->GetPackedJacobianMap();
+        _nv = (int)map.size();
+        _slot_to_packed.assign((size_t)_nnz, -1);
+        for (int q = 0; q < _nv; q++) _slot_to_packed[(size_t)map[(size_t)q]] = q;
+        std::vector<uint8_t> is_const;
+        _prob->GetJacobianConstants(is_const, _const_value);
         _x = pinned((size_t)_N * _n);
         _g = pinned((size_t)_N * _m);
-        _jac = pinned((size_t)_N * _nnz);
+        _jac = pinned((size_t)_N * _nv);
         _grad = pinned((size_t)_N * _n);
         _cost = pinned((size_t)_N);
         std::memset(_x, 0, sizeof(double) * _N * _n);  // Variable3D starts at 0 (src/Variable3D.cpp:8-10)
@@ -100,10 +113,18 @@ public:
         Refresh(i);
         return _g + i * _m;
     }
+    // instance i's PACKED Jacobian slice (jac_packed_size() doubles); Entry::packed indexes it
     const double* jac(int64_t i)
     {
         Refresh(i);
-        return _jac + i * _nnz;
+        return _jac + i * _nv;
+    }
+    int jac_packed_size() const { return _nv; }
+    // one structural slot of instance i's Jacobian, constants included (what IpoptAdapter::eval_jac_g's values[slot] holds)
+    double jac_value(int64_t i, int slot)
+    {
+        const int q = _slot_to_packed[(size_t)slot];
+        return q < 0 ? _const_value[(size_t)slot] : jac(i)[q];
     }
     const double* grad(int64_t i)
     {
@@ -145,7 +166,7 @@ public:
         std::vector<Entry> e;
         for (int s = 0; s < _nnz; s++)
             if (_iRow[s] >= row0 && _iRow[s] < row0 + rows && _jCol[s] >= 3 * v && _jCol[s] < 3 * v + 3)
-                e.push_back(Entry{_iRow[s] - row0, _jCol[s] - 3 * v, s});
+                e.push_back(Entry{_iRow[s] - row0, _jCol[s] - 3 * v, s, _slot_to_packed[(size_t)s], _const_value[(size_t)s]});
         return _blocks.emplace(key, std::move(e)).first->second;
     }
 
@@ -160,17 +181,28 @@ private:
     {
         if (_dirty_lo >= _dirty_hi) return;
         const int64_t lo = _dirty_lo, cnt = _dirty_hi - _dirty_lo;
-        _prob->EvaluateHost(cnt, _x + lo * _n, _g + lo * _m, _jac + lo * _nnz, _cost + lo, _grad + lo * _n);
+        _prob->EvaluateHost(cnt, _x + lo * _n, _g + lo * _m, _jac + lo * _nv, _cost + lo, _grad + lo * _n, nullptr, CPLB_JAC_PACKED);
         std::fill(_dirty.begin() + lo, _dirty.begin() + lo + cnt, 0);
         _dirty_lo = _dirty_hi = 0;
         _evaluations++;
     }
-    void Release()  // _mu held: the round is complete
+    // _mu held: the round is complete.  A failing evaluation (CUDA error, out of memory) must not strand the other solver
+    // threads in their wait: the round is released whatever happens, the exception is kept with the round's generation and
+    // rethrown in EVERY participant (the evaluating thread included).
+    void Release()
     {
-        EvaluateDirtyRange();
+        std::exception_ptr failure;
+        try {
+            EvaluateDirtyRange();
+        } catch (...) {
+            failure = std::current_exception();
+        }
         _arrived = 0;
         _generation++;
+        _failure = failure;
+        _failure_generation = _generation;
         _cv.notify_all();
+        if (failure) std::rethrow_exception(failure);
     }
     void Refresh(int64_t i)
     {
@@ -186,12 +218,17 @@ private:
         } else {
             const int64_t gen = _generation;
             _cv.wait(lk, [&] { return _generation != gen; });
+            if (_failure && _failure_generation == gen + 1) std::rethrow_exception(_failure);
         }
     }
 
     BatchedProblem::Ptr _prob;
     int64_t _N;
-    int _n, _m, _nnz;
+    int _n, _m, _nnz, _nv = 0;
+    std::vector<int> _slot_to_packed;
+    std::vector<double> _const_value;
+    std::exception_ptr _failure;
+    int64_t _failure_generation = -1;
     double *_x = nullptr, *_g = nullptr, *_jac = nullptr, *_grad = nullptr, *_cost = nullptr;
     std::vector<int32_t> _iRow, _jCol;
     std::map<std::string, int> _var_index;
@@ -279,8 +316,8 @@ private:
         jac_block.setZero();
         const int v = _batch->var_index(var_set);
         if (v < 0) return;
-        const double* vals = _batch->jac(_i);
-        for (const auto& e : _batch->Block(_row0, GetRows(), v)) jac_block.coeffRef(e.r, e.c) = vals[e.slot];
+        const double* vals = _batch->jac(_i);  // the packed slice
+        for (const auto& e : _batch->Block(_row0, GetRows(), v)) jac_block.coeffRef(e.r, e.c) = e.packed >= 0 ? vals[e.packed] : e.constant;
     }
     InstanceBatch::Ptr _batch;
     int64_t _i;

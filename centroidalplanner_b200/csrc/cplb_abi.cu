@@ -12,6 +12,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cpl_batched.h"
@@ -78,25 +79,31 @@ struct cplb_problem {
     std::vector<double> x_lb, x_ub;
     std::atomic<long long> launches{0};
     int cm_kernel = CPLB_CM_AUTO;  // cplb_set_component_major_kernel
+    int im_kernel = CPLB_IM_AUTO;  // cplb_set_instance_major_kernel
 
     // kernel timing (cplb_timing_begin/end)
     std::mutex timing_mu;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
 
-    // cplb_eval_host pipeline
+    // cplb_eval_host pipeline, one per device of the problem (cplb_create: one; cplb_create_sharded: one per shard)
+    struct HostPipe {
+        int device = -1;
+        cudaStream_t streams[kHostStreams] = {};
+        double* stage[kHostStreams] = {};
+        double* bounce[kHostStreams] = {};  // pinned mirrors of stage[], used when the caller's buffers are pageable
+        size_t bounce_bytes = 0;
+        size_t stage_bytes = 0;
+        bool streams_ready = false;
+        // cplb_eval_host_begin / _wait: completion events of the outstanding asynchronous calls (ring of tickets)
+        cudaEvent_t host_done[kHostTickets][kHostStreams] = {};
+        bool host_done_ready = false;
+        int next_stream = 0;
+    };
     std::mutex host_mu;
-    cudaStream_t streams[kHostStreams] = {};
-    double* stage[kHostStreams] = {};
-    double* bounce[kHostStreams] = {};  // pinned mirrors of stage[], used when the caller's buffers are pageable
-    size_t bounce_bytes = 0;
-    size_t stage_bytes = 0;
-    bool streams_ready = false;
-    // cplb_eval_host_begin / _wait: completion events of the outstanding asynchronous calls (ring of tickets)
-    cudaEvent_t host_done[kHostTickets][kHostStreams] = {};
-    bool host_done_ready = false;
+    std::vector<HostPipe> pipes;  // pipes[0].device mirrors `device` for a single-device problem
+    bool sharded = false;
     int next_ticket = 0;
-    int next_stream = 0;
 
     int find(const char* name) const
     {
@@ -142,8 +149,8 @@ extern "C" {
 const char* cplb_last_error(void) { return g_last_error; }
 int32_t cplb_abi_version(void) { return CPLB_ABI_VERSION; }
 
-cplb_status cplb_create(int32_t num_contacts, const char* const* contact_names, cplb_env_kind env, double robot_mass,
-                        int32_t device, cplb_problem** out)
+static cplb_status create_impl(int32_t num_contacts, const char* const* contact_names, cplb_env_kind env, double robot_mass,
+                               int32_t num_devices, const int32_t* devices, bool sharded, cplb_problem** out)
 {
     CPLB_REQUIRE(out);
     *out = nullptr;
@@ -155,13 +162,20 @@ cplb_status cplb_create(int32_t num_contacts, const char* const* contact_names, 
         return fail(CPLB_INVALID_ARGUMENT, "unknown environment kind %d", (int)env);
     if (!(robot_mass > 0.0)) return fail(CPLB_INVALID_ARGUMENT, "Invalid robot mass");  // CentroidalPlanner.cpp:12-15
 
-    if (device >= 0) {  // an explicit ordinal is validated now; -1 binds to the caller's current device at first evaluation
+    bool any_explicit = false;
+    for (int d = 0; d < num_devices; d++) any_explicit = any_explicit || devices[d] >= 0;
+    if (any_explicit) {  // explicit ordinals are validated now; -1 binds to the caller's current device at first evaluation
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
         if (e != cudaSuccess || ndev == 0)
             return fail(CPLB_CUDA_ERROR, "no usable CUDA device (%s); this library has no CPU fallback",
                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-        if (device >= ndev) return fail(CPLB_INVALID_ARGUMENT, "device %d out of range (%d devices)", device, ndev);
+        for (int d = 0; d < num_devices; d++) {
+            if (devices[d] >= ndev) return fail(CPLB_INVALID_ARGUMENT, "device %d out of range (%d devices)", devices[d], ndev);
+            if (sharded && devices[d] < 0) return fail(CPLB_INVALID_ARGUMENT, "a sharded problem needs explicit device ordinals (devices[%d] = %d)", d, devices[d]);
+        }
+    } else if (sharded) {
+        return fail(CPLB_INVALID_ARGUMENT, "a sharded problem needs explicit device ordinals");
     }
 
     cplb_problem* p = new (std::nothrow) cplb_problem();
@@ -178,7 +192,10 @@ cplb_status cplb_create(int32_t num_contacts, const char* const* contact_names, 
         p->names.emplace_back(contact_names[k]);
     }
     p->env = env;
-    p->device = device;
+    p->device = devices[0];
+    p->sharded = sharded;
+    p->pipes.resize((size_t)num_devices);
+    for (int d = 0; d < num_devices; d++) p->pipes[(size_t)d].device = devices[d];
     p->mass = robot_mass;
     p->layout.build(p->names, env != CPLB_ENV_NONE, env == CPLB_ENV_GROUND);
 
@@ -205,6 +222,23 @@ cplb_status cplb_create(int32_t num_contacts, const char* const* contact_names, 
     return CPLB_OK;
 }
 
+cplb_status cplb_create(int32_t num_contacts, const char* const* contact_names, cplb_env_kind env, double robot_mass,
+                        int32_t device, cplb_problem** out)
+{
+    return create_impl(num_contacts, contact_names, env, robot_mass, 1, &device, false, out);
+}
+
+cplb_status cplb_create_sharded(int32_t num_contacts, const char* const* contact_names, cplb_env_kind env, double robot_mass,
+                                int32_t num_devices, const int32_t* devices, cplb_problem** out)
+{
+    CPLB_REQUIRE(out);
+    *out = nullptr;
+    CPLB_REQUIRE(devices);
+    if (num_devices < 1 || num_devices > CPLB_MAX_SHARDS)
+        return fail(CPLB_INVALID_ARGUMENT, "num_devices must be in 1..%d (got %d)", CPLB_MAX_SHARDS, (int)num_devices);
+    return create_impl(num_contacts, contact_names, env, robot_mass, num_devices, devices, true, out);
+}
+
 void cplb_destroy(cplb_problem* p)
 {
     if (!p) return;
@@ -214,16 +248,18 @@ void cplb_destroy(cplb_problem* p)
             cudaEventDestroy(ev.first);
             cudaEventDestroy(ev.second);
         }
-        if (p->host_done_ready)
+    }
+    for (auto& pipe : p->pipes) {
+        if (pipe.device < 0 || !pipe.streams_ready) continue;
+        DeviceGuard dg(pipe.device);
+        if (pipe.host_done_ready)
             for (int t = 0; t < kHostTickets; t++)
-                for (int s = 0; s < kHostStreams; s++) cudaEventDestroy(p->host_done[t][s]);
-        if (p->streams_ready) {
-            for (int s = 0; s < kHostStreams; s++) {
-                cudaStreamSynchronize(p->streams[s]);
-                cudaStreamDestroy(p->streams[s]);
-                if (p->stage[s]) cudaFree(p->stage[s]);
-                if (p->bounce[s]) cudaFreeHost(p->bounce[s]);
-            }
+                for (int s = 0; s < kHostStreams; s++) cudaEventDestroy(pipe.host_done[t][s]);
+        for (int s = 0; s < kHostStreams; s++) {
+            cudaStreamSynchronize(pipe.streams[s]);
+            cudaStreamDestroy(pipe.streams[s]);
+            if (pipe.stage[s]) cudaFree(pipe.stage[s]);
+            if (pipe.bounce[s]) cudaFreeHost(pipe.bounce[s]);
         }
     }
     delete p;
@@ -322,6 +358,34 @@ cplb_status cplb_fill_jacobian_constants(const cplb_problem* p, int64_t num_inst
     return CPLB_OK;
 }
 
+cplb_status cplb_get_packed_jacobian_map(const cplb_problem* p, int32_t* num_packed, int32_t* packed_to_slot)
+{
+    CPLB_REQUIRE(p);
+    const auto& map = p->layout.packed_to_slot;
+    if (num_packed) *num_packed = (int32_t)map.size();
+    if (packed_to_slot) std::memcpy(packed_to_slot, map.data(), sizeof(int32_t) * map.size());
+    return CPLB_OK;
+}
+
+cplb_status cplb_unpack_jacobian(const cplb_problem* p, int64_t num_instances, const double* packed, double* full)
+{
+    CPLB_REQUIRE(p);
+    if (num_instances < 0) return fail(CPLB_INVALID_ARGUMENT, "num_instances is negative");
+    if (num_instances == 0) return CPLB_OK;
+    CPLB_REQUIRE(packed);
+    CPLB_REQUIRE(full);
+    const cplb::Layout& L = p->layout;
+    const int nv = (int)L.packed_to_slot.size();
+    for (long long i = 0; i < num_instances; i++) {
+        double* row = full + i * L.nnz;
+        const double* src = packed + i * nv;
+        for (int s = 0; s < L.nnz; s++)
+            if (L.is_const[s]) row[s] = L.const_value[s];
+        for (int q = 0; q < nv; q++) row[L.packed_to_slot[q]] = src[q];
+    }
+    return CPLB_OK;
+}
+
 cplb_status cplb_get_variable_bounds(const cplb_problem* p, double* lower, double* upper)
 {
     CPLB_REQUIRE(p);
@@ -383,6 +447,15 @@ cplb_status cplb_set_component_major_kernel(cplb_problem* p, int32_t kernel)
     if (kernel == CPLB_KERNEL_PER_INSTANCE && p->layout.nc != 4 && p->layout.nc != 8)
         return fail(CPLB_INVALID_ARGUMENT, "the thread-per-instance kernel exists for 4 and 8 contacts only (this problem has %d)", p->layout.nc);
     p->cm_kernel = kernel == CPLB_KERNEL_AUTO ? CPLB_CM_AUTO : (kernel == CPLB_KERNEL_PER_CONTACT ? CPLB_CM_SPLIT : CPLB_CM_WHOLE);
+    return CPLB_OK;
+}
+
+cplb_status cplb_set_instance_major_kernel(cplb_problem* p, int32_t kernel)
+{
+    CPLB_REQUIRE(p);
+    if (kernel != CPLB_KERNEL_AUTO && kernel != CPLB_KERNEL_WARP_TILE && kernel != CPLB_KERNEL_CTA_TILE)
+        return fail(CPLB_INVALID_ARGUMENT, "unknown instance-major kernel choice %d", (int)kernel);
+    p->im_kernel = kernel == CPLB_KERNEL_AUTO ? CPLB_IM_AUTO : (kernel == CPLB_KERNEL_WARP_TILE ? CPLB_IM_WARP_TILE : CPLB_IM_CTA_TILE);
     return CPLB_OK;
 }
 
@@ -651,6 +724,7 @@ static cplb_status bind_device(cplb_problem* p)
     int dev = 0;
     CPLB_CUDA(cudaGetDevice(&dev));
     p->device = dev;
+    p->pipes[0].device = dev;
     return CPLB_OK;
 }
 
@@ -672,6 +746,10 @@ static cplb_status check_args(const cplb_problem* p, const cplb_eval_args* a, un
     if (a->layout == CPLB_COMPONENT_MAJOR && pitch >= (1LL << 29))
         return fail(CPLB_INVALID_ARGUMENT, "ld (%lld) must be below 2^29: the kernels hold the row pitch in bytes in 32 bits", pitch);
     *ld = pitch;
+    if (a->host_flags & CPLB_JAC_PACKED) {
+        if (a->layout != CPLB_INSTANCE_MAJOR) return fail(CPLB_INVALID_ARGUMENT, "CPLB_JAC_PACKED needs INSTANCE_MAJOR buffers (COMPONENT_MAJOR host calls skip whole rows with CPLB_HOST_JAC_CONSTANTS_PRESENT instead)");
+        *flags |= CPLB_JAC_PACKED_K;
+    }
     (void)p;
     return CPLB_OK;
 }
@@ -711,25 +789,16 @@ static cplb_status launch(cplb_problem* p, const CplbIo& io, int layout, unsigne
                           const CplbInstParams* q = nullptr)
 {
     cudaError_t e = layout == CPLB_COMPONENT_MAJOR ? cplb::launch_component_major(p->P, io, flags, q, p->cm_kernel, st)
-                                                   : cplb::launch_instance_major(p->P, io, flags, q, st);
+                                                   : cplb::launch_instance_major(p->P, io, flags, q, p->im_kernel, st);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     p->launches.fetch_add(1, std::memory_order_relaxed);
     return CPLB_OK;
 }
 
-cplb_status cplb_eval_device(cplb_problem* p, const cplb_eval_args* args, void* cuda_stream)
+static cplb_status eval_device_on(cplb_problem* p, int device, const cplb_eval_args* args, unsigned flags, long long ld, void* cuda_stream)
 {
-    CPLB_REQUIRE(p);
-    CPLB_REQUIRE(args);
-    unsigned flags = 0;
-    long long ld = 0;
-    cplb_status st = check_args(p, args, &flags, &ld);
-    if (st != CPLB_OK) return st;
-    if (args->num_instances == 0 || flags == 0) return CPLB_OK;
-    st = bind_device(p);
-    if (st != CPLB_OK) return st;
-    DeviceGuard dg(p->device);
-    if (!dg.ok) return fail(CPLB_CUDA_ERROR, "cudaSetDevice(%d) failed", p->device);
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(CPLB_CUDA_ERROR, "cudaSetDevice(%d) failed", device);
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     CplbIo io{args->x, args->g, args->jac, args->cost, args->grad, ld, args->num_instances};
 
@@ -749,7 +818,7 @@ cplb_status cplb_eval_device(cplb_problem* p, const cplb_eval_args* args, void* 
     if (per_inst)
         for (const auto& f : kInstFields) q.*(f.dst) = args->per_instance->*(f.src);
     if (args->host_flags & CPLB_DEVICE_INPUTS_READY) flags |= CPLB_INPUTS_READY;
-    st = launch(p, io, args->layout, flags, stream, per_inst ? &q : nullptr);
+    cplb_status st = launch(p, io, args->layout, flags, stream, per_inst ? &q : nullptr);
     if (timed) {
         cudaEventRecord(e1, stream);
         std::lock_guard<std::mutex> lk(p->timing_mu);
@@ -758,23 +827,95 @@ cplb_status cplb_eval_device(cplb_problem* p, const cplb_eval_args* args, void* 
     return st;
 }
 
-static cplb_status ensure_host_pipeline(cplb_problem* p, size_t bytes_per_stream)
+cplb_status cplb_eval_device(cplb_problem* p, const cplb_eval_args* args, void* cuda_stream)
 {
-    if (!p->streams_ready) {
-        for (int s = 0; s < kHostStreams; s++) CPLB_CUDA(cudaStreamCreateWithFlags(&p->streams[s], cudaStreamNonBlocking));
-        p->streams_ready = true;
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(args);
+    unsigned flags = 0;
+    long long ld = 0;
+    cplb_status st = check_args(p, args, &flags, &ld);
+    if (st != CPLB_OK) return st;
+    if (p->pipes.size() > 1)
+        return fail(CPLB_INVALID_ARGUMENT, "this problem is sharded over %d devices: device buffers belong to one of them, use cplb_eval_device_shard",
+                    (int)p->pipes.size());
+    if (args->num_instances == 0 || (flags & 15u) == 0) return CPLB_OK;
+    st = bind_device(p);
+    if (st != CPLB_OK) return st;
+    return eval_device_on(p, p->device, args, flags, ld, cuda_stream);
+}
+
+cplb_status cplb_eval_device_shard(cplb_problem* p, int32_t shard, const cplb_eval_args* args, void* cuda_stream)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(args);
+    if (shard < 0 || shard >= (int32_t)p->pipes.size()) return fail(CPLB_INVALID_ARGUMENT, "shard %d out of range (%d shards)", (int)shard, (int)p->pipes.size());
+    unsigned flags = 0;
+    long long ld = 0;
+    cplb_status st = check_args(p, args, &flags, &ld);
+    if (st != CPLB_OK) return st;
+    if (args->num_instances == 0 || (flags & 15u) == 0) return CPLB_OK;
+    st = bind_device(p);
+    if (st != CPLB_OK) return st;
+    return eval_device_on(p, p->pipes[(size_t)shard].device, args, flags, ld, cuda_stream);
+}
+
+// Contiguous index ranges of a batch of N instances over the problem's devices (GPU r of G evaluates
+// [r*N/G, (r+1)*N/G)); boundaries are rounded to multiples of 32 instances so that every shard's slices keep the 16-byte
+// alignment and tile alignment of the whole buffer.
+static void shard_range(long long N, int shard, int shards, long long* begin, long long* end)
+{
+    long long per = (N + shards - 1) / shards;
+    per = (per + 31) & ~31LL;
+    long long b = per * shard, e = b + per;
+    if (b > N) b = N;
+    if (e > N) e = N;
+    *begin = b;
+    *end = e;
+}
+
+cplb_status cplb_get_num_shards(const cplb_problem* p, int32_t* num_shards)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(num_shards);
+    *num_shards = (int32_t)p->pipes.size();
+    return CPLB_OK;
+}
+
+cplb_status cplb_get_shard(const cplb_problem* p, int32_t shard, int64_t num_instances, int32_t* device, int64_t* begin, int64_t* end)
+{
+    CPLB_REQUIRE(p);
+    if (shard < 0 || shard >= (int32_t)p->pipes.size()) return fail(CPLB_INVALID_ARGUMENT, "shard %d out of range (%d shards)", (int)shard, (int)p->pipes.size());
+    if (num_instances < 0) return fail(CPLB_INVALID_ARGUMENT, "num_instances is negative");
+    long long b = 0, e = 0;
+    shard_range(num_instances, shard, (int)p->pipes.size(), &b, &e);
+    if (device) *device = p->pipes[(size_t)shard].device;
+    if (begin) *begin = b;
+    if (end) *end = e;
+    return CPLB_OK;
+}
+
+using HostPipe = cplb_problem::HostPipe;
+
+// doubles per instance of the Jacobian slice of this evaluation: every structural slot, or only the x-dependent ones
+static int jac_len(const cplb_problem* p, unsigned flags) { return (flags & CPLB_JAC_PACKED_K) ? (int)p->layout.packed_to_slot.size() : p->layout.nnz; }
+
+static cplb_status ensure_host_pipeline(HostPipe& pipe, size_t bytes_per_stream)
+{
+    if (!pipe.streams_ready) {
+        for (int s = 0; s < kHostStreams; s++) CPLB_CUDA(cudaStreamCreateWithFlags(&pipe.streams[s], cudaStreamNonBlocking));
+        pipe.streams_ready = true;
     }
-    if (bytes_per_stream > p->stage_bytes) {
+    if (bytes_per_stream > pipe.stage_bytes) {
         for (int s = 0; s < kHostStreams; s++) {
-            if (p->stage[s]) {
-                CPLB_CUDA(cudaStreamSynchronize(p->streams[s]));
-                CPLB_CUDA(cudaFree(p->stage[s]));
-                p->stage[s] = nullptr;
+            if (pipe.stage[s]) {
+                CPLB_CUDA(cudaStreamSynchronize(pipe.streams[s]));
+                CPLB_CUDA(cudaFree(pipe.stage[s]));
+                pipe.stage[s] = nullptr;
             }
         }
-        p->stage_bytes = 0;
-        for (int s = 0; s < kHostStreams; s++) CPLB_CUDA(cudaMalloc(&p->stage[s], bytes_per_stream));
-        p->stage_bytes = bytes_per_stream;
+        pipe.stage_bytes = 0;
+        for (int s = 0; s < kHostStreams; s++) CPLB_CUDA(cudaMalloc(&pipe.stage[s], bytes_per_stream));
+        pipe.stage_bytes = bytes_per_stream;
     }
     return CPLB_OK;
 }
@@ -816,24 +957,24 @@ static std::vector<HostInput> host_inputs(const cplb_problem* p, const cplb_eval
     return in;
 }
 
-static cplb_status eval_host_bounced(cplb_problem* p, const cplb_eval_args* args, unsigned flags, long long ld, long long chunk,
-                                     size_t stage_bytes)
+// instances [begin, end) of the caller's buffers through one device's pipeline; the calling thread's current device is pipe.device
+static cplb_status eval_host_bounced(cplb_problem* p, HostPipe& pipe, const cplb_eval_args* args, unsigned flags, long long ld, long long chunk,
+                                     size_t stage_bytes, long long begin, long long end)
 {
-    const long long N = args->num_instances;
-    const int n = p->layout.n, m = p->layout.m, nnz = p->layout.nnz;
+    const int n = p->layout.n, m = p->layout.m, nnz = jac_len(p, flags);
     const bool cm = args->layout == CPLB_COMPONENT_MAJOR;
     const bool skip_const = (args->host_flags & CPLB_HOST_JAC_CONSTANTS_PRESENT) != 0;
-    if (stage_bytes > p->bounce_bytes) {
+    if (stage_bytes > pipe.bounce_bytes) {
         for (int s = 0; s < kHostStreams; s++) {
-            if (p->bounce[s]) {
-                CPLB_CUDA(cudaStreamSynchronize(p->streams[s]));
-                CPLB_CUDA(cudaFreeHost(p->bounce[s]));
-                p->bounce[s] = nullptr;
+            if (pipe.bounce[s]) {
+                CPLB_CUDA(cudaStreamSynchronize(pipe.streams[s]));
+                CPLB_CUDA(cudaFreeHost(pipe.bounce[s]));
+                pipe.bounce[s] = nullptr;
             }
         }
-        p->bounce_bytes = 0;
-        for (int s = 0; s < kHostStreams; s++) CPLB_CUDA(cudaHostAlloc((void**)&p->bounce[s], stage_bytes, cudaHostAllocDefault));
-        p->bounce_bytes = stage_bytes;
+        pipe.bounce_bytes = 0;
+        for (int s = 0; s < kHostStreams; s++) CPLB_CUDA(cudaHostAlloc((void**)&pipe.bounce[s], stage_bytes, cudaHostAllocDefault));
+        pipe.bounce_bytes = stage_bytes;
     }
     struct Pending { long long i0 = 0, cnt = 0; };
     Pending pend[kHostStreams];
@@ -849,8 +990,8 @@ static cplb_status eval_host_bounced(cplb_problem* p, const cplb_eval_args* args
     };
     auto drain = [&](int s) -> cplb_status {
         if (pend[s].cnt == 0) return CPLB_OK;
-        CPLB_CUDA(cudaStreamSynchronize(p->streams[s]));
-        const double* h = p->bounce[s];
+        CPLB_CUDA(cudaStreamSynchronize(pipe.streams[s]));
+        const double* h = pipe.bounce[s];
         unpack_one(args->g, h + og, m, pend[s].i0, pend[s].cnt);
         if (cm && skip_const && args->jac) {  // rows of x-independent slots stay as the caller pre-filled them
             for (const auto& r : p->layout.var_runs)
@@ -864,40 +1005,114 @@ static cplb_status eval_host_bounced(cplb_problem* p, const cplb_eval_args* args
         pend[s].cnt = 0;
         return CPLB_OK;
     };
+    // a failure leaves nothing in flight: the caller may free or reuse its buffers as soon as the call has returned
+    auto bail = [&](cplb_status st) {
+        for (int t = 0; t < kHostStreams; t++) cudaStreamSynchronize(pipe.streams[t]);
+        return st;
+    };
     int s = 0;
-    for (long long i0 = 0; i0 < N; i0 += chunk, s = (s + 1) % kHostStreams) {
-        const long long cnt = (N - i0) < chunk ? (N - i0) : chunk;
+    for (long long i0 = begin; i0 < end; i0 += chunk, s = (s + 1) % kHostStreams) {
+        const long long cnt = (end - i0) < chunk ? (end - i0) : chunk;
         cplb_status st = drain(s);
-        if (st != CPLB_OK) return st;
-        cudaStream_t stream = p->streams[s];
-        double* h = p->bounce[s];
-        double* d = p->stage[s];
+        if (st != CPLB_OK) return bail(st);
+        cudaStream_t stream = pipe.streams[s];
+        double* h = pipe.bounce[s];
+        double* d = pipe.stage[s];
         CplbInstParams q{};
         for (const auto& in : inputs) {
             double* hb = h + in.off;
             if (cm) for (int e = 0; e < in.len; e++) std::memcpy(hb + (size_t)e * chunk, in.user + (long long)e * ld + i0, (size_t)cnt * sizeof(double));
             else std::memcpy(hb, in.user + i0 * in.len, (size_t)cnt * in.len * sizeof(double));
-            CPLB_CUDA(cudaMemcpyAsync(d + in.off, hb, (size_t)in.len * chunk * sizeof(double), cudaMemcpyHostToDevice, stream));
+            cudaError_t e = cudaMemcpyAsync(d + in.off, hb, (size_t)in.len * chunk * sizeof(double), cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpyAsync (host to device)"));
             if (in.dst) q.*(in.dst) = d + in.off;
         }
         CplbIo io{d + ox, (flags & CPLB_WANT_G) ? d + og : nullptr, (flags & CPLB_WANT_J) ? d + oj : nullptr,
                   (flags & CPLB_WANT_COST) ? d + oc : nullptr, (flags & CPLB_WANT_GRAD) ? d + ogr : nullptr, chunk, cnt};
         st = launch(p, io, args->layout, flags, stream, inputs.size() > 1 ? &q : nullptr);
-        if (st != CPLB_OK) return st;
+        if (st != CPLB_OK) return bail(st);
         const size_t out_doubles = (oc - og) + ((flags & CPLB_WANT_COST) ? (size_t)chunk : 0);
-        if (out_doubles) CPLB_CUDA(cudaMemcpyAsync(h + og, d + og, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (out_doubles) {
+            cudaError_t e = cudaMemcpyAsync(h + og, d + og, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, stream);
+            if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpyAsync (device to host)"));
+        }
         pend[s].i0 = i0;
         pend[s].cnt = cnt;
     }
     for (int t = 0; t < kHostStreams; t++) {
         cplb_status st = drain(t);
-        if (st != CPLB_OK) return st;
+        if (st != CPLB_OK) return bail(st);
     }
+    return CPLB_OK;
+}
+
+// One chunk [i0, i0 + cnt) of a pinned-buffer call on stream s of one device's pipeline: H2D, kernel, D2H, all asynchronous.
+static cplb_status enqueue_chunk(cplb_problem* p, HostPipe& pipe, int s, const cplb_eval_args* args, unsigned flags, long long ld, long long chunk,
+                                 long long i0, long long cnt)
+{
+    const int n = p->layout.n, m = p->layout.m, nnz = jac_len(p, flags);
+    const bool cm = args->layout == CPLB_COMPONENT_MAJOR;
+    const bool skip_const = (args->host_flags & CPLB_HOST_JAC_CONSTANTS_PRESENT) != 0;
+    cudaStream_t stream = pipe.streams[s];
+    double* d = pipe.stage[s];
+    double* dx = d;
+    d += (size_t)n * chunk;
+    double *dg_ = nullptr, *dj = nullptr, *dc = nullptr, *dgr = nullptr;
+    if (flags & CPLB_WANT_G) { dg_ = d; d += (size_t)m * chunk; }
+    if (flags & CPLB_WANT_J) { dj = d; d += (size_t)nnz * chunk; }
+    if (flags & CPLB_WANT_GRAD) { dgr = d; d += (size_t)n * chunk; }
+    if (flags & CPLB_WANT_COST) { dc = d; d += (size_t)chunk; }
+    // device-side chunk buffers use pitch `chunk` (component-major) or are dense (instance-major)
+    CplbInstParams q{};
+    bool per_inst = false;
+    auto h2d = [&](double* dst, const double* src, int len) -> cplb_status {
+        if (cm) CPLB_CUDA(cudaMemcpy2DAsync(dst, chunk * sizeof(double), src + i0, ld * sizeof(double), cnt * sizeof(double), len, cudaMemcpyHostToDevice, stream));
+        else CPLB_CUDA(cudaMemcpyAsync(dst, src + i0 * len, (size_t)cnt * len * sizeof(double), cudaMemcpyHostToDevice, stream));
+        return CPLB_OK;
+    };
+    cplb_status st = h2d(dx, args->x, n);
+    if (st != CPLB_OK) return st;
+    if (args->per_instance)
+        for (const auto& f : kInstFields)
+            if (const double* src = args->per_instance->*(f.src)) {
+                const int len = f.len(p->layout.nc);
+                st = h2d(d, src, len);
+                if (st != CPLB_OK) return st;
+                q.*(f.dst) = d;
+                d += (size_t)len * chunk;
+                per_inst = true;
+            }
+    CplbIo io{dx, dg_, dj, dc, dgr, chunk, cnt};
+    st = launch(p, io, args->layout, flags, stream, per_inst ? &q : nullptr);
+    if (st != CPLB_OK) return st;
+    if (cm) {
+        if (dg_) CPLB_CUDA(cudaMemcpy2DAsync(args->g + i0, ld * sizeof(double), dg_, chunk * sizeof(double), cnt * sizeof(double), m, cudaMemcpyDeviceToHost, stream));
+        if (dj && skip_const) {  // only the rows of x-dependent slots
+            for (const auto& r : p->layout.var_runs)
+                CPLB_CUDA(cudaMemcpy2DAsync(args->jac + (long long)r.begin * ld + i0, ld * sizeof(double), dj + (size_t)r.begin * chunk,
+                                            chunk * sizeof(double), cnt * sizeof(double), r.end - r.begin, cudaMemcpyDeviceToHost, stream));
+        } else if (dj) {
+            CPLB_CUDA(cudaMemcpy2DAsync(args->jac + i0, ld * sizeof(double), dj, chunk * sizeof(double), cnt * sizeof(double), nnz, cudaMemcpyDeviceToHost, stream));
+        }
+        if (dgr) CPLB_CUDA(cudaMemcpy2DAsync(args->grad + i0, ld * sizeof(double), dgr, chunk * sizeof(double), cnt * sizeof(double), n, cudaMemcpyDeviceToHost, stream));
+    } else {
+        if (dg_) CPLB_CUDA(cudaMemcpyAsync(args->g + i0 * m, dg_, (size_t)cnt * m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        // instance-major: the x-dependent slots are 96..432-byte runs inside each 1.4 KB row; strided 2-D DMA copies
+        // of such runs, and a scatter kernel writing them straight into the mapped host buffer, both measured no
+        // faster than one contiguous copy of whole rows (2.16 / 2.17 vs 2.15 ms for 65,536 instances), so the rows
+        // travel whole -- the constant slots are simply rewritten with the same values
+        if (dj) CPLB_CUDA(cudaMemcpyAsync(args->jac + i0 * nnz, dj, (size_t)cnt * nnz * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (dgr) CPLB_CUDA(cudaMemcpyAsync(args->grad + i0 * n, dgr, (size_t)cnt * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    if (dc) CPLB_CUDA(cudaMemcpyAsync(args->cost + i0, dc, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
     return CPLB_OK;
 }
 
 // ticket == nullptr: synchronous (returns when the outputs have landed).  Otherwise the work is only enqueued, a completion
 // event per stream is recorded into the next ticket slot and its index returned; pinned buffers are required then.
+// A sharded problem cuts [0, N) into one contiguous range per device and drives every device's pipeline from this call:
+// with pinned buffers everything is asynchronous, so the chunks of all devices are enqueued round robin by the calling thread;
+// pageable buffers are packed / unpacked by one worker thread per device.
 static cplb_status eval_host_impl(cplb_problem* p, const cplb_eval_args* args, int32_t* ticket)
 {
     CPLB_REQUIRE(p);
@@ -908,20 +1123,26 @@ static cplb_status eval_host_impl(cplb_problem* p, const cplb_eval_args* args, i
     cplb_status st = check_args(p, args, &flags, &ld);
     if (st != CPLB_OK) return st;
     const long long N = args->num_instances;
-    if (N == 0 || flags == 0) return CPLB_OK;
+    if (N == 0 || (flags & 15u) == 0) return CPLB_OK;
     st = bind_device(p);
     if (st != CPLB_OK) return st;
-    DeviceGuard dg(p->device);
-    if (!dg.ok) return fail(CPLB_CUDA_ERROR, "cudaSetDevice(%d) failed", p->device);
     std::lock_guard<std::mutex> lk(p->host_mu);
+    const int shards = (int)p->pipes.size();
+    DeviceGuard restore(p->pipes[0].device);  // every cudaSetDevice below is undone when the call returns
+    if (!restore.ok) return fail(CPLB_CUDA_ERROR, "cudaSetDevice(%d) failed", p->pipes[0].device);
 
-    const int n = p->layout.n, m = p->layout.m, nnz = p->layout.nnz;
-    // chunk: big enough for efficient PCIe bursts (several MB per copy), small enough that three
-    // chunks in flight overlap H2D, kernel and D2H
-    // 32,768-instance chunks (few, long copies: the download engine is the bound).  A synchronous call starts with one
-    // short chunk so that its first download begins early; a queued call is preceded by the previous call's downloads anyway.
+    const int n = p->layout.n, m = p->layout.m, nnz = jac_len(p, flags);
+    // 32,768-instance chunks (few, long copies: the download engine is the bound), big enough for efficient PCIe bursts, small
+    // enough that three chunks in flight overlap H2D, kernel and D2H.  A synchronous call starts with one short chunk so that
+    // its first download begins early; a queued call is preceded by the previous call's downloads anyway.
+    long long longest = 0;
+    for (int sh = 0; sh < shards; sh++) {
+        long long b, e;
+        shard_range(N, sh, shards, &b, &e);
+        if (e - b > longest) longest = e - b;
+    }
     long long chunk = 32768;
-    if (chunk > N) chunk = N;
+    if (chunk > longest) chunk = longest;
     chunk = (chunk + 31) & ~31LL;  // keeps every chunk's slices 16-byte aligned and tile-aligned
     size_t per_inst = (size_t)n;
     if (flags & CPLB_WANT_G) per_inst += m;
@@ -931,95 +1152,130 @@ static cplb_status eval_host_impl(cplb_problem* p, const cplb_eval_args* args, i
     if (args->per_instance)
         for (const auto& f : kInstFields)
             if (args->per_instance->*(f.src)) per_inst += f.len(p->layout.nc);
-    st = ensure_host_pipeline(p, per_inst * (size_t)chunk * sizeof(double));
-    if (st != CPLB_OK) return st;
+    const size_t stage_bytes = per_inst * (size_t)chunk * sizeof(double);
+    auto set_device = [&](int sh) -> cplb_status {
+        if (shards > 1) CPLB_CUDA(cudaSetDevice(p->pipes[(size_t)sh].device));
+        return CPLB_OK;
+    };
+    for (int sh = 0; sh < shards; sh++) {
+        long long b, e;
+        shard_range(N, sh, shards, &b, &e);
+        if (b == e) continue;
+        st = set_device(sh);
+        if (st == CPLB_OK) st = ensure_host_pipeline(p->pipes[(size_t)sh], stage_bytes);
+        if (st != CPLB_OK) return st;
+    }
 
     bool all_pinned = is_pinned(args->x) && is_pinned(args->g) && is_pinned(args->jac) && is_pinned(args->cost) && is_pinned(args->grad);
     if (args->per_instance)
         for (const auto& f : kInstFields) all_pinned = all_pinned && is_pinned(args->per_instance->*(f.src));
     if (!all_pinned) {
         if (ticket) return fail(CPLB_INVALID_ARGUMENT, "cplb_eval_host_begin needs pinned host buffers (cplb_host_alloc)");
-        return eval_host_bounced(p, args, flags, ld, chunk, per_inst * (size_t)chunk * sizeof(double));
+        if (shards == 1) return eval_host_bounced(p, p->pipes[0], args, flags, ld, chunk, stage_bytes, 0, N);
+        std::vector<std::thread> workers;
+        std::vector<cplb_status> status((size_t)shards, CPLB_OK);
+        std::vector<std::string> message((size_t)shards);
+        for (int sh = 0; sh < shards; sh++) {
+            long long b, e;
+            shard_range(N, sh, shards, &b, &e);
+            if (b == e) continue;
+            workers.emplace_back([&, sh, b, e] {
+                HostPipe& pipe = p->pipes[(size_t)sh];
+                if (cudaSetDevice(pipe.device) != cudaSuccess) {
+                    status[(size_t)sh] = CPLB_CUDA_ERROR;
+                    message[(size_t)sh] = "cudaSetDevice failed in a shard worker";
+                    return;
+                }
+                status[(size_t)sh] = eval_host_bounced(p, pipe, args, flags, ld, chunk, stage_bytes, b, e);
+                if (status[(size_t)sh] != CPLB_OK) message[(size_t)sh] = g_last_error;  // the worker's thread-local message
+            });
+        }
+        for (auto& w : workers) w.join();
+        for (int sh = 0; sh < shards; sh++)
+            if (status[(size_t)sh] != CPLB_OK) return fail(status[(size_t)sh], "shard %d (device %d): %s", sh, p->pipes[(size_t)sh].device, message[(size_t)sh].c_str());
+        return CPLB_OK;
     }
-    if (ticket && !p->host_done_ready) {
-        for (int t = 0; t < kHostTickets; t++)
-            for (int q = 0; q < kHostStreams; q++) CPLB_CUDA(cudaEventCreateWithFlags(&p->host_done[t][q], cudaEventDisableTiming));
-        p->host_done_ready = true;
+    if (ticket) {
+        for (int sh = 0; sh < shards; sh++) {
+            HostPipe& pipe = p->pipes[(size_t)sh];
+            if (pipe.host_done_ready || !pipe.streams_ready) continue;
+            st = set_device(sh);
+            if (st != CPLB_OK) return st;
+            for (int t = 0; t < kHostTickets; t++)
+                for (int q = 0; q < kHostStreams; q++) CPLB_CUDA(cudaEventCreateWithFlags(&pipe.host_done[t][q], cudaEventDisableTiming));
+            pipe.host_done_ready = true;
+        }
     }
 
-    const bool cm = args->layout == CPLB_COMPONENT_MAJOR;
-    const bool skip_const = (args->host_flags & CPLB_HOST_JAC_CONSTANTS_PRESENT) != 0;
-    // the round robin over the streams continues across calls: the first chunk of a queued call then lands on the stream
-    // whose previous work finished longest ago instead of behind the previous call's last download
-    int s = p->next_stream;
-    const long long first = (!ticket && N > chunk) ? chunk / 4 : chunk;
-    for (long long i0 = 0, cnt = 0; i0 < N; i0 += cnt, s = (s + 1) % kHostStreams) {
-        const long long want = (i0 == 0) ? first : chunk;
-        cnt = (N - i0) < want ? (N - i0) : want;
-        cudaStream_t stream = p->streams[s];
-        double* d = p->stage[s];
-        double* dx = d;
-        d += (size_t)n * chunk;
-        double *dg_ = nullptr, *dj = nullptr, *dc = nullptr, *dgr = nullptr;
-        if (flags & CPLB_WANT_G) { dg_ = d; d += (size_t)m * chunk; }
-        if (flags & CPLB_WANT_J) { dj = d; d += (size_t)nnz * chunk; }
-        if (flags & CPLB_WANT_GRAD) { dgr = d; d += (size_t)n * chunk; }
-        if (flags & CPLB_WANT_COST) { dc = d; d += (size_t)chunk; }
-        // device-side chunk buffers use pitch `chunk` (component-major) or are dense (instance-major)
-        CplbInstParams q{};
-        bool per_inst = false;
-        auto h2d = [&](double* dst, const double* src, int len) -> cplb_status {
-            if (cm) CPLB_CUDA(cudaMemcpy2DAsync(dst, chunk * sizeof(double), src + i0, ld * sizeof(double), cnt * sizeof(double), len, cudaMemcpyHostToDevice, stream));
-            else CPLB_CUDA(cudaMemcpyAsync(dst, src + i0 * len, (size_t)cnt * len * sizeof(double), cudaMemcpyHostToDevice, stream));
-            return CPLB_OK;
-        };
-        st = h2d(dx, args->x, n);
-        if (st != CPLB_OK) return st;
-        if (args->per_instance)
-            for (const auto& f : kInstFields)
-                if (const double* src = args->per_instance->*(f.src)) {
-                    const int len = f.len(p->layout.nc);
-                    st = h2d(d, src, len);
-                    if (st != CPLB_OK) return st;
-                    q.*(f.dst) = d;
-                    d += (size_t)len * chunk;
-                    per_inst = true;
-                }
-        CplbIo io{dx, dg_, dj, dc, dgr, chunk, cnt};
-        st = launch(p, io, args->layout, flags, stream, per_inst ? &q : nullptr);
-        if (st != CPLB_OK) return st;
-        if (cm) {
-            if (dg_) CPLB_CUDA(cudaMemcpy2DAsync(args->g + i0, ld * sizeof(double), dg_, chunk * sizeof(double), cnt * sizeof(double), m, cudaMemcpyDeviceToHost, stream));
-            if (dj && skip_const) {  // only the rows of x-dependent slots
-                for (const auto& r : p->layout.var_runs)
-                    CPLB_CUDA(cudaMemcpy2DAsync(args->jac + (long long)r.begin * ld + i0, ld * sizeof(double), dj + (size_t)r.begin * chunk,
-                                                chunk * sizeof(double), cnt * sizeof(double), r.end - r.begin, cudaMemcpyDeviceToHost, stream));
-            } else if (dj) {
-                CPLB_CUDA(cudaMemcpy2DAsync(args->jac + i0, ld * sizeof(double), dj, chunk * sizeof(double), cnt * sizeof(double), nnz, cudaMemcpyDeviceToHost, stream));
-            }
-            if (dgr) CPLB_CUDA(cudaMemcpy2DAsync(args->grad + i0, ld * sizeof(double), dgr, chunk * sizeof(double), cnt * sizeof(double), n, cudaMemcpyDeviceToHost, stream));
-        } else {
-            if (dg_) CPLB_CUDA(cudaMemcpyAsync(args->g + i0 * m, dg_, (size_t)cnt * m * sizeof(double), cudaMemcpyDeviceToHost, stream));
-            // instance-major: the x-dependent slots are 96..432-byte runs inside each 1.4 KB row; strided 2-D DMA copies
-            // of such runs, and a scatter kernel writing them straight into the mapped host buffer, both measured no
-            // faster than one contiguous copy of whole rows (2.16 / 2.17 vs 2.15 ms for 65,536 instances), so the rows
-            // travel whole -- the constant slots are simply rewritten with the same values
-            if (dj) {
-                CPLB_CUDA(cudaMemcpyAsync(args->jac + i0 * nnz, dj, (size_t)cnt * nnz * sizeof(double), cudaMemcpyDeviceToHost, stream));
-            }
-            if (dgr) CPLB_CUDA(cudaMemcpyAsync(args->grad + i0 * n, dgr, (size_t)cnt * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    // On any failure after the first enqueue nothing may stay in flight: the caller gets an error and no ticket, so it has
+    // nothing to wait on before it frees or reuses its buffers.
+    auto bail = [&](cplb_status err) {
+        char keep[sizeof g_last_error];
+        std::memcpy(keep, g_last_error, sizeof keep);
+        for (int sh = 0; sh < shards; sh++) {
+            HostPipe& pipe = p->pipes[(size_t)sh];
+            if (!pipe.streams_ready) continue;
+            if (shards > 1) cudaSetDevice(pipe.device);
+            for (int t = 0; t < kHostStreams; t++) cudaStreamSynchronize(pipe.streams[t]);
         }
-        if (dc) CPLB_CUDA(cudaMemcpyAsync(args->cost + i0, dc, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        std::memcpy(g_last_error, keep, sizeof keep);
+        return err;
+    };
+    // The round robin over a pipeline's streams continues across calls: the first chunk of a queued call then lands on the
+    // stream whose previous work finished longest ago instead of behind the previous call's last download.  Chunks of the
+    // devices are enqueued interleaved (chunk 0 of every shard, then chunk 1, ...) so that every device starts at once.
+    struct Cursor { long long next, end; bool first; };
+    std::vector<Cursor> cur((size_t)shards);
+    for (int sh = 0; sh < shards; sh++) {
+        long long b, e;
+        shard_range(N, sh, shards, &b, &e);
+        cur[(size_t)sh] = Cursor{b, e, true};
     }
-    p->next_stream = s;
+    for (bool any = true; any;) {
+        any = false;
+        for (int sh = 0; sh < shards; sh++) {
+            Cursor& c = cur[(size_t)sh];
+            if (c.next >= c.end) continue;
+            any = true;
+            HostPipe& pipe = p->pipes[(size_t)sh];
+            const long long len = c.end - c.next;
+            long long want = chunk;
+            if (c.first && !ticket && len > chunk) want = chunk / 4;
+            const long long cnt = len < want ? len : want;
+            st = set_device(sh);
+            if (st == CPLB_OK) st = enqueue_chunk(p, pipe, pipe.next_stream, args, flags, ld, chunk, c.next, cnt);
+            pipe.next_stream = (pipe.next_stream + 1) % kHostStreams;
+            if (st != CPLB_OK) return bail(st);
+            c.next += cnt;
+            c.first = false;
+        }
+    }
     if (!ticket) {
-        for (int t = 0; t < kHostStreams; t++) CPLB_CUDA(cudaStreamSynchronize(p->streams[t]));
+        for (int sh = 0; sh < shards; sh++) {
+            HostPipe& pipe = p->pipes[(size_t)sh];
+            if (!pipe.streams_ready) continue;
+            st = set_device(sh);
+            if (st != CPLB_OK) return bail(st);
+            for (int t = 0; t < kHostStreams; t++) {
+                cudaError_t e = cudaStreamSynchronize(pipe.streams[t]);
+                if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamSynchronize"));
+            }
+        }
         return CPLB_OK;
     }
     const int slot = p->next_ticket;
     p->next_ticket = (slot + 1) % kHostTickets;
     // the slot's previous use must be over before its events are re-recorded (the caller waited for it or never will)
-    for (int t = 0; t < kHostStreams; t++) CPLB_CUDA(cudaEventRecord(p->host_done[slot][t], p->streams[t]));
+    for (int sh = 0; sh < shards; sh++) {
+        HostPipe& pipe = p->pipes[(size_t)sh];
+        if (!pipe.host_done_ready) continue;
+        st = set_device(sh);
+        if (st != CPLB_OK) return bail(st);
+        for (int t = 0; t < kHostStreams; t++) {
+            cudaError_t e = cudaEventRecord(pipe.host_done[slot][t], pipe.streams[t]);
+            if (e != cudaSuccess) return bail(cuda_fail(e, "cudaEventRecord"));
+        }
+    }
     *ticket = slot;
     return CPLB_OK;
 }
@@ -1036,10 +1292,16 @@ cplb_status cplb_eval_host_wait(cplb_problem* p, int32_t ticket)
 {
     CPLB_REQUIRE(p);
     if (ticket == -1) return CPLB_OK;  // an empty call (no instances / no outputs) completed at once
-    if (ticket < 0 || ticket >= kHostTickets || !p->host_done_ready) return fail(CPLB_INVALID_ARGUMENT, "unknown ticket %d", (int)ticket);
-    DeviceGuard dg(p->device);
-    if (!dg.ok) return fail(CPLB_CUDA_ERROR, "cudaSetDevice(%d) failed", p->device);
-    for (int t = 0; t < kHostStreams; t++) CPLB_CUDA(cudaEventSynchronize(p->host_done[ticket][t]));
+    bool any_ready = false;
+    for (const auto& pipe : p->pipes) any_ready = any_ready || pipe.host_done_ready;
+    if (ticket < 0 || ticket >= kHostTickets || !any_ready) return fail(CPLB_INVALID_ARGUMENT, "unknown ticket %d", (int)ticket);
+    DeviceGuard restore(p->pipes[0].device);
+    if (!restore.ok) return fail(CPLB_CUDA_ERROR, "cudaSetDevice(%d) failed", p->pipes[0].device);
+    for (auto& pipe : p->pipes) {
+        if (!pipe.host_done_ready) continue;
+        if (p->pipes.size() > 1) CPLB_CUDA(cudaSetDevice(pipe.device));
+        for (int t = 0; t < kHostStreams; t++) CPLB_CUDA(cudaEventSynchronize(pipe.host_done[ticket][t]));
+    }
     return CPLB_OK;
 }
 

@@ -22,13 +22,13 @@ namespace cplb {
 template <int ENV>
 cudaError_t launch_cm_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, int cm_kernel, cudaStream_t st);
 template <int ENV>
-cudaError_t launch_im_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st);
+cudaError_t launch_im_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, int im_kernel, cudaStream_t st);
 extern template cudaError_t launch_cm_env<CPLB_ENV_NONE_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, int, cudaStream_t);
 extern template cudaError_t launch_cm_env<CPLB_ENV_GROUND_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, int, cudaStream_t);
 extern template cudaError_t launch_cm_env<CPLB_ENV_SUPERQUADRIC_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, int, cudaStream_t);
-extern template cudaError_t launch_im_env<CPLB_ENV_NONE_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, cudaStream_t);
-extern template cudaError_t launch_im_env<CPLB_ENV_GROUND_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, cudaStream_t);
-extern template cudaError_t launch_im_env<CPLB_ENV_SUPERQUADRIC_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, cudaStream_t);
+extern template cudaError_t launch_im_env<CPLB_ENV_NONE_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, int, cudaStream_t);
+extern template cudaError_t launch_im_env<CPLB_ENV_GROUND_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, int, cudaStream_t);
+extern template cudaError_t launch_im_env<CPLB_ENV_SUPERQUADRIC_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, int, cudaStream_t);
 
 cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, int cm_kernel, cudaStream_t st)
 {
@@ -41,13 +41,13 @@ cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsign
     }
 }
 
-cudaError_t launch_instance_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
+cudaError_t launch_instance_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, int im_kernel, cudaStream_t st)
 {
     if (io.N <= 0) return cudaSuccess;
     switch (P.env) {
-    case CPLB_ENV_NONE_K: return launch_im_env<CPLB_ENV_NONE_K>(P, io, flags, Q, st);
-    case CPLB_ENV_GROUND_K: return launch_im_env<CPLB_ENV_GROUND_K>(P, io, flags, Q, st);
-    default: return launch_im_env<CPLB_ENV_SUPERQUADRIC_K>(P, io, flags, Q, st);
+    case CPLB_ENV_NONE_K: return launch_im_env<CPLB_ENV_NONE_K>(P, io, flags, Q, im_kernel, st);
+    case CPLB_ENV_GROUND_K: return launch_im_env<CPLB_ENV_GROUND_K>(P, io, flags, Q, im_kernel, st);
+    default: return launch_im_env<CPLB_ENV_SUPERQUADRIC_K>(P, io, flags, Q, im_kernel, st);
     }
 }
 

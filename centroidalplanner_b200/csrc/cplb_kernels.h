@@ -16,8 +16,13 @@ namespace cplb {
 #define CPLB_CM_WHOLE 2
 cudaError_t launch_component_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* per_instance, int cm_kernel,
                                    cudaStream_t st);
-// buf[i*len + e]: warp tiles staged through shared memory with bulk async (TMA) copies.
-cudaError_t launch_instance_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* per_instance, cudaStream_t st);
+// buf[i*len + e]: tiles staged through shared memory with bulk async (TMA) copies; im_kernel picks the kernel: auto, a warp
+// per tile (lanes = (instance, contact) grid), or a CTA per tile (one warp per contact, lanes = instances).
+#define CPLB_IM_AUTO 0
+#define CPLB_IM_WARP_TILE 1
+#define CPLB_IM_CTA_TILE 2
+cudaError_t launch_instance_major(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* per_instance, int im_kernel,
+                                  cudaStream_t st);
 
 }  // namespace cplb
 #endif

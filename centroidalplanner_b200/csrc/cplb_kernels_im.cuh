@@ -11,6 +11,11 @@
 namespace cplb {
 
 constexpr int kMaxDevices = 64;
+// AUTO: the CTA-tile kernel where it measured faster (profiles/r02_instance_major.md): an even number of contacts from 4 on
+// (n = 3 + 9 nc is then odd: its lane = instance shared-memory accesses are conflict-free), one contact, more than 8 contacts.
+// With an odd contact count > 1 the row lengths n, m are even and lanes that step through instances collide on a few banks:
+// those shapes and the two-contact one stay on the warp-tile kernel.
+inline bool instance_major_auto_is_cta_tile(int nc) { return (nc % 2 == 0 && nc >= 4) || nc == 1 || nc > 8; }
 
 // ================================================================================================
 // instance-major (AoS): warp tile, LPI lanes per instance, bulk async copies in and out
@@ -406,9 +411,21 @@ cudaError_t launch_im_cfg(const CplbParams& P, const CplbIo& io, unsigned flags,
     return launch_im_kernel<ENV, LPI, 1, 0u, false>(P, io, flags, per_warp, Q, PT, st);  // many contacts: one warp per CTA
 }
 
+}  // namespace cplb
+
+#include "cplb_kernels_imc.cuh"
+
+namespace cplb {
+
+// im_kernel: CPLB_IM_AUTO (pick by shape), CPLB_IM_WARP_TILE (eval_instance_major: a warp per tile), CPLB_IM_CTA_TILE
+// (eval_instance_major_cta: a CTA per tile, one warp per contact) -- cplb_set_instance_major_kernel; the parity tests force
+// each of them on the same inputs.
 template <int ENV>
-cudaError_t launch_im_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
+cudaError_t launch_im_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, int im_kernel, cudaStream_t st)
 {
+    const bool cta_tile = im_kernel == CPLB_IM_CTA_TILE || (im_kernel == CPLB_IM_AUTO && instance_major_auto_is_cta_tile(P.nc)) ||
+                          (flags & CPLB_JAC_PACKED_K);  // packed Jacobian slices exist in the CTA-tile kernel only
+    if (cta_tile) return launch_imc_env<ENV>(P, io, flags, Q, st);
     // lanes per instance: the smallest power of two >= nc (capped at 8; more contacts loop)
     if (P.nc <= 1) return launch_im_cfg<ENV, 1>(P, io, flags, Q, st);
     if (P.nc <= 2) return launch_im_cfg<ENV, 2>(P, io, flags, Q, st);

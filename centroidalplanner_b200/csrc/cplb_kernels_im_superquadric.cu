@@ -2,5 +2,5 @@
 #include "cplb_kernels_im.cuh"
 
 namespace cplb {
-template cudaError_t launch_im_env<CPLB_ENV_SUPERQUADRIC_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, cudaStream_t);
+template cudaError_t launch_im_env<CPLB_ENV_SUPERQUADRIC_K>(const CplbParams&, const CplbIo&, unsigned, const CplbInstParams*, int, cudaStream_t);
 }  // namespace cplb

@@ -23,6 +23,7 @@ struct Layout {
     std::vector<double> const_value;
     struct Run { int begin, end; };  // [begin, end) runs of x-dependent slots
     std::vector<Run> var_runs;
+    std::vector<int32_t> packed_to_slot;  // the x-dependent slots in slot order: element q of a PACKED Jacobian slice is slot packed_to_slot[q]
 
     static int col_com() { return 0; }
     static int col_F(int k) { return 3 + 9 * k; }  // AddVariableSet order: F_, p_, n_ per name (CplProblem.cpp:31-33)
@@ -87,6 +88,9 @@ struct Layout {
             }
         }
         nnz = (int)iRow.size();
+        packed_to_slot.clear();
+        for (int s = 0; s < nnz; s++)
+            if (!is_const[s]) packed_to_slot.push_back(s);
         var_runs.clear();
         for (int s = 0; s < nnz;) {
             if (is_const[s]) {

@@ -133,7 +133,10 @@ class BatchedCplProblem:
     env=None selects the CoMPlanner variant (FrictionCone only, src/CplProblem.cpp:63-71).
     """
 
-    def __init__(self, contact_names, robot_mass, env=None, device=None):
+    def __init__(self, contact_names, robot_mass, env=None, device=None, devices=None):
+        """device: CUDA ordinal (None: the current device at the first evaluation).  devices: a list of ordinals makes this a
+        SHARDED problem (cplb_create_sharded): host-buffer evaluations then cut the batch into one contiguous range per device
+        and drive all of them from this process; device tensors go through eval_shard()."""
         self._lib = _cabi.load()
         self._names = [str(s) for s in contact_names]
         self._env = env
@@ -141,8 +144,15 @@ class BatchedCplProblem:
         self._ground_fake = Ground() if env is None else None  # CplProblem.cpp:14
         arr = (C.c_char_p * len(self._names))(*[s.encode() for s in self._names])
         h = C.c_void_p()
-        dev = -1 if device is None else int(device)
-        _check(self._lib.cplb_create(len(self._names), arr, self._env_kind, float(robot_mass), dev, C.byref(h)))
+        if devices is not None:
+            if device is not None:
+                raise ValueError("give either device or devices")
+            devs = np.ascontiguousarray(np.asarray(list(devices), dtype=np.int32))
+            _check(self._lib.cplb_create_sharded(len(self._names), arr, self._env_kind, float(robot_mass), len(devs),
+                                                 devs.ctypes.data_as(_cabi.ip), C.byref(h)))
+        else:
+            dev = -1 if device is None else int(device)
+            _check(self._lib.cplb_create(len(self._names), arr, self._env_kind, float(robot_mass), dev, C.byref(h)))
         self._h = h
         n, m, nnz = C.c_int32(), C.c_int32(), C.c_int32()
         _check(self._lib.cplb_get_dims(self._h, C.byref(n), C.byref(m), C.byref(nnz)))
@@ -322,6 +332,22 @@ class BatchedCplProblem:
         kernel = {"auto": _cabi.KERNEL_AUTO, "split": _cabi.KERNEL_PER_CONTACT, "whole": _cabi.KERNEL_PER_INSTANCE}.get(kernel, kernel)
         _check(self._lib.cplb_set_component_major_kernel(self._h, int(kernel)))
 
+    def SetInstanceMajorKernel(self, kernel):
+        """cplb_set_instance_major_kernel: KERNEL_AUTO / KERNEL_WARP_TILE / KERNEL_CTA_TILE (or 'auto', 'warp', 'cta')."""
+        kernel = {"auto": _cabi.KERNEL_AUTO, "warp": _cabi.KERNEL_WARP_TILE, "cta": _cabi.KERNEL_CTA_TILE}.get(kernel, kernel)
+        _check(self._lib.cplb_set_instance_major_kernel(self._h, int(kernel)))
+
+    def GetNumShards(self):
+        v = C.c_int32()
+        _check(self._lib.cplb_get_num_shards(self._h, C.byref(v)))
+        return v.value
+
+    def GetShard(self, shard, num_instances):
+        """(device ordinal, begin, end): the contiguous instance range of a batch of num_instances that shard evaluates."""
+        d, b, e = C.c_int32(), C.c_int64(), C.c_int64()
+        _check(self._lib.cplb_get_shard(self._h, int(shard), int(num_instances), C.byref(d), C.byref(b), C.byref(e)))
+        return d.value, b.value, e.value
+
     def GetDevice(self):
         d = C.c_int32()
         _check(self._lib.cplb_get_device(self._h, C.byref(d)))
@@ -337,6 +363,24 @@ class BatchedCplProblem:
         val = np.zeros(self.nnz)
         _check(self._lib.cplb_get_jacobian_constants(self._h, mask.ctypes.data_as(C.POINTER(C.c_uint8)), val.ctypes.data_as(_cabi.dp)))
         return mask.astype(bool), val
+
+    def GetPackedJacobianMap(self):
+        """packed_to_slot[nv]: element q of a packed Jacobian slice (jac_packed=True) is structural slot packed_to_slot[q]."""
+        nv = C.c_int32()
+        _check(self._lib.cplb_get_packed_jacobian_map(self._h, C.byref(nv), None))
+        m = np.zeros(nv.value, dtype=np.int32)
+        _check(self._lib.cplb_get_packed_jacobian_map(self._h, C.byref(nv), m.ctypes.data_as(_cabi.ip)))
+        return m
+
+    def UnpackJacobian(self, packed):
+        """cplb_unpack_jacobian: (N, nv) packed host slices -> (N, nnz) full rows, constants included."""
+        a = np.ascontiguousarray(packed.numpy() if _is_torch(packed) else packed, dtype=np.float64)
+        nv = len(self.GetPackedJacobianMap())
+        if a.ndim != 2 or a.shape[1] != nv:
+            raise ValueError(f"packed has shape {a.shape}, expected (N, {nv})")
+        full = np.empty((a.shape[0], self.nnz))
+        _check(self._lib.cplb_unpack_jacobian(self._h, a.shape[0], a.ctypes.data_as(_cabi.dp), full.ctypes.data_as(_cabi.dp)))
+        return full
 
     def FillJacobianConstants(self, jac_host, layout=_cabi.INSTANCE_MAJOR):
         """Write the constant slots of a host jac buffer once; later host evaluations into the same buffer may then
@@ -381,16 +425,23 @@ class BatchedCplProblem:
         return st, keep
 
     def eval(self, x, g=True, jac=True, cost=False, grad=False, layout=_cabi.INSTANCE_MAJOR, out=None, stream=None,
-             jac_constants_present=False, per_instance=None, inputs_ready=False):
+             jac_constants_present=False, per_instance=None, inputs_ready=False, jac_packed=False):
         """One batched evaluation.  x: (N, n) [instance-major] or (n, N) [component-major], fp64,
         a torch CUDA tensor (device path, asynchronous on the current stream) or a NumPy array /
         CPU tensor (host path through cplb_eval_host).  Returns a dict of outputs of the same kind."""
         out = dict(out or {})
         if _is_torch(x) and x.is_cuda:
-            return self._eval_device(x, g, jac, cost, grad, layout, out, stream, per_instance, inputs_ready)
-        return self._eval_host(x, g, jac, cost, grad, layout, out, jac_constants_present, per_instance)
+            return self._eval_device(x, g, jac, cost, grad, layout, out, stream, per_instance, inputs_ready, jac_packed=jac_packed)
+        return self._eval_host(x, g, jac, cost, grad, layout, out, jac_constants_present, per_instance, jac_packed=jac_packed)
 
-    def _eval_device(self, x, g, jac, cost, grad, layout, out, stream, per_instance=None, inputs_ready=False):
+    def _jac_len(self, jac_packed):
+        if not jac_packed:
+            return self.nnz
+        if getattr(self, "_nv", None) is None:
+            self._nv = len(self.GetPackedJacobianMap())
+        return self._nv
+
+    def _eval_device(self, x, g, jac, cost, grad, layout, out, stream, per_instance=None, inputs_ready=False, shard=None, jac_packed=False):
         import torch
 
         if x.dtype != torch.float64 or not x.is_contiguous() or x.dim() != 2:
@@ -398,7 +449,7 @@ class BatchedCplProblem:
         N = x.shape[0] if layout == _cabi.INSTANCE_MAJOR else x.shape[1]
         if tuple(x.shape) != self._shape(self.n, N, layout):
             raise ValueError(f"x has shape {tuple(x.shape)}, expected {self._shape(self.n, N, layout)} for this layout")
-        bound = self.GetDevice()
+        bound = self.GetDevice() if shard is None else self.GetShard(shard, 0)[0]
         if bound >= 0 and bound != x.device.index:
             raise ValueError(f"this problem evaluates on cuda:{bound}; x lives on {x.device}")
 
@@ -417,29 +468,38 @@ class BatchedCplProblem:
                 raise ValueError(f"out['{key}'] has shape {tuple(t.shape)}, expected {shape}")
             return t
 
-        res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self.nnz), "cost": buf("cost", cost, None),
+        res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self._jac_len(jac_packed)), "cost": buf("cost", cost, None),
                "grad": buf("grad", grad, self.n)}
         pi, keep = self._instance_params(per_instance, N, layout, x.device)
-        args = _cabi.EvalArgs(N, layout, _cabi.DEVICE_INPUTS_READY if inputs_ready else 0, N, x.data_ptr(), *[None if res[k] is None else res[k].data_ptr()
+        args = _cabi.EvalArgs(N, layout, (_cabi.DEVICE_INPUTS_READY if inputs_ready else 0) | (_cabi.JAC_PACKED if jac_packed else 0), N, x.data_ptr(), *[None if res[k] is None else res[k].data_ptr()
                                                               for k in ("g", "jac", "cost", "grad")],
                               C.pointer(pi) if pi is not None else None)
         s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
         # a problem created without a device binds to the calling thread's CURRENT device at its first evaluation: make that x's
         with torch.cuda.device(x.device):
-            _check(self._lib.cplb_eval_device(self._h, C.byref(args), C.c_void_p(s)))
+            if shard is None:
+                _check(self._lib.cplb_eval_device(self._h, C.byref(args), C.c_void_p(s)))
+            else:
+                _check(self._lib.cplb_eval_device_shard(self._h, shard, C.byref(args), C.c_void_p(s)))
         return res
 
+    def eval_shard(self, shard, x, g=True, jac=True, cost=False, grad=False, layout=_cabi.INSTANCE_MAJOR, out=None, stream=None,
+                   per_instance=None, inputs_ready=False, jac_packed=False):
+        """cplb_eval_device_shard: x (and the outputs) are CUDA tensors on the shard's device holding that shard's instances."""
+        return self._eval_device(x, g, jac, cost, grad, layout, dict(out or {}), stream, per_instance, inputs_ready, shard=int(shard),
+                                 jac_packed=jac_packed)
+
     def eval_host_begin(self, x, out, g=True, jac=True, cost=False, grad=False, layout=_cabi.INSTANCE_MAJOR,
-                        jac_constants_present=False, per_instance=None):
+                        jac_constants_present=False, per_instance=None, jac_packed=False):
         """cplb_eval_host_begin: enqueue one host-buffer evaluation and return (ticket, outputs) without waiting.  `x` and
         every array in `out` must be PINNED NumPy arrays (cplb_host_alloc) that stay alive and untouched until
         `eval_host_wait(ticket)`; with two buffer sets (begin k+1, wait k) consecutive batches keep the PCIe link busy."""
-        return self._eval_host(x, g, jac, cost, grad, layout, dict(out), jac_constants_present, per_instance, begin=True)
+        return self._eval_host(x, g, jac, cost, grad, layout, dict(out), jac_constants_present, per_instance, begin=True, jac_packed=jac_packed)
 
     def eval_host_wait(self, ticket):
         _check(self._lib.cplb_eval_host_wait(self._h, int(ticket)))
 
-    def _eval_host(self, x, g, jac, cost, grad, layout, out, jac_constants_present=False, per_instance=None, begin=False):
+    def _eval_host(self, x, g, jac, cost, grad, layout, out, jac_constants_present=False, per_instance=None, begin=False, jac_packed=False):
         is_t = _is_torch(x)
         xa = x.numpy() if is_t else np.asarray(x, dtype=np.float64)
         xa = np.ascontiguousarray(xa)
@@ -463,9 +523,9 @@ class BatchedCplProblem:
                 raise ValueError(f"out['{key}'] has shape {tuple(t.shape)}, expected {shape}")
             return t
 
-        res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self.nnz), "cost": buf("cost", cost, None),
+        res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self._jac_len(jac_packed)), "cost": buf("cost", cost, None),
                "grad": buf("grad", grad, self.n)}
-        hflags = _cabi.HOST_JAC_CONSTANTS_PRESENT if jac_constants_present else 0
+        hflags = (_cabi.HOST_JAC_CONSTANTS_PRESENT if jac_constants_present else 0) | (_cabi.JAC_PACKED if jac_packed else 0)
         pi, keep = self._instance_params(per_instance, N, layout, None)
         args = _cabi.EvalArgs(N, layout, hflags, N, xa.ctypes.data, *[None if res[k] is None else res[k].ctypes.data
                                                                      for k in ("g", "jac", "cost", "grad")],

@@ -37,8 +37,9 @@
 extern "C" {
 #endif
 
-#define CPLB_ABI_VERSION 2
+#define CPLB_ABI_VERSION 3
 #define CPLB_MAX_CONTACTS 32
+#define CPLB_MAX_SHARDS 64
 
 typedef enum cplb_status {
     CPLB_OK = 0,
@@ -92,6 +93,26 @@ typedef struct cplb_problem cplb_problem; /* opaque */
 cplb_status cplb_create(int32_t num_contacts, const char *const *contact_names, cplb_env_kind env,
                         double robot_mass, int32_t device, cplb_problem **out);
 void cplb_destroy(cplb_problem *p);
+
+/* The same problem on SEVERAL GPUs of one box, driven from this one process: `devices` lists num_devices CUDA ordinals
+ * (validated now; an ordinal listed twice simply gets two pipelines -- how a one-GPU box exercises the sharded path).  Instances shard by index with no collective anywhere (no cross-instance term exists in
+ * the files under src/Constraints or src/MinimizeCentroidalVariables.cpp): a batch of N instances is cut into contiguous ranges, shard s of
+ * G owning [s*per, (s+1)*per) with per = ceil(N / G) rounded up to a multiple of 32 (cplb_get_shard reports the exact range),
+ * parameters are replicated (they travel as kernel arguments), and
+ *   cplb_eval_host / cplb_eval_host_begin / _wait   take ONE set of host buffers for the whole batch and run every device's
+ *       H2D / kernel / D2H pipeline at once (pinned buffers: all asynchronous, enqueued round robin over the devices by the
+ *       calling thread; pageable buffers: one packing thread per device);
+ *   cplb_eval_device_shard   evaluates device-resident buffers of one shard on that shard's device and stream
+ *       (cplb_eval_device refuses a problem with more than one shard: a device pointer belongs to one device).
+ * Everything else (setters, layout, bounds) is shared by the shards.  This is what a C++ caller in the position of
+ * cpl::solver::CplProblem (src/CplProblem.cpp:6-82) uses to feed the solver threads of one process from all GPUs of the box;
+ * a single-device problem (cplb_create) behaves as a problem with one shard. */
+cplb_status cplb_create_sharded(int32_t num_contacts, const char *const *contact_names, cplb_env_kind env,
+                                double robot_mass, int32_t num_devices, const int32_t *devices, cplb_problem **out);
+cplb_status cplb_get_num_shards(const cplb_problem *p, int32_t *num_shards);
+/* Device ordinal of a shard and its instance range [begin, end) in a batch of num_instances; each out-pointer may be NULL. */
+cplb_status cplb_get_shard(const cplb_problem *p, int32_t shard, int64_t num_instances, int32_t *device, int64_t *begin,
+                           int64_t *end);
 
 /* Thread-local message of the last failing call on this thread ("" if none). */
 const char *cplb_last_error(void);
@@ -217,6 +238,17 @@ typedef struct cplb_instance_params {
  * are always written after the preceding kernel has completed.  Without the bit, plain stream order holds. */
 #define CPLB_DEVICE_INPUTS_READY 2
 
+/* cplb_eval_args.host_flags bit for every evaluation call, INSTANCE_MAJOR only: `jac` is a PACKED slice per instance that holds
+ * only the x-dependent Jacobian slots, jac[i*nv + q] = value of slot packed_to_slot[q] of instance i (cplb_get_packed_jacobian_map;
+ * nv = 102 of 174 for a 4-contact Ground problem, 150 of 174 for a Superquadric one, 6+24*nc of 6+27*nc without environment).
+ * The x-independent slots -- CentroidalStatics' 1.0 identities (CentroidalStatics.cpp:93-95), EnvironmentNormal's
+ * (EnvironmentNormal.cpp:66-68), everything a Ground contributes (Ground.cpp:33-34,49) -- are neither computed into the slice nor
+ * transferred: cplb_get_jacobian_constants has their values, cplb_unpack_jacobian rebuilds full rows on the host, and the IFOPT
+ * views (cplb/ifopt_views.hpp) read a packed batch through the slot map.  The kernel keeps a smaller output tile per instance
+ * and a host call moves 35 % fewer device -> host bytes (4-contact Ground, g + Jacobian).  The packed values are bit-identical to
+ * the same slots of a full evaluation.  Any other layout -> CPLB_INVALID_ARGUMENT. */
+#define CPLB_JAC_PACKED 4
+
 typedef struct cplb_eval_args {
     int64_t num_instances;
     int32_t layout; /* cplb_layout */
@@ -233,6 +265,10 @@ typedef struct cplb_eval_args {
 /* All pointers are DEVICE pointers on the problem's device; the kernel is enqueued on `cuda_stream`
  * (a cudaStream_t, NULL = default stream) and the call returns without synchronising. */
 cplb_status cplb_eval_device(cplb_problem *p, const cplb_eval_args *args, void *cuda_stream);
+
+/* cplb_eval_device for one shard of a sharded problem: all pointers are device pointers on THAT shard's device and hold the
+ * shard's instances only (args->num_instances = their count), `cuda_stream` is a stream of that device. */
+cplb_status cplb_eval_device_shard(cplb_problem *p, int32_t shard, const cplb_eval_args *args, void *cuda_stream);
 
 /* All pointers are HOST pointers (pinned memory makes the copies asynchronous and faster, pageable
  * works).  Instances are cut into chunks; each chunk's host->device copy, kernel and device->host copy
@@ -260,6 +296,13 @@ cplb_status cplb_get_jacobian_constants(const cplb_problem *p, uint8_t *is_const
 cplb_status cplb_fill_jacobian_constants(const cplb_problem *p, int64_t num_instances, int32_t layout, int64_t ld,
                                          double *jac_host);
 
+/* The x-dependent slots in slot order: element q of a CPLB_JAC_PACKED slice is structural slot packed_to_slot[q] (0-based index
+ * into the (iRow, jCol) list of cplb_get_jacobian_structure).  packed_to_slot[*num_packed] may be NULL to query the count only. */
+cplb_status cplb_get_packed_jacobian_map(const cplb_problem *p, int32_t *num_packed, int32_t *packed_to_slot);
+/* Host helper: expands num_instances packed slices (packed[i*nv + q]) into full instance-major rows full[i*nnz + s]: the
+ * values[] array IpoptAdapter::eval_jac_g hands to IPOPT, constants included. */
+cplb_status cplb_unpack_jacobian(const cplb_problem *p, int64_t num_instances, const double *packed, double *full);
+
 /* Pinned host memory for cplb_eval_host buffers (cudaHostAlloc / cudaFreeHost). */
 cplb_status cplb_host_alloc(size_t bytes, void **out);
 cplb_status cplb_host_free(void *ptr);
@@ -275,6 +318,11 @@ cplb_status cplb_host_free(void *ptr);
 #define CPLB_KERNEL_PER_CONTACT 1
 #define CPLB_KERNEL_PER_INSTANCE 2
 cplb_status cplb_set_component_major_kernel(cplb_problem *p, int32_t kernel);
+/* The same for the two INSTANCE_MAJOR kernels: a warp per tile of 32/LPI instances (lanes = an (instance, contact) grid) or a
+ * CTA per tile (one warp per contact, lanes = consecutive instances).  Same arithmetic, same bits; AUTO picks by shape. */
+#define CPLB_KERNEL_WARP_TILE 1
+#define CPLB_KERNEL_CTA_TILE 2
+cplb_status cplb_set_instance_major_kernel(cplb_problem *p, int32_t kernel);
 /* CUDA ordinal this problem evaluates on; -1 while a problem created with device = -1 has not evaluated yet. */
 cplb_status cplb_get_device(const cplb_problem *p, int32_t *device);
 

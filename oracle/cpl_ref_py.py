@@ -109,12 +109,21 @@ class RefProblem:
         lib().cpl_ref_bounds(self._h, _dp(xl), _dp(xu), _dp(gl), _dp(gu))
         return xl, xu, gl, gu
 
-    def eval_batch(self, X, want=("g", "jac", "cost", "grad"), nthreads=1):
+    def eval_batch(self, X, want=("g", "jac", "cost", "grad"), nthreads=1, out=None):
+        """out: optional dict of preallocated C-contiguous float64 arrays (a timed loop must not page-fault fresh arrays)."""
         X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
         N = X.shape[0]
-        g = np.zeros((N, self.m)) if "g" in want else None
-        jac = np.zeros((N, self.nnz)) if "jac" in want else None
-        cost = np.zeros(N) if "cost" in want else None
-        grad = np.zeros((N, self.n)) if "grad" in want else None
+        out = out or {}
+
+        def buf(key, shape):
+            if key not in want:
+                return None
+            a = out.get(key)
+            if a is None:
+                return np.zeros(shape)
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == shape, key
+            return a
+
+        g, jac, cost, grad = buf("g", (N, self.m)), buf("jac", (N, self.nnz)), buf("cost", (N,)), buf("grad", (N, self.n))
         used = lib().cpl_ref_eval_batch(self._h, N, _dp(X), _dp(g), _dp(jac), _dp(cost), _dp(grad), int(nthreads))
         return {"g": g, "jac": jac, "cost": cost, "grad": grad, "threads": used}

@@ -2,6 +2,8 @@
 and the parity comparison (bit-exact where no pow() is upstream, <= 1e-12 relative elsewhere)."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 import centroidalplanner_b200 as cpl
@@ -104,6 +106,8 @@ def make_pair(case, mass=100.0, rich=True):
     env = {"none": None, "ground": cpl.Ground, "superquadric": cpl.Superquadric}[env_name]
     env = env() if env is not None else None
     prob = cpl.BatchedCplProblem(names, mass, env)
+    if os.environ.get("CPLB_TEST_IM_KERNEL"):  # development aid: run the whole suite with one instance-major kernel forced
+        prob.SetInstanceMajorKernel(os.environ["CPLB_TEST_IM_KERNEL"])
     configure(prob, env, names, env_name, rich, extra)
     op = OracleProblem(names, env_name, mass)
     configure(op, op if env_name != "none" else None, names, env_name, rich, extra)

@@ -26,7 +26,7 @@ def test_library_exports_every_symbol_the_header_declares():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libcplb.so does not export {name}"
     assert declared == set(_cabi.PROTOTYPES), declared ^ set(_cabi.PROTOTYPES)
-    assert _cabi.load().cplb_abi_version() == 2
+    assert _cabi.load().cplb_abi_version() == 3
 
 
 def test_product_never_imports_the_oracle():
@@ -314,6 +314,29 @@ def test_kernel_choice_validation():
         prob.SetComponentMajorKernel(7)
     prob.SetComponentMajorKernel(_cabi.KERNEL_PER_CONTACT)
     prob.SetComponentMajorKernel(_cabi.KERNEL_AUTO)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_packed_jacobian_map_and_host_unpack(case):
+    """cplb_get_packed_jacobian_map lists the x-dependent slots in slot order; cplb_unpack_jacobian (host-only) rebuilds full rows
+    from packed slices: checked here on the oracle's values, no GPU involved."""
+    prob, o, gen = make_pair(case)
+    pmap = prob.GetPackedJacobianMap()
+    mask, cval = prob.GetJacobianConstants()
+    assert np.array_equal(pmap, np.nonzero(~mask)[0]) and len(pmap) + int(mask.sum()) == prob.nnz
+    nc = o.nc
+    expect = {orc.ENV_NONE: 6 + 24 * nc, orc.ENV_GROUND: 6 + 24 * nc, orc.ENV_SUPERQUADRIC: 6 + 36 * nc}[o.env_kind]
+    assert len(pmap) == expect
+    x = gen(50)
+    jac = o.eval_batch(x, want=("jac",))["jac"]
+    assert same_bits_host(prob.UnpackJacobian(np.ascontiguousarray(jac[:, pmap])), jac)
+    with pytest.raises(ValueError):
+        prob.UnpackJacobian(jac)            # full rows are not packed slices
+
+
+def same_bits_host(a, b):
+    na, nb = np.isnan(a), np.isnan(b)
+    return bool((na == nb).all() and (a[~na] == b[~nb]).all())
 
 
 def test_header_is_valid_c99_and_usable_from_plain_c(tmp_path):

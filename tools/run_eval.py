@@ -28,9 +28,15 @@ def main():
     ap.add_argument("--sets", type=int, default=0, help="buffer sets to rotate through (0 = enough to exceed L2 8x)")
     ap.add_argument("--all", action="store_true", help="also cost + gradient")
     ap.add_argument("--ready", action="store_true", help="pass inputs_ready=True (x is not produced by the preceding kernel)")
+    ap.add_argument("--im-kernel", default="auto", choices=["auto", "warp", "cta"], help="cplb_set_instance_major_kernel")
+    ap.add_argument("--cm-kernel", default="auto", choices=["auto", "split", "whole"], help="cplb_set_component_major_kernel")
+    ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays of one rotation over the buffer sets (no Python launch path in the step)")
+    ap.add_argument("--perinst", action="store_true", help="per-instance constraint parameters (mass, wrench, mu, thresholds, ground z)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     prob, _, gen = make_pair(a.case, rich=False)
+    prob.SetInstanceMajorKernel(a.im_kernel)
+    prob.SetComponentMajorKernel(a.cm_kernel)
     x = gen(min(a.n, 1 << 16))
     if a.n > x.shape[0]:
         x = np.tile(x, ((a.n + x.shape[0] - 1) // x.shape[0], 1))[: a.n]
@@ -48,19 +54,54 @@ def main():
         for o in outs:
             o["cost"] = torch.empty(a.n, dtype=torch.float64, device="cuda")
             o["grad"] = torch.empty(shp(prob.n), dtype=torch.float64, device="cuda")
+    pi = None
+    if a.perinst:
+        nc = (prob.n - 3) // 9
+        rng = np.random.default_rng(1)
+        shp_p = (lambda L: (a.n, L)) if layout == cpl.INSTANCE_MAJOR else (lambda L: (L, a.n))
+        pi = {"mass": rng.uniform(20, 150, a.n), "wrench": rng.uniform(-50, 50, shp_p(6)), "mu": rng.uniform(0.2, 1.2, a.n),
+              "force_threshold": rng.uniform(0, 30, shp_p(nc))}
+        if a.case.startswith("ground"):
+            pi["ground_z"] = rng.uniform(-0.2, 0.4, a.n)
+        pi = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in pi.items()}
     for i in range(a.warmup):
-        prob.eval(xs[i % sets], g=True, jac=True, cost=a.all, grad=a.all, layout=layout, out=outs[i % sets])
+        prob.eval(xs[i % sets], g=True, jac=True, cost=a.all, grad=a.all, layout=layout, out=outs[i % sets], per_instance=pi)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(a.steps):
+    def step(i):
         s = (a.warmup + i) % sets
-        prob.eval(xs[s], g=True, jac=True, cost=a.all, grad=a.all, layout=layout, out=outs[s], inputs_ready=a.ready)
-    e1.record()
+        prob.eval(xs[s], g=True, jac=True, cost=a.all, grad=a.all, layout=layout, out=outs[s], inputs_ready=a.ready, per_instance=pi)
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if a.graph:
+        stream = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(sets):
+                    step(i)
+        stream.wait_stream(side)
+        graph.replay()
+        torch.cuda.synchronize()
+        reps = max(1, a.steps // sets)
+        a.steps = reps * sets
+        e0.record()
+        for _ in range(reps):
+            graph.replay()
+        e1.record()
+    else:
+        e0.record()
+        for i in range(a.steps):
+            step(i)
+        e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     alg = per + (8 * (prob.n + 1) * a.n if a.all else 0)
-    print(f"{a.case} {a.layout} N={a.n} steps={a.steps} sets={sets}: {ms*1e3:.2f} us/step, "
+    if a.graph:
+        a.case += " [graph]"
+    tag = f" im={a.im_kernel}" if a.layout == "instance" else f" cm={a.cm_kernel}"
+    print(f"{a.case} {a.layout}{tag}{' perinst' if a.perinst else ''}{' all4' if a.all else ''} N={a.n} steps={a.steps} sets={sets}: {ms*1e3:.2f} us/step, "
           f"{a.n/ms/1e3:.1f} M inst/s, {alg/ms/1e6:.0f} GB/s algorithmic ({alg/ms/1e6/6449.7*100:.1f}% of 6449.7)")
 
 
