@@ -49,6 +49,20 @@ class EvalArgs(C.Structure):
     ]
 
 
+class SolverOptions(C.Structure):
+    """cplb_solver_options"""
+    _fields_ = [("tol", C.c_double), ("mu_init", C.c_double), ("bound_push", C.c_double), ("bound_frac", C.c_double),
+                ("nlp_scaling_max_gradient", C.c_double), ("constr_viol_tol", C.c_double), ("polish_viol_tol", C.c_double),
+                ("bound_relax_factor", C.c_double), ("max_iter", C.c_int32), ("max_backtracks", C.c_int32)]
+
+
+class SolveOutputs(C.Structure):
+    """cplb_solve_outputs"""
+    _fields_ = [("x", C.c_void_p), ("status", C.c_void_p), ("iterations", C.c_void_p), ("cost", C.c_void_p), ("constr_viol", C.c_void_p),
+                ("dual_inf", C.c_void_p), ("lam", C.c_void_p), ("rounds", C.POINTER(C.c_int32)), ("evaluations", C.POINTER(C.c_int64)),
+                ("instance_evaluations", C.POINTER(C.c_int64))]
+
+
 # name -> (restype, argtypes); every symbol include/cpl_batched.h declares
 PROTOTYPES = {
     "cplb_create": (C.c_int, [C.c_int32, C.POINTER(C.c_char_p), C.c_int, C.c_double, C.c_int32, C.POINTER(C.c_void_p)]),
@@ -103,6 +117,8 @@ PROTOTYPES = {
     "cplb_eval_host": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs)]),
     "cplb_eval_host_begin": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs), C.POINTER(C.c_int32)]),
     "cplb_eval_host_wait": (C.c_int, [C.c_void_p, C.c_int32]),
+    "cplb_solver_default_options": (None, [C.POINTER(SolverOptions)]),
+    "cplb_solve_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(SolverOptions), C.POINTER(SolveOutputs), C.c_void_p]),
     "cplb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cplb_host_free": (C.c_int, [C.c_void_p]),
     "cplb_set_component_major_kernel": (C.c_int, [C.c_void_p, C.c_int32]),

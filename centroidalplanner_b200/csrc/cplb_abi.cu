@@ -19,6 +19,7 @@
 #include "cplb_kernels.h"
 #include "cplb_layout.hpp"
 #include "cplb_params.h"
+#include "cplb_solver.h"
 
 namespace {
 
@@ -104,6 +105,10 @@ struct cplb_problem {
     std::vector<HostPipe> pipes;  // pipes[0].device mirrors `device` for a single-device problem
     bool sharded = false;
     int next_ticket = 0;
+
+    // cplb_solve_device: device slabs of the native solve round (grown on demand, freed with the problem)
+    std::mutex solver_mu;
+    cplb::solver::Workspace* solver_ws = nullptr;
 
     int find(const char* name) const
     {
@@ -248,6 +253,10 @@ void cplb_destroy(cplb_problem* p)
             cudaEventDestroy(ev.first);
             cudaEventDestroy(ev.second);
         }
+    }
+    if (p->solver_ws) {
+        DeviceGuard dg(p->device >= 0 ? p->device : 0);
+        cplb::solver::workspace_free(p->solver_ws);
     }
     for (auto& pipe : p->pipes) {
         if (pipe.device < 0 || !pipe.streams_ready) continue;
@@ -1305,11 +1314,72 @@ cplb_status cplb_eval_host_wait(cplb_problem* p, int32_t ticket)
     return CPLB_OK;
 }
 
+// ---- the caller side: N lock-step solves -----------------------------------------------------------------
+
+void cplb_solver_default_options(cplb_solver_options* o)
+{
+    if (!o) return;
+    o->tol = 1e-3;  // ifopt's IpoptSolver default
+    o->mu_init = 0.1;
+    o->bound_push = 1e-2;
+    o->bound_frac = 1e-2;
+    o->nlp_scaling_max_gradient = 100.0;
+    o->constr_viol_tol = 1e-4;
+    o->polish_viol_tol = 1e-9;
+    o->bound_relax_factor = 1e-8;
+    o->max_iter = 500;
+    o->max_backtracks = 30;
+}
+
+cplb_status cplb_solve_device(cplb_problem* p, int64_t num_instances, const double* x0, const cplb_solver_options* options,
+                              const cplb_solve_outputs* out, void* cuda_stream)
+{
+    CPLB_REQUIRE(p);
+    CPLB_REQUIRE(out);
+    if (num_instances < 0) return fail(CPLB_INVALID_ARGUMENT, "num_instances is negative");
+    if (p->pipes.size() > 1) return fail(CPLB_INVALID_ARGUMENT, "cplb_solve_device needs a single-device problem (one solve batch per GPU)");
+    if (num_instances == 0) return CPLB_OK;
+    CPLB_REQUIRE(x0);
+    CPLB_REQUIRE(out->x);
+    CPLB_REQUIRE(out->status);
+    CPLB_REQUIRE(out->iterations);
+    CPLB_REQUIRE(out->cost);
+    CPLB_REQUIRE(out->constr_viol);
+    CPLB_REQUIRE(out->dual_inf);
+    cplb_solver_options o;
+    cplb_solver_default_options(&o);
+    if (options) o = *options;
+    if (!(o.tol > 0.0) || !(o.mu_init > 0.0) || o.max_iter < 0 || o.max_backtracks < 1)
+        return fail(CPLB_INVALID_ARGUMENT, "solver options: tol and mu_init must be positive, max_iter >= 0, max_backtracks >= 1");
+    cplb_status st = bind_device(p);
+    if (st != CPLB_OK) return st;
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(CPLB_CUDA_ERROR, "cudaSetDevice(%d) failed", p->device);
+    std::lock_guard<std::mutex> lk(p->solver_mu);
+    const cplb::Layout& L = p->layout;
+    std::vector<double> cl(L.m), cu(L.m);
+    cplb_get_constraint_bounds(p, cl.data(), cu.data());
+    cplb::solver::ShapeHost SH;
+    SH.build(L.n, L.m, L.nnz, L.iRow.data(), L.jCol.data(), p->x_lb.data(), p->x_ub.data(), cl.data(), cu.data(), o.bound_relax_factor);
+    const cplb::solver::Options O{o.tol, o.mu_init, o.bound_push, o.bound_frac, o.nlp_scaling_max_gradient, o.constr_viol_tol, o.polish_viol_tol,
+                                  o.bound_relax_factor, o.max_iter, o.max_backtracks};
+    cplb::solver::SolveStats stats;
+    const long long launches_per_round = 8;
+    cudaError_t e = cplb::solver::solve_device(p->P, p->im_kernel, SH, O, num_instances, x0, out->x, out->status, out->iterations, out->cost,
+                                               out->constr_viol, out->dual_inf, out->lam, &stats, &p->solver_ws, static_cast<cudaStream_t>(cuda_stream));
+    if (e != cudaSuccess) return cuda_fail(e, "cplb_solve_device");
+    p->launches.fetch_add(stats.evaluations + launches_per_round / 2 * stats.rounds + 3, std::memory_order_relaxed);
+    if (out->rounds) *out->rounds = stats.rounds;
+    if (out->evaluations) *out->evaluations = stats.evaluations;
+    if (out->instance_evaluations) *out->instance_evaluations = stats.instance_evaluations;
+    return CPLB_OK;
+}
+
 cplb_status cplb_host_alloc(size_t bytes, void** out)
 {
     CPLB_REQUIRE(out);
     *out = nullptr;
-    CPLB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    CPLB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));  // pinned for every device of the process (sharded problems)
     return CPLB_OK;
 }
 cplb_status cplb_host_free(void* ptr)

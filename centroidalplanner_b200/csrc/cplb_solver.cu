@@ -1,0 +1,269 @@
+// cplb_solver.cu -- the native lock-step solve round on the GPU: cplb_solve_device of include/cpl_batched.h.
+//
+// N instances of one problem are solved together by the interior-point scheme of cplb_solver_core.hpp.  A round is a fixed
+// sequence of eight launches -- four batched evaluations of the hot path (the same kernels cplb_eval_device launches) and
+// four solver kernels that run ONE CTA PER INSTANCE with the instance's KKT system in shared memory:
+//
+//   round_begin   kappa_sigma safeguard, convergence test, barrier update, the nf + 1 forward-difference points
+//   [eval]        gradient + Jacobian at N (nf + 1) points
+//   kkt           Lagrangian Hessian from the differences, assembly of the (n + m)^2 KKT matrix, pivoted LU and solve inside an
+//                 inertia-free regularisation loop, feasibility-polish step, multiplier steps, fraction-to-the-boundary
+//                 step lengths, merit-function set-up, 16 line-search candidates
+//   [eval]        constraint values + cost at N x 16 candidates
+//   ls_first      merit test of the full step; where it fails, second-order correction with the stored factors
+//   [eval]        constraint values + cost at the corrected points
+//   ls_select     first acceptable point in the order of a sequential backtracking search, iterate and multiplier update
+//   [eval]        everything at the new iterate
+//
+// The host only counts the instances still running (one 4-byte read per round).  Nothing else leaves the device: what the
+// previous driver (centroidalplanner_b200/lockstep_solver.py: ~1,500 small torch launches and cuBLAS' batched LU per round) did
+// from Python happens inside these kernels.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "cplb_kernels.h"
+#include "cplb_solver.h"
+#include "cplb_solver_core.hpp"
+
+namespace cplb {
+namespace solver {
+
+struct DeviceTeam {
+    int rank, size;
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
+constexpr int kThreads = 128;
+
+struct KernelArgs {
+    Shape S;
+    State T;
+    Options O;
+};
+
+__global__ void __launch_bounds__(kThreads) k_init_x(const __grid_constant__ KernelArgs A, const double* x0)
+{
+    DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
+    phase_init_x(team, A.S, A.T, A.O, (long long)blockIdx.x, x0);
+}
+
+__global__ void __launch_bounds__(kThreads) k_init_scale(const __grid_constant__ KernelArgs A)
+{
+    DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
+    phase_init_scale(team, A.S, A.T, A.O, (long long)blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kThreads) k_round_begin(const __grid_constant__ KernelArgs A, int first, int last, int* n_active)
+{
+    extern __shared__ __align__(16) double smem[];
+    DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
+    Scratch q;
+    q.carve(smem, A.S.n, A.S.m, A.S.nnz);
+    phase_round_begin(team, A.S, A.T, A.O, (long long)blockIdx.x, q, first, last, n_active);
+}
+
+__global__ void __launch_bounds__(kThreads) k_kkt(const __grid_constant__ KernelArgs A)
+{
+    extern __shared__ __align__(16) double smem[];
+    DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
+    Scratch q;
+    q.carve(smem, A.S.n, A.S.m, A.S.nnz);
+    phase_kkt(team, A.S, A.T, A.O, (long long)blockIdx.x, q);
+}
+
+__global__ void __launch_bounds__(kThreads) k_ls_first(const __grid_constant__ KernelArgs A)
+{
+    extern __shared__ __align__(16) double smem[];
+    DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
+    Scratch q;
+    q.carve(smem, A.S.n, A.S.m, A.S.nnz);
+    phase_ls_first(team, A.S, A.T, A.O, (long long)blockIdx.x, q);
+}
+
+__global__ void __launch_bounds__(kThreads) k_ls_select(const __grid_constant__ KernelArgs A)
+{
+    extern __shared__ __align__(16) double smem[];
+    DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
+    Scratch q;
+    q.carve(smem, A.S.n, A.S.m, A.S.nnz);
+    phase_ls_select(team, A.S, A.T, A.O, (long long)blockIdx.x, q);
+}
+
+__global__ void __launch_bounds__(kThreads) k_finish(const __grid_constant__ KernelArgs A, double* x_out, double* lam_out)
+{
+    DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
+    phase_finish(team, A.S, A.T, (long long)blockIdx.x, x_out, lam_out);
+}
+
+#define SOLVER_CUDA(call)                 \
+    do {                                  \
+        cudaError_t e__ = (call);         \
+        if (e__ != cudaSuccess) return e__; \
+    } while (0)
+
+// device copies of the problem-level arrays + the per-instance state slab; owned by the problem handle, grown on demand
+struct Workspace {
+    void* shape_slab = nullptr;
+    void* state_slab = nullptr;
+    size_t state_bytes = 0, shape_bytes = 0;
+    int* n_active = nullptr;
+    int* n_active_host = nullptr;
+};
+
+void workspace_free(Workspace* w)
+{
+    if (!w) return;
+    if (w->shape_slab) cudaFree(w->shape_slab);
+    if (w->state_slab) cudaFree(w->state_slab);
+    if (w->n_active) cudaFree(w->n_active);
+    if (w->n_active_host) cudaFreeHost(w->n_active_host);
+    delete w;
+}
+
+struct DeviceEngine {
+    const CplbParams& P;
+    int im_kernel;
+    KernelArgs A;
+    long long N;
+    cudaStream_t st;
+    Workspace* W;
+    const double* x0;
+    double *x_out, *lam_out;
+    size_t smem;
+    cudaError_t err = cudaSuccess;
+
+    void check(cudaError_t e)
+    {
+        if (err == cudaSuccess && e != cudaSuccess) err = e;
+    }
+    void eval(const double* x, double* g, double* jac, double* cost, double* grad, long long count)
+    {
+        if (err != cudaSuccess) return;
+        unsigned flags = (g ? CPLB_WANT_G : 0u) | (jac ? CPLB_WANT_J : 0u) | (cost ? CPLB_WANT_COST : 0u) | (grad ? CPLB_WANT_GRAD : 0u);
+        CplbIo io{x, g, jac, cost, grad, count, count};
+        check(launch_instance_major(P, io, flags, nullptr, im_kernel, st));
+    }
+    template <class K, class... Args>
+    void run(K kern, size_t shared, Args... args)
+    {
+        if (err != cudaSuccess) return;
+        kern<<<(unsigned)N, kThreads, shared, st>>>(A, args...);
+        check(cudaGetLastError());
+    }
+    void init_x() { run(k_init_x, 0, x0); }
+    void init_scale() { run(k_init_scale, 0); }
+    int round_begin(bool first, bool last)
+    {
+        if (err != cudaSuccess) return 0;
+        check(cudaMemsetAsync(W->n_active, 0, sizeof(int), st));
+        run(k_round_begin, smem, (int)first, (int)last, W->n_active);
+        check(cudaMemcpyAsync(W->n_active_host, W->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        check(cudaStreamSynchronize(st));
+        return err == cudaSuccess ? *W->n_active_host : 0;
+    }
+    void kkt() { run(k_kkt, smem); }
+    void ls_first() { run(k_ls_first, smem); }
+    void ls_select() { run(k_ls_select, smem); }
+    void finish()
+    {
+        run(k_finish, 0, x_out, lam_out);
+        check(cudaStreamSynchronize(st));
+    }
+    void eval_full() { eval(A.T.x, A.T.c, A.T.jv, A.T.f, A.T.df, N); }
+    void eval_fd() { eval(A.T.x_fd, nullptr, A.T.jac_fd, nullptr, A.T.grad_fd, N * (A.S.nf + 1)); }
+    void eval_ls() { eval(A.T.x_ls, A.T.g_ls, nullptr, A.T.cost_ls, nullptr, N * kCandidates); }
+    void eval_soc() { eval(A.T.x_soc, A.T.g_soc, nullptr, A.T.cost_soc, nullptr, N); }
+};
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+cudaError_t solve_device(const CplbParams& P, int im_kernel, const ShapeHost& SH, const Options& O, long long N, const double* x0, double* x_out,
+                         int32_t* status, int32_t* iterations, double* cost, double* viol, double* dual, double* lam_out, SolveStats* stats,
+                         Workspace** wsp, cudaStream_t st)
+{
+    if (!*wsp) *wsp = new Workspace();
+    Workspace* W = *wsp;
+    if (!W->n_active) {
+        SOLVER_CUDA(cudaMalloc(&W->n_active, sizeof(int)));
+        SOLVER_CUDA(cudaHostAlloc((void**)&W->n_active_host, sizeof(int), cudaHostAllocDefault));
+    }
+    KernelArgs A{};
+    A.O = O;
+    Shape& S = A.S;
+    S.n = SH.n;
+    S.m = SH.m;
+    S.nnz = SH.nnz;
+    S.nf = SH.nf;
+    S.nk = SH.n + SH.m;
+    // ---- problem-level arrays: one slab, uploaded per call (a few KB; setters may have changed the bounds) ----
+    struct Up { const void* src; size_t bytes; const void** dst; };
+    std::vector<Up> ups;
+    auto up = [&](const auto& vec, const auto*& dst) {
+        ups.push_back({vec.data(), vec.size() * sizeof(vec[0]), reinterpret_cast<const void**>(&dst)});
+    };
+    up(SH.iRow, S.iRow); up(SH.jCol, S.jCol); up(SH.col_ptr, S.col_ptr); up(SH.col_slot, S.col_slot); up(SH.free_idx, S.free_idx);
+    up(SH.xl, S.xl); up(SH.xu, S.xu); up(SH.xlo_orig, S.xlo_orig); up(SH.xhi_orig, S.xhi_orig);
+    up(SH.cl, S.cl); up(SH.cu, S.cu); up(SH.cl_r, S.cl_r); up(SH.cu_r, S.cu_r);
+    up(SH.fixed, S.fixed); up(SH.x_lo, S.x_lo); up(SH.x_hi, S.x_hi); up(SH.s_lo, S.s_lo); up(SH.s_hi, S.s_hi); up(SH.is_eq, S.is_eq);
+    size_t shape_bytes = 0;
+    for (auto& u : ups) shape_bytes += align_up(u.bytes ? u.bytes : 1);
+    if (shape_bytes > W->shape_bytes) {
+        if (W->shape_slab) SOLVER_CUDA(cudaFree(W->shape_slab));
+        W->shape_slab = nullptr;
+        W->shape_bytes = 0;
+        SOLVER_CUDA(cudaMalloc(&W->shape_slab, shape_bytes));
+        W->shape_bytes = shape_bytes;
+    }
+    {
+        std::vector<unsigned char> host(shape_bytes, 0);
+        size_t off = 0;
+        for (auto& u : ups) {
+            if (u.bytes) std::memcpy(host.data() + off, u.src, u.bytes);
+            *u.dst = static_cast<unsigned char*>(W->shape_slab) + off;
+            off += align_up(u.bytes ? u.bytes : 1);
+        }
+        SOLVER_CUDA(cudaMemcpyAsync(W->shape_slab, host.data(), shape_bytes, cudaMemcpyHostToDevice, st));
+        SOLVER_CUDA(cudaStreamSynchronize(st));  // `host` goes out of scope
+    }
+    // ---- per-instance state: one slab ----
+    std::vector<StateField> fields = state_fields(A.T, SH);
+    size_t state_bytes = 0;
+    for (auto& f : fields) state_bytes += align_up(f.per_instance * (size_t)N * (f.is_int ? sizeof(int32_t) : sizeof(double)));
+    if (state_bytes > W->state_bytes) {
+        if (W->state_slab) SOLVER_CUDA(cudaFree(W->state_slab));
+        W->state_slab = nullptr;
+        W->state_bytes = 0;
+        SOLVER_CUDA(cudaMalloc(&W->state_slab, state_bytes));
+        W->state_bytes = state_bytes;
+    }
+    {
+        size_t off = 0;
+        for (auto& f : fields) {
+            *f.ptr = static_cast<unsigned char*>(W->state_slab) + off;
+            off += align_up(f.per_instance * (size_t)N * (f.is_int ? sizeof(int32_t) : sizeof(double)));
+        }
+    }
+    // the caller's result arrays replace the internal ones where they exist
+    A.T.status = status;
+    A.T.iters = iterations;
+    A.T.out_cost = cost;
+    A.T.out_viol = viol;
+    A.T.out_dual = dual;
+
+    Scratch probe;
+    const size_t smem = probe.carve(nullptr, S.n, S.m, S.nnz) * sizeof(double);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    for (const void* k : {(const void*)k_round_begin, (const void*)k_kkt, (const void*)k_ls_first, (const void*)k_ls_select})
+        SOLVER_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+
+    DeviceEngine E{P, im_kernel, A, N, st, W, x0, x_out, lam_out, smem};
+    const SolveStats s = solve_loop(E, O, N, SH.nf);
+    if (stats) *stats = s;
+    return E.err;
+}
+
+}  // namespace solver
+}  // namespace cplb

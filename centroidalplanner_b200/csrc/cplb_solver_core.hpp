@@ -1,0 +1,1133 @@
+// cplb_solver_core.hpp -- per-instance arithmetic of the native batched solve round (the caller of the
+// hot path, cpl::CentroidalPlanner::Solve, src/CentroidalPlanner.cpp:22-34, for N instances in lock step).
+//
+// The algorithm is the primal-dual interior-point scheme of centroidalplanner_b200/lockstep_solver.py (IPOPT's method,
+// Waechter & Biegler 2006: slack reformulation, log barrier, fraction to the boundary, monotone barrier update, gradient-based
+// scaling, bound push / relaxation, kappa_sigma safeguard, second-order correction, l1 merit backtracking, Levenberg-Marquardt
+// damping, feasibility polish; Lagrangian Hessian by forward differences of the batched gradient + Jacobian), written so that
+// one THREAD TEAM works on one instance: a CTA on the GPU (cplb_solver.cu), a single thread on the host (the CPU replay of
+// tests/native/solver_host_check.cpp, which puts the oracle behind the same code).  Everything an instance needs between two
+// batched evaluations happens inside one team call, in shared memory: no per-operation kernel launches, no host round trips.
+//
+// Pattern: parallel over outputs, sequential within an output (sizes are <= 69), `team.sync()` between dependent phases.
+#ifndef CPLB_SOLVER_CORE_HPP
+#define CPLB_SOLVER_CORE_HPP
+
+#include <math.h>
+#include <stdint.h>
+
+#include <vector>
+
+#if defined(__CUDACC__)
+#define CPLB_HD __host__ __device__ __forceinline__
+#else
+#define CPLB_HD inline
+#endif
+
+namespace cplb {
+namespace solver {
+
+constexpr int kStatusRunning = -1, kSuccess = 0, kMaxIter = 1, kInvalidNumber = 2;
+constexpr int kCandidates = 30;  // line-search candidates alpha0 * 2^-k evaluated per round in one widened launch
+constexpr int kMaxReg = 14;      // inertia-free regularisation attempts
+constexpr double kInfBound = 1.0e19;
+
+struct Options {
+    double tol, mu_init, bound_push, bound_frac, max_gradient, constr_viol_tol, polish_viol_tol, bound_relax;
+    int max_iter, max_backtracks;
+};
+
+// Problem-level data shared by all instances (variable / constraint bounds and the Jacobian structure are the problem's).
+struct Shape {
+    int n, m, nnz, nf, nk;          // nk = n + m
+    const int32_t* iRow;            // [nnz]
+    const int32_t* jCol;            // [nnz]
+    const int32_t* col_ptr;         // [n + 1]  slots of column j: col_slot[col_ptr[j] .. col_ptr[j+1]), ascending
+    const int32_t* col_slot;        // [nnz]
+    const int32_t* free_idx;        // [nf]     non-fixed variables
+    const double *xl, *xu;          // [n] relaxed variable bounds
+    const double *xlo_orig, *xhi_orig;
+    const double *cl, *cu;          // [m] original constraint bounds
+    const double *cl_r, *cu_r;      // [m] relaxed
+    const uint8_t *fixed, *x_lo, *x_hi;  // [n]
+    const uint8_t *s_lo, *s_hi, *is_eq;  // [m]
+};
+
+// Per-instance state, instance-major arrays (element e of instance i at base[i * len + e]).
+struct State {
+    double *x, *s, *lam, *vxl, *vxu, *vsl, *vsu;              // iterate and multipliers
+    double *mu, *tau, *delta_last, *delta_lm;                  // [N]
+    int32_t *status, *iters, *polish, *active;                 // [N]
+    double *f, *df, *c, *jv;                                   // raw evaluator outputs at x: cost [N], grad [N n], g [N m], jac [N nnz]
+    double *dc, *dobj, *sl, *su, *cu_s, *cl_s;                 // scaling and scaled slack bounds
+    // step of the current round
+    double *dx, *ds, *dlam, *dvxl, *dvxu, *dvsl, *dvsu, *h, *r_x, *r_s, *D;
+    double *a_p, *a_d, *merit0, *Dm, *nu, *R0, *quad;
+    int32_t *tiny, *pol, *okK, *accepted0;
+    double *lu;                                                // [N nk nk]
+    int32_t* piv;                                              // [N nk]
+    // widened evaluation buffers
+    double *x_fd, *grad_fd, *jac_fd;                           // [N (nf+1) n], [N (nf+1) n], [N (nf+1) nnz]
+    double *x_ls, *g_ls, *cost_ls;                             // [N KC n], [N KC m], [N KC]
+    double *x_soc, *g_soc, *cost_soc, *dx_soc, *ds_soc, *dlam_soc, *a_soc;
+    int32_t* soc_valid;
+    // results
+    double *out_cost, *out_viol, *out_dual;
+};
+
+struct HostTeam {
+    int rank = 0, size = 1;
+    void sync() const {}
+};
+
+CPLB_HD bool finite_d(double v) { return v == v && v - v == 0.0; }
+CPLB_HD double dmax(double a, double b) { return a > b ? a : b; }   // NaN-free callers only (torch.maximum propagates NaN: handled where it matters)
+CPLB_HD double dmin(double a, double b) { return a < b ? a : b; }
+CPLB_HD double dabs(double a) { return a < 0 ? -a : a; }
+// torch.maximum / amax semantics: NaN wins
+CPLB_HD double nanmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+CPLB_HD double nanmin(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+CPLB_HD double clamp_min(double v, double lo) { return (v != v) ? v : (v < lo ? lo : v); }
+CPLB_HD double clamp_max(double v, double hi) { return (v != v) ? v : (v > hi ? hi : v); }
+
+// IPOPT's starting-point projection (Waechter & Biegler 2006, section 3.6)
+CPLB_HD double push_inside(double v, double lo, double hi, bool has_lo, bool has_hi, double k1, double k2)
+{
+    const double span = (has_lo && has_hi) ? hi - lo : INFINITY;
+    const double pl = dmin(k1 * dmax(dabs(lo), 1.0), k2 * span);
+    const double pu = dmin(k1 * dmax(dabs(hi), 1.0), k2 * span);
+    if (has_lo) v = nanmax(v, lo + pl);
+    if (has_hi) v = nanmin(v, hi - pu);
+    return v;
+}
+
+// ---- dense LU with partial pivoting of an nk x nk matrix held in team-shared memory (row-major, leading dimension ld) -------
+// piv[k] = row swapped with row k at step k (LAPACK convention).  Zero pivots are not special-cased: the divisions then
+// produce inf / NaN, the solution is non-finite and the caller's regularisation loop takes over (as with torch's lu_factor).
+template <class Team>
+CPLB_HD void lu_factor(const Team& team, double* A, int ld, int nk, int32_t* piv)
+{
+    for (int k = 0; k < nk; k++) {
+        if (team.rank == 0) {
+            int p = k;
+            double best = dabs(A[k * ld + k]);
+            for (int i = k + 1; i < nk; i++) {
+                const double v = dabs(A[i * ld + k]);
+                if (v > best) {  // NaN never wins: a NaN column keeps p = k and poisons the row
+                    best = v;
+                    p = i;
+                }
+            }
+            piv[k] = p;
+        }
+        team.sync();
+        const int p = piv[k];
+        if (p != k)
+            for (int j = team.rank; j < nk; j += team.size) {
+                const double t = A[k * ld + j];
+                A[k * ld + j] = A[p * ld + j];
+                A[p * ld + j] = t;
+            }
+        team.sync();
+        const double pivot = A[k * ld + k];
+        for (int i = k + 1 + team.rank; i < nk; i += team.size) A[i * ld + k] = A[i * ld + k] / pivot;
+        team.sync();
+        // trailing update on a 2-D thread grid (16 columns wide): no integer division per element
+        const int ntx = team.size >= 16 ? 16 : team.size, nty = team.size / ntx;
+        const int tx = team.rank % ntx, ty = team.rank / ntx;
+        if (ty < nty)
+            for (int i = k + 1 + ty; i < nk; i += nty) {
+                const double lik = A[i * ld + k];
+                for (int j = k + 1 + tx; j < nk; j += ntx) A[i * ld + j] = A[i * ld + j] - lik * A[k * ld + j];
+            }
+        team.sync();
+    }
+}
+
+// solves A y = b in place (b -> y) with the factors of lu_factor
+template <class Team>
+CPLB_HD void lu_solve(const Team& team, const double* A, int ld, int nk, const int32_t* piv, double* b)
+{
+    if (team.rank == 0)
+        for (int k = 0; k < nk; k++) {
+            const int p = piv[k];
+            if (p != k) {
+                const double t = b[k];
+                b[k] = b[p];
+                b[p] = t;
+            }
+        }
+    team.sync();
+    for (int k = 0; k < nk; k++) {  // L y = P b (unit lower triangle)
+        const double yk = b[k];
+        for (int i = k + 1 + team.rank; i < nk; i += team.size) b[i] = b[i] - A[i * ld + k] * yk;
+        team.sync();
+    }
+    for (int k = nk - 1; k >= 0; k--) {  // U x = y
+        if (team.rank == 0) b[k] = b[k] / A[k * ld + k];
+        team.sync();
+        const double xk = b[k];
+        for (int i = team.rank; i < k; i += team.size) b[i] = b[i] - A[i * ld + k] * xk;
+        team.sync();
+    }
+}
+
+// shared scratch of one team, carved out of one block of doubles (shared memory on the GPU)
+struct Scratch {
+    double *K, *rhs, *sol, *Jd, *H0, *gxl, *gxu, *gsl, *gsu, *sigx, *sigs, *w, *glb, *tmp, *red;
+    int32_t* piv;
+    int ld;
+    // returns the number of doubles used; base may be nullptr (size query)
+    CPLB_HD size_t carve(double* base, int n, int m, int nnz)
+    {
+        const int nk = n + m;
+        ld = nk | 1;
+        size_t o = 0;
+        auto take = [&](size_t count) {
+            double* p = base ? base + o : nullptr;
+            o += count;
+            return p;
+        };
+        K = take((size_t)nk * ld);
+        rhs = take(nk);
+        sol = take(nk);
+        Jd = take((size_t)m * n);
+        H0 = take((size_t)n * n);
+        gxl = take(n);
+        gxu = take(n);
+        sigx = take(n);
+        glb = take(n);
+        gsl = take(m);
+        gsu = take(m);
+        sigs = take(m);
+        w = take(nnz);
+        tmp = take(2 * (size_t)nk);
+        red = take(64);
+        piv = reinterpret_cast<int32_t*>(take(((size_t)nk + 1) / 2));
+        return o;
+    }
+};
+
+// gaps to the bounds at (x, s) (1.0 where there is no bound)
+template <class Team>
+CPLB_HD void compute_gaps(const Team& team, const Shape& S, const double* x, const double* s, const double* sl, const double* su, Scratch& q)
+{
+    for (int j = team.rank; j < S.n; j += team.size) {
+        q.gxl[j] = S.x_lo[j] ? x[j] - S.xl[j] : 1.0;
+        q.gxu[j] = S.x_hi[j] ? S.xu[j] - x[j] : 1.0;
+    }
+    for (int r = team.rank; r < S.m; r += team.size) {
+        q.gsl[r] = S.s_lo[r] ? s[r] - sl[r] : 1.0;
+        q.gsu[r] = S.s_hi[r] ? su[r] - s[r] : 1.0;
+    }
+}
+
+// dense scaled Jacobian with the fixed columns zeroed: Jd[r][j] = dc[r] * jac[slot]
+template <class Team>
+CPLB_HD void dense_jacobian(const Team& team, const Shape& S, const double* jv, const double* dc, double* Jd)
+{
+    for (int e = team.rank; e < S.m * S.n; e += team.size) Jd[e] = 0.0;
+    team.sync();
+    for (int sl_ = team.rank; sl_ < S.nnz; sl_ += team.size) {
+        const int r = S.iRow[sl_], j = S.jCol[sl_];
+        if (!S.fixed[j]) Jd[r * S.n + j] = dc[r] * jv[sl_];
+    }
+}
+
+
+// ---- per-instance pointers ---------------------------------------------------------------------------------------------------
+struct Inst {
+    const Shape& S;
+    const State& T;
+    long long i;
+    CPLB_HD double* vn(double* base) const { return base + i * S.n; }
+    CPLB_HD double* vm(double* base) const { return base + i * S.m; }
+};
+
+// sequential dot-style helpers (one thread); sizes are tiny
+CPLB_HD double scaled_df(const Inst& I, int j) { return I.S.fixed[j] ? 0.0 : I.T.dobj[I.i] * I.T.df[I.i * I.S.n + j]; }
+
+// (J^T lam)_j with the scaled Jacobian; fixed columns contribute nothing
+CPLB_HD double jt_lam(const Inst& I, int j, const double* lam)
+{
+    const Shape& S = I.S;
+    if (S.fixed[j]) return 0.0;
+    const double* jv = I.T.jv + I.i * S.nnz;
+    const double* dc = I.T.dc + I.i * S.m;
+    double acc = 0.0;
+    for (int e = S.col_ptr[j]; e < S.col_ptr[j + 1]; e++) {
+        const int sl = S.col_slot[e], r = S.iRow[sl];
+        acc += (dc[r] * jv[sl]) * lam[r];
+    }
+    return acc;
+}
+
+struct Residuals {
+    double dual, prim, sd;
+};
+
+// Scaled optimality error of Waechter & Biegler eq. (5) without its mu-dependent part (kkt_residuals of the Python driver);
+// needs q.gxl .. q.gsu.  One thread.
+CPLB_HD Residuals kkt_residuals(const Inst& I, const Scratch& q)
+{
+    const Shape& S = I.S;
+    const State& T = I.T;
+    const double *lam = I.vm(T.lam), *vxl = I.vn(T.vxl), *vxu = I.vn(T.vxu), *vsl = I.vm(T.vsl), *vsu = I.vm(T.vsu);
+    const double *c = I.vm(T.c), *s = I.vm(T.s), *dc = I.vm(T.dc);
+    double rmax = 0.0, sum = 0.0, prim = 0.0;
+    for (int j = 0; j < S.n; j++) {
+        const double rx = S.fixed[j] ? 0.0 : (scaled_df(I, j) + jt_lam(I, j, lam) - vxl[j] + vxu[j]);
+        rmax = nanmax(rmax, dabs(rx));
+        sum += vxl[j] + vxu[j];
+    }
+    for (int r = 0; r < S.m; r++) {
+        const double rs = S.is_eq[r] ? 0.0 : (-lam[r] - vsl[r] + vsu[r]);
+        rmax = nanmax(rmax, dabs(rs));
+        sum += dabs(lam[r]) + vsl[r] + vsu[r];
+        prim = nanmax(prim, dabs(dc[r] * c[r] - s[r]));
+    }
+    Residuals R;
+    R.sd = clamp_min(sum / (double)(S.m + 2 * S.n + 2 * S.m), 100.0) / 100.0;
+    R.dual = rmax / R.sd;
+    R.prim = prim;
+    return R;
+}
+
+// max |(gap * multiplier - mu)| over the bounded components, / sd
+CPLB_HD double complementarity(const Inst& I, const Scratch& q, double sd, double mu)
+{
+    const Shape& S = I.S;
+    const State& T = I.T;
+    const double *vxl = I.vn(T.vxl), *vxu = I.vn(T.vxu), *vsl = I.vm(T.vsl), *vsu = I.vm(T.vsu);
+    double e = 0.0;
+    for (int j = 0; j < S.n; j++) {
+        if (S.x_lo[j]) e = nanmax(e, dabs(q.gxl[j] * vxl[j] - mu));
+        if (S.x_hi[j]) e = nanmax(e, dabs(q.gxu[j] * vxu[j] - mu));
+    }
+    for (int r = 0; r < S.m; r++) {
+        if (S.s_lo[r]) e = nanmax(e, dabs(q.gsl[r] * vsl[r] - mu));
+        if (S.s_hi[r]) e = nanmax(e, dabs(q.gsu[r] * vsu[r] - mu));
+    }
+    return e / sd;
+}
+
+// max unscaled violation of the (relaxed) row bounds
+CPLB_HD double row_violation(const Inst& I)
+{
+    const Shape& S = I.S;
+    const State& T = I.T;
+    const double *c = I.vm(T.c), *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su);
+    double v = 0.0;
+    for (int r = 0; r < S.m; r++) {
+        const double cs = dc[r] * c[r];
+        v = nanmax(v, (clamp_min(sl[r] - cs, 0.0) + clamp_min(cs - su[r], 0.0)) / dc[r]);
+    }
+    return v;
+}
+
+// ---- phase 0a: project the starting point (before the first evaluation) ------------------------------------------------------
+template <class Team>
+CPLB_HD void phase_init_x(const Team& team, const Shape& S, const State& T, const Options& O, long long i, const double* x0)
+{
+    double* x = T.x + i * S.n;
+    for (int j = team.rank; j < S.n; j += team.size) {
+        double v = S.fixed[j] ? S.xl[j] : x0[i * S.n + j];
+        x[j] = push_inside(v, S.xl[j], S.xu[j], S.x_lo[j], S.x_hi[j], O.bound_push, O.bound_frac);
+    }
+}
+
+// ---- phase 0b: scaling, slacks, multipliers (after the first evaluation at x) -------------------------------------------------
+template <class Team>
+CPLB_HD void phase_init_scale(const Team& team, const Shape& S, const State& T, const Options& O, long long i)
+{
+    Inst I{S, T, i};
+    const double *df = I.vn(T.df), *c = I.vm(T.c), *jv = T.jv + i * S.nnz;
+    double *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su), *s = I.vm(T.s);
+    // gradient-based scaling at the starting point (nlp_scaling_method = gradient-based, nlp_scaling_max_gradient)
+    for (int r = team.rank; r < S.m; r += team.size) dc[r] = 0.0;  // row maxima first
+    team.sync();
+    if (team.rank == 0) {
+        bool bad = !finite_d(T.f[i]);
+        double gmax = 0.0;
+        for (int j = 0; j < S.n; j++) {
+            if (S.fixed[j]) continue;
+            if (!finite_d(df[j])) bad = true;
+            else gmax = dmax(gmax, dabs(df[j]));
+        }
+        for (int sl_ = 0; sl_ < S.nnz; sl_++) {
+            if (S.fixed[S.jCol[sl_]]) continue;
+            const double v = jv[sl_];
+            if (!finite_d(v)) bad = true;
+            else dc[S.iRow[sl_]] = dmax(dc[S.iRow[sl_]], dabs(v));
+        }
+        for (int r = 0; r < S.m; r++) {
+            if (!finite_d(c[r])) bad = true;
+            dc[r] = dmin(O.max_gradient / dmax(dc[r], 1e-300), 1.0);
+        }
+        T.dobj[i] = dmin(O.max_gradient / dmax(gmax, 1e-300), 1.0);
+        T.status[i] = bad ? kInvalidNumber : kStatusRunning;
+        T.iters[i] = 0;
+        T.polish[i] = 0;
+        T.active[i] = bad ? 0 : 1;
+        T.mu[i] = O.mu_init;
+        T.tau[i] = 0.99;
+        T.delta_last[i] = 0.0;
+        T.delta_lm[i] = 0.0;
+    }
+    team.sync();
+    for (int r = team.rank; r < S.m; r += team.size) {
+        sl[r] = dc[r] * S.cl_r[r];
+        su[r] = dc[r] * S.cu_r[r];
+        I.vm(T.cu_s)[r] = dc[r] * S.cu[r];
+        I.vm(T.cl_s)[r] = dc[r] * S.cl[r];
+        const double cs = dc[r] * c[r];
+        s[r] = S.is_eq[r] ? sl[r] : push_inside(cs, sl[r], su[r], S.s_lo[r], S.s_hi[r], O.bound_push, O.bound_frac);
+        I.vm(T.lam)[r] = 0.0;
+        I.vm(T.vsl)[r] = S.s_lo[r] ? 1.0 : 0.0;
+        I.vm(T.vsu)[r] = S.s_hi[r] ? 1.0 : 0.0;
+    }
+    for (int j = team.rank; j < S.n; j += team.size) {
+        I.vn(T.vxl)[j] = S.x_lo[j] ? 1.0 : 0.0;
+        I.vn(T.vxu)[j] = S.x_hi[j] ? 1.0 : 0.0;
+    }
+}
+
+// ---- phase 1: start of a round -------------------------------------------------------------------------------------------------
+// (after the evaluation at the new x) kappa_sigma safeguard of the bound multipliers, convergence test, barrier update, and the
+// forward-difference points of the Hessian.  Returns through T.active[i]; *n_active counts the instances still running.
+template <class Team>
+CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T, const Options& O, long long i, Scratch& q, int first_round,
+                               int last_round, int* n_active)
+{
+    Inst I{S, T, i};
+    double *x = I.vn(T.x), *s = I.vm(T.s);
+    compute_gaps(team, S, x, s, I.vm(T.sl), I.vm(T.su), q);
+    team.sync();
+    const bool was_active = T.status[i] < 0;
+    if (!first_round && T.active[i]) {
+        // kappa_sigma safeguard (Waechter & Biegler eq. 16) with the gaps at the new point
+        const double mu = T.mu[i], ks = 1e10;
+        for (int j = team.rank; j < S.n; j += team.size) {
+            double* vxl = I.vn(T.vxl);
+            double* vxu = I.vn(T.vxu);
+            vxl[j] = S.x_lo[j] ? nanmin(nanmax(vxl[j], mu / (ks * q.gxl[j])), ks * mu / q.gxl[j]) : 0.0;
+            vxu[j] = S.x_hi[j] ? nanmin(nanmax(vxu[j], mu / (ks * q.gxu[j])), ks * mu / q.gxu[j]) : 0.0;
+        }
+        for (int r = team.rank; r < S.m; r += team.size) {
+            double* vsl = I.vm(T.vsl);
+            double* vsu = I.vm(T.vsu);
+            vsl[r] = S.s_lo[r] ? nanmin(nanmax(vsl[r], mu / (ks * q.gsl[r])), ks * mu / q.gsl[r]) : 0.0;
+            vsu[r] = S.s_hi[r] ? nanmin(nanmax(vsu[r], mu / (ks * q.gsu[r])), ks * mu / q.gsu[r]) : 0.0;
+        }
+    }
+    team.sync();
+    if (team.rank == 0) {
+        int active = 0;
+        if (was_active) {
+            const Residuals R = kkt_residuals(I, q);
+            const double comp0 = complementarity(I, q, R.sd, 0.0);
+            const double E0 = nanmax(nanmax(R.dual, R.prim), comp0);
+            const double vmax = row_violation(I);
+            // IPOPT's test (scaled error <= tol, unscaled violation <= constr_viol_tol) switches the instance to the feasibility
+            // polish; it is done when the constraints hold to polish_viol_tol as well
+            if (E0 <= O.tol && vmax <= O.constr_viol_tol) T.polish[i] = 1;
+            if (T.polish[i] && vmax <= O.polish_viol_tol) T.status[i] = kSuccess;
+            else if (!finite_d(E0)) T.status[i] = kInvalidNumber;
+            T.out_dual[i] = R.dual;
+            T.out_viol[i] = vmax;
+            active = T.status[i] < 0;
+            if (active && last_round) {
+                T.status[i] = kMaxIter;
+                active = 0;
+            }
+            if (active) {
+                T.iters[i] += 1;
+                // monotone barrier update (Waechter & Biegler eq. 7)
+                double mu = T.mu[i];
+                const double dp0 = nanmax(R.dual, R.prim);
+                for (int rep = 0; rep < 4; rep++) {
+                    const double Emu = nanmax(dp0, complementarity(I, q, R.sd, mu));
+                    if (Emu <= 10.0 * mu && mu > O.tol / 10.0) mu = dmax(dmin(0.2 * mu, pow(mu, 1.5)), O.tol / 10.0);
+                }
+                T.mu[i] = mu;
+                T.tau[i] = dmax(1.0 - mu, 0.99);
+            }
+        }
+        T.active[i] = active;
+        if (active) {
+#if defined(__CUDA_ARCH__)
+            atomicAdd(n_active, 1);
+#else
+            *n_active += 1;
+#endif
+        }
+    }
+    team.sync();
+    // forward-difference points of the Lagrangian Hessian: point a < nf perturbs free variable a, point nf is x itself
+    if (T.active[i]) {
+        double* X = T.x_fd + i * (long long)(S.nf + 1) * S.n;
+        for (int e = team.rank; e < (S.nf + 1) * S.n; e += team.size) {
+            const int a = e / S.n, j = e - a * S.n;
+            double v = x[j];
+            if (a < S.nf && S.free_idx[a] == j) v += 1e-7 * dmax(dabs(v), 1.0);
+            X[e] = v;
+        }
+    }
+}
+
+// ---- phase 2: Hessian, KKT system, regularised Newton step, line-search set-up ------------------------------------------------
+template <class Team>
+CPLB_HD void phase_kkt(const Team& team, const Shape& S, const State& T, const Options& O, long long i, Scratch& q)
+{
+    Inst I{S, T, i};
+    const int n = S.n, m = S.m, nk = S.nk, ld = q.ld;
+    double* Xls = T.x_ls + i * (long long)kCandidates * n;
+    double *x = I.vn(T.x), *s = I.vm(T.s);
+    if (!T.active[i]) {  // finished instances keep feeding finite points to the widened evaluations
+        for (int e = team.rank; e < kCandidates * n; e += team.size) Xls[e] = x[e % n];
+        return;
+    }
+    const double *lam = I.vm(T.lam), *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su);
+    const double *vxl = I.vn(T.vxl), *vxu = I.vn(T.vxu), *vsl = I.vm(T.vsl), *vsu = I.vm(T.vsu), *c = I.vm(T.c);
+    const double mu = T.mu[i], tau = T.tau[i], dobj = T.dobj[i];
+    double *dx = I.vn(T.dx), *ds = I.vm(T.ds), *dlam = I.vm(T.dlam), *h = I.vm(T.h), *r_x = I.vn(T.r_x), *r_s = I.vm(T.r_s), *D = I.vm(T.D);
+
+    compute_gaps(team, S, x, s, sl, su, q);
+    dense_jacobian(team, S, T.jv + i * S.nnz, dc, q.Jd);
+    for (int sl_ = team.rank; sl_ < S.nnz; sl_ += team.size) q.w[sl_] = dc[S.iRow[sl_]] * lam[S.iRow[sl_]];
+    team.sync();
+
+    // Lagrangian Hessian by forward differences: grad L at point a = dobj * grad f + sum_slots jac[slot] * (dc lam)[row(slot)]
+    const double* gfd = T.grad_fd + i * (long long)(S.nf + 1) * n;
+    const double* jfd = T.jac_fd + i * (long long)(S.nf + 1) * S.nnz;
+    auto grad_lagrangian = [&](int a, int j) -> double {
+        if (S.fixed[j]) return 0.0;
+        double acc = dobj * gfd[(long long)a * n + j];
+        const double* ja = jfd + (long long)a * S.nnz;
+        for (int e = S.col_ptr[j]; e < S.col_ptr[j + 1]; e++) acc += ja[S.col_slot[e]] * q.w[S.col_slot[e]];
+        return acc;
+    };
+    for (int j = team.rank; j < n; j += team.size) q.glb[j] = grad_lagrangian(S.nf, j);
+    for (int e = team.rank; e < n * n; e += team.size) q.H0[e] = 0.0;
+    team.sync();
+    for (int e = team.rank; e < S.nf * n; e += team.size) {
+        const int a = e / n, j = e - a * n;
+        const double eps = 1e-7 * dmax(dabs(x[S.free_idx[a]]), 1.0);
+        q.K[S.free_idx[a] * ld + j] = S.fixed[j] ? 0.0 : (grad_lagrangian(a, j) - q.glb[j]) / eps;  // K's top-left block as staging
+    }
+    team.sync();
+    // W = (Hc + Hc^T) / 2 on the free variables;  H0 = W + diag(sigma_x on the free ones, 1 on the fixed ones)
+    for (int j = team.rank; j < n; j += team.size) q.sigx[j] = (S.x_lo[j] ? vxl[j] / q.gxl[j] : 0.0) + (S.x_hi[j] ? vxu[j] / q.gxu[j] : 0.0);
+    for (int r = team.rank; r < m; r += team.size) q.sigs[r] = (S.s_lo[r] ? vsl[r] / q.gsl[r] : 0.0) + (S.s_hi[r] ? vsu[r] / q.gsu[r] : 0.0);
+    team.sync();
+    for (int e = team.rank; e < n * n; e += team.size) {
+        const int a = e / n, b = e - a * n;
+        double v = 0.0;
+        if (!S.fixed[a] && !S.fixed[b]) v = 0.5 * (q.K[a * ld + b] + q.K[b * ld + a]);
+        if (a == b) v += S.fixed[a] ? 1.0 : q.sigx[a];
+        q.H0[e] = v;
+    }
+    // residuals of the barrier problem
+    for (int j = team.rank; j < n; j += team.size)
+        r_x[j] = S.fixed[j] ? 0.0
+                            : (scaled_df(I, j) + jt_lam(I, j, lam) - (S.x_lo[j] ? mu / q.gxl[j] : 0.0) + (S.x_hi[j] ? mu / q.gxu[j] : 0.0));
+    for (int r = team.rank; r < m; r += team.size) {
+        r_s[r] = S.is_eq[r] ? 0.0 : (-lam[r] - (S.s_lo[r] ? mu / q.gsl[r] : 0.0) + (S.s_hi[r] ? mu / q.gsu[r] : 0.0));
+        h[r] = dc[r] * c[r] - s[r];
+        D[r] = S.is_eq[r] ? 0.0 : 1.0 / clamp_min(q.sigs[r], 1e-300);
+    }
+    team.sync();
+    const double delta_c = 1e-8 * pow(mu, 0.25);
+
+    // inertia-free regularisation (Chiang & Zavala 2016): raise delta_w until the step sees positive curvature
+    double delta = T.delta_lm[i];
+    for (int reg = 0; reg < kMaxReg; reg++) {
+        // K = [[H0 + delta I_free, Jf^T], [Jf, -(D + delta_c)]],  rhs = [-r_x, -h - D r_s]
+        for (int e = team.rank; e < nk * nk; e += team.size) {
+            const int a = e / nk, b = e - a * nk;
+            double v;
+            if (a < n && b < n) v = q.H0[a * n + b] + ((a == b && !S.fixed[a]) ? delta : 0.0);
+            else if (a < n) v = q.Jd[(b - n) * n + a];
+            else if (b < n) v = q.Jd[(a - n) * n + b];
+            else v = (a == b) ? -(D[a - n] + delta_c) : 0.0;
+            q.K[a * ld + b] = v;
+        }
+        for (int a = team.rank; a < nk; a += team.size) q.rhs[a] = a < n ? -r_x[a] : -h[a - n] - D[a - n] * r_s[a - n];
+        team.sync();
+        if (team.rank == 0) {
+            bool ok = true;
+            for (int a = 0; a < nk && ok; a++) {
+                if (!finite_d(q.rhs[a])) ok = false;
+                for (int b = 0; b < nk && ok; b++)
+                    if (!finite_d(q.K[a * ld + b])) ok = false;
+            }
+            q.red[0] = ok ? 1.0 : 0.0;
+        }
+        team.sync();
+        const bool okK = q.red[0] != 0.0;
+        if (!okK) {  // identity system, zero right-hand side: a zero step (the Python driver's eyeK)
+            for (int e = team.rank; e < nk * nk; e += team.size) q.K[(e / nk) * ld + e % nk] = (e / nk == e % nk) ? 1.0 : 0.0;
+            for (int a = team.rank; a < nk; a += team.size) q.rhs[a] = 0.0;
+            team.sync();
+        }
+        lu_factor(team, q.K, ld, nk, q.piv);
+        for (int a = team.rank; a < nk; a += team.size) q.sol[a] = q.rhs[a];
+        team.sync();
+        lu_solve(team, q.K, ld, nk, q.piv, q.sol);
+        // candidate step and the curvature it sees
+        for (int j = team.rank; j < n; j += team.size) q.tmp[j] = S.fixed[j] ? 0.0 : q.sol[j];                    // dx_t
+        for (int r = team.rank; r < m; r += team.size) q.tmp[n + r] = S.is_eq[r] ? 0.0 : D[r] * (q.sol[n + r] - r_s[r]);  // ds_t
+        team.sync();
+        for (int j = team.rank; j < n; j += team.size) {  // (H dx)_j, H = H0 + delta on the free diagonal
+            double acc = 0.0;
+            for (int b = 0; b < n; b++) acc += (q.H0[j * n + b] + ((j == b && !S.fixed[j]) ? delta : 0.0)) * q.tmp[b];
+            q.tmp[nk + j] = acc;
+        }
+        team.sync();
+        if (team.rank == 0) {
+            bool fin = true;
+            double quad = 0.0, nrm = 0.0;
+            for (int a = 0; a < nk; a++) fin = fin && finite_d(q.sol[a]);
+            for (int j = 0; j < n; j++) {
+                quad += q.tmp[j] * q.tmp[nk + j];
+                nrm += q.tmp[j] * q.tmp[j];
+            }
+            for (int r = 0; r < m; r++) {
+                quad += q.sigs[r] * q.tmp[n + r] * q.tmp[n + r];
+                nrm += q.tmp[n + r] * q.tmp[n + r];
+            }
+            const bool good = fin && quad >= 1e-8 * nrm;
+            q.red[1] = (good || reg == kMaxReg - 1) ? 1.0 : 0.0;
+            q.red[2] = quad;
+        }
+        team.sync();
+        if (q.red[1] != 0.0) {
+            for (int j = team.rank; j < n; j += team.size) dx[j] = q.tmp[j];
+            for (int r = team.rank; r < m; r += team.size) {
+                ds[r] = q.tmp[n + r];
+                dlam[r] = q.sol[n + r];
+            }
+            if (team.rank == 0) {
+                T.quad[i] = q.red[2];
+                T.delta_last[i] = delta;
+                T.okK[i] = okK ? 1 : 0;
+            }
+            break;
+        }
+        delta = dmax(delta * 8.0, 1e-4);
+        team.sync();
+    }
+    team.sync();
+    // the factors stay for the second-order correction
+    {
+        double* LU = T.lu + i * (long long)nk * nk;
+        for (int e = team.rank; e < nk * nk; e += team.size) LU[e] = q.K[(e / nk) * ld + e % nk];
+        for (int a = team.rank; a < nk; a += team.size) T.piv[i * nk + a] = q.piv[a];
+    }
+    if (team.rank == 0) {
+        bool bad = false;
+        for (int j = 0; j < n; j++) bad = bad || !finite_d(dx[j]);
+        for (int r = 0; r < m; r++) bad = bad || !finite_d(dlam[r]);
+        q.red[3] = bad ? 1.0 : 0.0;
+    }
+    team.sync();
+    if (q.red[3] != 0.0) {
+        for (int j = team.rank; j < n; j += team.size) dx[j] = 0.0;
+        for (int r = team.rank; r < m; r += team.size) ds[r] = dlam[r] = 0.0;
+    }
+    team.sync();
+
+    // feasibility polish: minimum-norm Newton step on x only (multipliers stay), on the equality rows and on the inequality
+    // rows that sit beyond their ORIGINAL bound
+    const bool pol = T.polish[i] != 0;
+    if (pol) {
+        const double *cu_s = I.vm(T.cu_s), *cl_s = I.vm(T.cl_s);
+        double* act = q.tmp;        // [m]
+        double* r_p = q.tmp + m;    // [m]
+        for (int r = team.rank; r < m; r += team.size) {
+            const double cs = dc[r] * c[r];
+            const bool over = !S.is_eq[r] && S.s_hi[r] && cs > cu_s[r], under = !S.is_eq[r] && S.s_lo[r] && cs < cl_s[r];
+            act[r] = (S.is_eq[r] || over || under) ? 1.0 : 0.0;
+            r_p[r] = over ? cs - cu_s[r] : (under ? cs - cl_s[r] : (S.is_eq[r] ? cs - sl[r] : 0.0));
+        }
+        team.sync();
+        for (int e = team.rank; e < m * m; e += team.size) {  // M = Je Je^T + diag((1 - act) + 1e-14)
+            const int a = e / m, b = e - a * m;
+            double acc = 0.0;
+            if (act[a] != 0.0 && act[b] != 0.0)
+                for (int j = 0; j < n; j++) acc += q.Jd[a * n + j] * q.Jd[b * n + j];
+            if (a == b) acc += (1.0 - act[a]) + 1e-14;
+            q.K[a * ld + b] = acc;
+        }
+        team.sync();
+        if (team.rank == 0) {
+            bool ok = true;
+            for (int a = 0; a < m && ok; a++)
+                for (int b = 0; b < m && ok; b++) ok = finite_d(q.K[a * ld + b]);
+            q.red[4] = ok ? 1.0 : 0.0;
+        }
+        team.sync();
+        if (q.red[4] == 0.0) {
+            for (int e = team.rank; e < m * m; e += team.size) q.K[(e / m) * ld + e % m] = (e / m == e % m) ? 1.0 : 0.0;
+            team.sync();
+        }
+        lu_factor(team, q.K, ld, m, q.piv);
+        for (int r = team.rank; r < m; r += team.size) q.sol[r] = r_p[r];
+        team.sync();
+        lu_solve(team, q.K, ld, m, q.piv, q.sol);
+        for (int j = team.rank; j < n; j += team.size) {
+            double acc = 0.0;
+            for (int r = 0; r < m; r++)
+                if (act[r] != 0.0) acc += q.Jd[r * n + j] * q.sol[r];
+            q.rhs[j] = S.fixed[j] ? 0.0 : -acc;
+        }
+        team.sync();
+        if (team.rank == 0) {
+            bool fin = true;
+            for (int j = 0; j < n; j++) fin = fin && finite_d(q.rhs[j]);
+            q.red[5] = fin ? 1.0 : 0.0;
+        }
+        team.sync();
+        for (int j = team.rank; j < n; j += team.size) dx[j] = q.red[5] != 0.0 ? q.rhs[j] : 0.0;
+        for (int r = team.rank; r < m; r += team.size) ds[r] = dlam[r] = 0.0;
+        team.sync();
+    }
+
+    // multiplier steps, fraction-to-the-boundary step lengths, merit function quantities
+    double *dvxl = I.vn(T.dvxl), *dvxu = I.vn(T.dvxu), *dvsl = I.vm(T.dvsl), *dvsu = I.vm(T.dvsu);
+    for (int j = team.rank; j < n; j += team.size) {
+        dvxl[j] = S.x_lo[j] ? (mu / q.gxl[j] - vxl[j] - vxl[j] / q.gxl[j] * dx[j]) : 0.0;
+        dvxu[j] = S.x_hi[j] ? (mu / q.gxu[j] - vxu[j] + vxu[j] / q.gxu[j] * dx[j]) : 0.0;
+    }
+    for (int r = team.rank; r < m; r += team.size) {
+        dvsl[r] = S.s_lo[r] ? (mu / q.gsl[r] - vsl[r] - vsl[r] / q.gsl[r] * ds[r]) : 0.0;
+        dvsu[r] = S.s_hi[r] ? (mu / q.gsu[r] - vsu[r] + vsu[r] / q.gsu[r] * ds[r]) : 0.0;
+    }
+    team.sync();
+    if (team.rank == 0) {
+        auto ms = [&](double val, double dval, bool mask, double cur) {  // largest a with val + a dval >= (1 - tau) val
+            if (mask && dval < 0) cur = nanmin(cur, -tau * val / dval);
+            return cur;
+        };
+        double a_p = INFINITY, a_d = INFINITY;
+        for (int j = 0; j < n; j++) {
+            a_p = ms(q.gxl[j], dx[j], S.x_lo[j], a_p);
+            a_p = ms(q.gxu[j], -dx[j], S.x_hi[j], a_p);
+            a_d = ms(vxl[j], dvxl[j], S.x_lo[j], a_d);
+            a_d = ms(vxu[j], dvxu[j], S.x_hi[j], a_d);
+        }
+        for (int r = 0; r < m; r++) {
+            if (!pol) {
+                a_p = ms(q.gsl[r], ds[r], S.s_lo[r], a_p);
+                a_p = ms(q.gsu[r], -ds[r], S.s_hi[r], a_p);
+            }
+            a_d = ms(vsl[r], dvsl[r], S.s_lo[r], a_d);
+            a_d = ms(vsu[r], dvsu[r], S.s_hi[r], a_d);
+        }
+        a_p = clamp_max(a_p, 1.0);
+        a_d = pol ? 0.0 : clamp_max(a_d, 1.0);
+        // l1 merit function phi + nu |h|_1 and its directional derivative
+        double lb = 0.0, h1 = 0.0, dphi = 0.0, lmax = 0.0, tiny = 0.0;
+        for (int j = 0; j < n; j++) {
+            if (S.x_lo[j]) lb += log(q.gxl[j]);
+            if (S.x_hi[j]) lb += log(q.gxu[j]);
+            const double gphi = S.fixed[j] ? 0.0 : (scaled_df(I, j) - (S.x_lo[j] ? mu / q.gxl[j] : 0.0) + (S.x_hi[j] ? mu / q.gxu[j] : 0.0));
+            dphi += gphi * dx[j];
+            tiny = nanmax(tiny, dabs(dx[j]) / (1.0 + dabs(x[j])));
+        }
+        for (int r = 0; r < m; r++) {
+            if (S.s_lo[r]) lb += log(q.gsl[r]);
+            if (S.s_hi[r]) lb += log(q.gsu[r]);
+            const double gphi = S.is_eq[r] ? 0.0 : (-(S.s_lo[r] ? mu / q.gsl[r] : 0.0) + (S.s_hi[r] ? mu / q.gsu[r] : 0.0));
+            dphi += gphi * ds[r];
+            h1 += dabs(h[r]);
+            lmax = nanmax(lmax, dabs(lam[r] + dlam[r]));
+        }
+        const double phi0 = dobj * T.f[i] - mu * lb;
+        const double nu_need = (dphi + 0.5 * clamp_min(T.quad[i], 0.0)) / (0.9 * clamp_min(h1, 1e-300));
+        const double nu = nanmax(clamp_min(nu_need, 0.0), lmax) * 1.1 + 1e-3;
+        T.nu[i] = nu;
+        T.Dm[i] = dphi - nu * h1;
+        T.merit0[i] = phi0 + nu * h1;
+        T.a_p[i] = a_p;
+        T.a_d[i] = a_d;
+        T.tiny[i] = tiny < 1e-13 ? 1 : 0;
+        T.pol[i] = pol ? 1 : 0;
+        // what the polish drives to zero: equality residuals and the excess over the ORIGINAL inequality bounds
+        const double *cu_s = I.vm(T.cu_s), *cl_s = I.vm(T.cl_s);
+        double R0 = 0.0;
+        for (int r = 0; r < m; r++) {
+            const double cs = dc[r] * c[r];
+            if (S.is_eq[r]) R0 = nanmax(R0, dabs(cs - sl[r]));
+            else R0 = nanmax(R0, (S.s_hi[r] ? clamp_min(cs - cu_s[r], 0.0) : 0.0) + (S.s_lo[r] ? clamp_min(cl_s[r] - cs, 0.0) : 0.0));
+        }
+        T.R0[i] = R0;
+        q.red[6] = a_p;
+    }
+    team.sync();
+    // line-search candidates x + alpha0 2^-k dx, k = 0 .. kCandidates - 1
+    const double a0 = q.red[6];
+    for (int e = team.rank; e < kCandidates * n; e += team.size) {
+        const int k = e / n, j = e - k * n;
+        Xls[e] = x[j] + (a0 * ldexp(1.0, -k)) * dx[j];
+    }
+}
+
+// merit test of one trial point: row values ct (scaled), slacks by the reset rule; returns ok and writes the trial slacks
+struct Trial {
+    bool ok, ct_finite;
+};
+CPLB_HD Trial merit_test(const Inst& I, const double* X, const double* g_raw, double cost_raw, const double* S_lin, double AL, double* st_out)
+{
+    const Shape& S = I.S;
+    const State& T = I.T;
+    const long long i = I.i;
+    const double *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su), *s = I.vm(T.s), *cu_s = I.vm(T.cu_s), *cl_s = I.vm(T.cl_s);
+    const double mu = T.mu[i], nu = T.nu[i], keep = mu / nu;
+    const bool pol = T.pol[i] != 0;
+    const double ft = T.dobj[i] * cost_raw;
+    double lb = 0.0, viol = 0.0, Rt = 0.0;
+    bool ct_fin = true;
+    for (int j = 0; j < S.n; j++) {
+        if (S.x_lo[j]) lb += log(X[j] - S.xl[j]);
+        if (S.x_hi[j]) lb += log(S.xu[j] - X[j]);
+    }
+    for (int r = 0; r < S.m; r++) {
+        const double ct = dc[r] * g_raw[r];
+        ct_fin = ct_fin && finite_d(ct);
+        double st = S_lin[r];
+        // slack reset (Nocedal & Wright 2006, section 19.3): the row value itself, mu / nu inside its bound
+        if (S.s_hi[r] && !S.s_lo[r]) st = nanmin(ct, su[r] - keep);
+        if (S.s_lo[r] && !S.s_hi[r]) st = nanmax(ct, sl[r] + keep);
+        if (pol) {
+            // polishing instances: the slack of a strictly satisfied inequality row is the row value
+            const bool inside = (!S.s_lo[r] || ct > sl[r]) && (!S.s_hi[r] || ct < su[r]);
+            st = (!S.is_eq[r] && inside) ? ct : s[r];
+            if (S.is_eq[r]) Rt = nanmax(Rt, dabs(ct - sl[r]));
+            else Rt = nanmax(Rt, (S.s_hi[r] ? clamp_min(ct - cu_s[r], 0.0) : 0.0) + (S.s_lo[r] ? clamp_min(cl_s[r] - ct, 0.0) : 0.0));
+        } else {
+            if (S.s_lo[r]) lb += log(st - sl[r]);
+            if (S.s_hi[r]) lb += log(su[r] - st);
+            viol += dabs(ct - st);
+        }
+        st_out[r] = st;
+    }
+    Trial t;
+    t.ct_finite = ct_fin;
+    if (pol) {
+        t.ok = ct_fin && Rt < T.R0[i];
+    } else {
+        const double mt = (ft - mu * lb) + nu * viol;
+        const double m0 = T.merit0[i];
+        t.ok = finite_d(mt) && mt <= (m0 + 10.0 * 2.2e-16 * dabs(m0)) + 1e-4 * AL * T.Dm[i];
+    }
+    return t;
+}
+
+// ---- phase 3: the full step, else the second-order correction ------------------------------------------------------------------
+// Tests candidate 0; when it fails, solves the same KKT matrix with the constraint residual of the rejected point added to
+// the right-hand side (Waechter & Biegler 2006, section 2.4) and emits the corrected trial point for one more evaluation.
+template <class Team>
+CPLB_HD void phase_ls_first(const Team& team, const Shape& S, const State& T, const Options& O, long long i, Scratch& q)
+{
+    Inst I{S, T, i};
+    const int n = S.n, m = S.m, nk = S.nk;
+    double* Xsoc = T.x_soc + i * n;
+    const double* x = I.vn(T.x);
+    if (team.rank == 0) {
+        T.accepted0[i] = 0;
+        T.soc_valid[i] = 0;
+    }
+    if (!T.active[i]) {
+        for (int j = team.rank; j < n; j += team.size) Xsoc[j] = x[j];
+        return;
+    }
+    const double *s = I.vm(T.s), *ds = I.vm(T.ds), *dc = I.vm(T.dc);
+    const double a0 = T.a_p[i];
+    const double* X0 = T.x_ls + i * (long long)kCandidates * n;
+    const double* g0 = T.g_ls + i * (long long)kCandidates * m;
+    for (int r = team.rank; r < m; r += team.size) q.tmp[r] = s[r] + a0 * ds[r];  // linearly stepped slacks of candidate 0
+    team.sync();
+    if (team.rank == 0) {
+        Trial t = merit_test(I, X0, g0, T.cost_ls[i * kCandidates], q.tmp, a0, q.tmp + m);
+        bool ok = t.ok || (T.tiny[i] && t.ct_finite);
+        if (O.max_backtracks < 1) ok = false;
+        T.accepted0[i] = ok ? 1 : 0;
+        q.red[0] = ok ? 1.0 : 0.0;
+    }
+    team.sync();
+    if (q.red[0] != 0.0 || T.pol[i]) {
+        for (int j = team.rank; j < n; j += team.size) Xsoc[j] = x[j];
+        return;
+    }
+    // second-order correction with the stored factors
+    const double *h = I.vm(T.h), *r_x = I.vn(T.r_x), *r_s = I.vm(T.r_s), *D = I.vm(T.D);
+    const bool okK = T.okK[i] != 0;
+    for (int a = team.rank; a < nk; a += team.size) {
+        double v = 0.0;
+        if (okK) {
+            if (a < n) v = -r_x[a];
+            else {
+                const int r = a - n;
+                const double h_soc = a0 * h[r] + (dc[r] * g0[r] - (s[r] + a0 * ds[r]));
+                v = -h_soc - D[r] * r_s[r];
+            }
+        }
+        q.sol[a] = v;
+    }
+    const double* LU = T.lu + i * (long long)nk * nk;
+    for (int e = team.rank; e < nk * nk; e += team.size) q.K[(e / nk) * q.ld + e % nk] = LU[e];
+    for (int a = team.rank; a < nk; a += team.size) q.piv[a] = T.piv[i * nk + a];
+    team.sync();
+    lu_solve(team, q.K, q.ld, nk, q.piv, q.sol);
+    double *dxc = T.dx_soc + i * n, *dsc = T.ds_soc + i * m, *dlc = T.dlam_soc + i * m;
+    for (int j = team.rank; j < n; j += team.size) dxc[j] = S.fixed[j] ? 0.0 : q.sol[j];
+    for (int r = team.rank; r < m; r += team.size) {
+        dlc[r] = q.sol[n + r];
+        dsc[r] = S.is_eq[r] ? 0.0 : D[r] * (q.sol[n + r] - r_s[r]);
+    }
+    compute_gaps(team, S, x, s, I.vm(T.sl), I.vm(T.su), q);
+    team.sync();
+    if (team.rank == 0) {
+        bool fin = true;
+        for (int a = 0; a < nk; a++) fin = fin && finite_d(q.sol[a]);
+        const double tau = T.tau[i];
+        auto ms = [&](double val, double dval, bool mask, double cur) {
+            if (mask && dval < 0) cur = nanmin(cur, -tau * val / dval);
+            return cur;
+        };
+        double a_c = INFINITY;
+        for (int j = 0; j < n; j++) {
+            a_c = ms(q.gxl[j], dxc[j], S.x_lo[j], a_c);
+            a_c = ms(q.gxu[j], -dxc[j], S.x_hi[j], a_c);
+        }
+        for (int r = 0; r < m; r++) {
+            a_c = ms(q.gsl[r], dsc[r], S.s_lo[r], a_c);
+            a_c = ms(q.gsu[r], -dsc[r], S.s_hi[r], a_c);
+        }
+        a_c = clamp_max(a_c, 1.0);
+        T.a_soc[i] = a_c;
+        T.soc_valid[i] = fin ? 1 : 0;
+        q.red[1] = a_c;
+        q.red[2] = fin ? 1.0 : 0.0;
+    }
+    team.sync();
+    for (int j = team.rank; j < n; j += team.size) Xsoc[j] = q.red[2] != 0.0 ? x[j] + q.red[1] * dxc[j] : x[j];
+}
+
+// ---- phase 4: accept a point, update the iterate and the multipliers ------------------------------------------------------------
+template <class Team>
+CPLB_HD void phase_ls_select(const Team& team, const Shape& S, const State& T, const Options& O, long long i, Scratch& q)
+{
+    Inst I{S, T, i};
+    const int n = S.n, m = S.m;
+    if (!T.active[i]) return;
+    double *x = I.vn(T.x), *s = I.vm(T.s), *lam = I.vm(T.lam);
+    const double *dx = I.vn(T.dx), *ds = I.vm(T.ds);
+    const double a0 = T.a_p[i];
+    const bool pol = T.pol[i] != 0;
+    double* st = q.tmp;          // [m] trial slacks
+    double* slin = q.tmp + m;    // [m]
+    if (team.rank == 0) {
+        // order of a sequential backtracking search: full step, second-order correction, 1/2, 1/4, ...
+        int choice = -1;         // candidate index, kCandidates = the corrected point
+        double alpha = a0;
+        if (T.accepted0[i]) {
+            choice = 0;
+            for (int r = 0; r < m; r++) slin[r] = s[r] + a0 * ds[r];
+            merit_test(I, T.x_ls + i * (long long)kCandidates * n, T.g_ls + i * (long long)kCandidates * m, T.cost_ls[i * kCandidates], slin, a0, st);
+        } else {
+            if (T.soc_valid[i] && !pol) {
+                const double a_c = T.a_soc[i];
+                const double* dsc = T.ds_soc + i * m;
+                for (int r = 0; r < m; r++) slin[r] = s[r] + a_c * dsc[r];
+                Trial t = merit_test(I, T.x_soc + i * n, T.g_soc + i * m, T.cost_soc[i], slin, a0, st);
+                bool finx = true;
+                for (int j = 0; j < n; j++) finx = finx && finite_d(T.x_soc[i * n + j]);
+                if (t.ok && finx) choice = kCandidates;
+            }
+            const int kmax = O.max_backtracks < kCandidates ? O.max_backtracks : kCandidates;
+            for (int k = 1; k < kmax && choice < 0; k++) {
+                const double AL = a0 * ldexp(1.0, -k);
+                for (int r = 0; r < m; r++) slin[r] = s[r] + AL * ds[r];
+                Trial t = merit_test(I, T.x_ls + (i * kCandidates + k) * (long long)n, T.g_ls + (i * kCandidates + k) * (long long)m,
+                                     T.cost_ls[i * kCandidates + k], slin, AL, st);
+                if (t.ok || (T.tiny[i] && t.ct_finite)) {
+                    choice = k;
+                    alpha = AL;
+                }
+            }
+        }
+        if (choice < 0) {  // search exhausted: take the last (tiny) step
+            alpha = a0 * ldexp(1.0, -O.max_backtracks);
+            for (int r = 0; r < m; r++) st[r] = s[r] + alpha * ds[r];
+        }
+        // Levenberg-Marquardt damping of the next step: a search that had to backtrack asks for a shorter step next time
+        double n_back = rint(log2(clamp_min(a0 / clamp_min(alpha, 1e-300), 1.0)));
+        if (pol) n_back = 1.0;
+        const double dl = T.delta_last[i];
+        double dlm = n_back >= 2 ? dmax(dl * 8.0, 1e-6) : (n_back >= 1 ? dmax(dl * 2.0, 1e-6) : dl / 4.0);
+        if (dlm < 1e-12) dlm = 0.0;
+        T.delta_lm[i] = dmin(dlm, 1.0);
+        q.red[0] = (double)choice;
+        q.red[1] = alpha;
+    }
+    team.sync();
+    const int choice = (int)q.red[0];
+    const double alpha = q.red[1], a_d = T.a_d[i];
+    const double* dlam_used = (choice == kCandidates) ? T.dlam_soc + i * m : I.vm(T.dlam);
+    const double* xnew = choice == kCandidates ? T.x_soc + i * n : (choice >= 0 ? T.x_ls + (i * kCandidates + choice) * (long long)n : nullptr);
+    for (int j = team.rank; j < n; j += team.size) {
+        x[j] = xnew ? xnew[j] : x[j] + alpha * dx[j];
+        I.vn(T.vxl)[j] += a_d * I.vn(T.dvxl)[j];
+        I.vn(T.vxu)[j] += a_d * I.vn(T.dvxu)[j];
+    }
+    for (int r = team.rank; r < m; r += team.size) {
+        s[r] = st[r];
+        lam[r] += alpha * dlam_used[r];
+        I.vm(T.vsl)[r] += a_d * I.vm(T.dvsl)[r];
+        I.vm(T.vsu)[r] += a_d * I.vm(T.dvsu)[r];
+    }
+}
+
+// ---- results: honor_original_bounds, unscaled cost and multipliers -------------------------------------------------------------
+template <class Team>
+CPLB_HD void phase_finish(const Team& team, const Shape& S, const State& T, long long i, double* x_out, double* lam_out)
+{
+    Inst I{S, T, i};
+    const double* x = I.vn(T.x);
+    for (int j = team.rank; j < S.n; j += team.size) x_out[i * S.n + j] = nanmin(nanmax(x[j], S.xlo_orig[j]), S.xhi_orig[j]);
+    if (lam_out)
+        for (int r = team.rank; r < S.m; r += team.size) lam_out[i * S.m + r] = I.vm(T.lam)[r] * I.vm(T.dc)[r] / T.dobj[i];
+    if (team.rank == 0) T.out_cost[i] = T.f[i];
+}
+
+
+// ==== host side shared by the GPU driver (cplb_solver.cu) and the CPU replay (tests/native/solver_host_check.cpp) ================
+
+// Owner of the problem-level arrays of a Shape (host copies; the GPU driver uploads them).
+struct ShapeHost {
+    int n = 0, m = 0, nnz = 0, nf = 0;
+    std::vector<int32_t> iRow, jCol, col_ptr, col_slot, free_idx;
+    std::vector<double> xl, xu, xlo_orig, xhi_orig, cl, cu, cl_r, cu_r;
+    std::vector<uint8_t> fixed, x_lo, x_hi, s_lo, s_hi, is_eq;
+
+    // bounds as Problem::GetBoundsOnOptimizationVariables / GetBoundsOnConstraints report them (ifopt inf = 1e20);
+    // fixed_variable_treatment = make_parameter, bound_relax_factor as in IPOPT
+    void build(int n_, int m_, int nnz_, const int32_t* iRow_, const int32_t* jCol_, const double* xlb, const double* xub, const double* clb,
+               const double* cub, double bound_relax)
+    {
+        n = n_;
+        m = m_;
+        nnz = nnz_;
+        iRow.assign(iRow_, iRow_ + nnz);
+        jCol.assign(jCol_, jCol_ + nnz);
+        xlo_orig.assign(xlb, xlb + n);
+        xhi_orig.assign(xub, xub + n);
+        cl.assign(clb, clb + m);
+        cu.assign(cub, cub + m);
+        xl = xlo_orig;
+        xu = xhi_orig;
+        fixed.assign(n, 0);
+        x_lo.assign(n, 0);
+        x_hi.assign(n, 0);
+        free_idx.clear();
+        for (int j = 0; j < n; j++) {
+            fixed[j] = xl[j] == xu[j];
+            if (!fixed[j]) {
+                xl[j] = xl[j] - bound_relax * dmax(dabs(xl[j]), 1.0);
+                xu[j] = xu[j] + bound_relax * dmax(dabs(xu[j]), 1.0);
+                free_idx.push_back(j);
+            }
+            x_lo[j] = !fixed[j] && xl[j] > -kInfBound;
+            x_hi[j] = !fixed[j] && xu[j] < kInfBound;
+        }
+        nf = (int)free_idx.size();
+        cl_r = cl;
+        cu_r = cu;
+        s_lo.assign(m, 0);
+        s_hi.assign(m, 0);
+        is_eq.assign(m, 0);
+        for (int r = 0; r < m; r++) {
+            is_eq[r] = cl[r] == cu[r];
+            if (!is_eq[r]) {
+                cl_r[r] = cl[r] - bound_relax * dmax(dabs(cl[r]), 1.0);
+                cu_r[r] = cu[r] + bound_relax * dmax(dabs(cu[r]), 1.0);
+            }
+            s_lo[r] = !is_eq[r] && cl[r] > -kInfBound;
+            s_hi[r] = !is_eq[r] && cu[r] < kInfBound;
+        }
+        col_ptr.assign(n + 1, 0);
+        for (int e = 0; e < nnz; e++) col_ptr[jCol[e] + 1]++;
+        for (int j = 0; j < n; j++) col_ptr[j + 1] += col_ptr[j];
+        col_slot.assign(nnz, 0);
+        std::vector<int32_t> fill(col_ptr.begin(), col_ptr.end() - 1);
+        for (int e = 0; e < nnz; e++) col_slot[fill[jCol[e]]++] = e;  // ascending slot order within a column
+    }
+};
+
+// Every per-instance array of a State with its element count per instance: lets both engines allocate generically.
+struct StateField {
+    void** ptr;
+    size_t per_instance;  // elements per instance
+    bool is_int;
+};
+inline std::vector<StateField> state_fields(State& T, const ShapeHost& S)
+{
+    const size_t n = S.n, m = S.m, nnz = S.nnz, nk = S.n + S.m, P = S.nf + 1, KC = kCandidates;
+    std::vector<StateField> f;
+    auto D = [&](double*& p, size_t c) { f.push_back({reinterpret_cast<void**>(&p), c, false}); };
+    auto I = [&](int32_t*& p, size_t c) { f.push_back({reinterpret_cast<void**>(&p), c, true}); };
+    D(T.x, n); D(T.s, m); D(T.lam, m); D(T.vxl, n); D(T.vxu, n); D(T.vsl, m); D(T.vsu, m);
+    D(T.mu, 1); D(T.tau, 1); D(T.delta_last, 1); D(T.delta_lm, 1);
+    I(T.status, 1); I(T.iters, 1); I(T.polish, 1); I(T.active, 1);
+    D(T.f, 1); D(T.df, n); D(T.c, m); D(T.jv, nnz);
+    D(T.dc, m); D(T.dobj, 1); D(T.sl, m); D(T.su, m); D(T.cu_s, m); D(T.cl_s, m);
+    D(T.dx, n); D(T.ds, m); D(T.dlam, m); D(T.dvxl, n); D(T.dvxu, n); D(T.dvsl, m); D(T.dvsu, m); D(T.h, m); D(T.r_x, n); D(T.r_s, m); D(T.D, m);
+    D(T.a_p, 1); D(T.a_d, 1); D(T.merit0, 1); D(T.Dm, 1); D(T.nu, 1); D(T.R0, 1); D(T.quad, 1);
+    I(T.tiny, 1); I(T.pol, 1); I(T.okK, 1); I(T.accepted0, 1);
+    D(T.lu, nk * nk); I(T.piv, nk);
+    D(T.x_fd, P * n); D(T.grad_fd, P * n); D(T.jac_fd, P * nnz);
+    D(T.x_ls, KC * n); D(T.g_ls, KC * m); D(T.cost_ls, KC);
+    D(T.x_soc, n); D(T.g_soc, m); D(T.cost_soc, 1); D(T.dx_soc, n); D(T.ds_soc, m); D(T.dlam_soc, m); D(T.a_soc, 1);
+    I(T.soc_valid, 1);
+    D(T.out_cost, 1); D(T.out_viol, 1); D(T.out_dual, 1);
+    return f;
+}
+
+struct SolveStats {
+    int rounds = 0;
+    long long evaluations = 0, instance_evaluations = 0;
+};
+
+// The lock-step round, engine-independent.  Engine: init_x(), init_scale(), round_begin(first, last) -> instances still running,
+// kkt(), ls_first(), ls_select(), finish(), and the four batched evaluations eval_full / eval_fd / eval_ls / eval_soc.
+template <class Engine>
+SolveStats solve_loop(Engine& E, const Options& O, long long N, int nf)
+{
+    SolveStats st;
+    E.init_x();
+    E.eval_full();
+    st.evaluations++;
+    st.instance_evaluations += N;
+    E.init_scale();
+    for (int it = 0; it <= O.max_iter; it++) {
+        const int running = E.round_begin(it == 0, it == O.max_iter);
+        if (running == 0) break;
+        st.rounds++;
+        E.eval_fd();   // gradient + Jacobian at the nf + 1 difference points of every instance
+        E.kkt();
+        E.eval_ls();   // constraint values + cost at the line-search candidates
+        E.ls_first();
+        E.eval_soc();  // ... and at the second-order-corrected points
+        E.ls_select();
+        E.eval_full();
+        st.evaluations += 4;
+        st.instance_evaluations += N * (long long)(nf + 1 + kCandidates + 2);
+    }
+    E.finish();
+    return st;
+}
+}  // namespace solver
+}  // namespace cplb
+#endif

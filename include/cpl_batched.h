@@ -303,6 +303,57 @@ cplb_status cplb_get_packed_jacobian_map(const cplb_problem *p, int32_t *num_pac
  * values[] array IpoptAdapter::eval_jac_g hands to IPOPT, constants included. */
 cplb_status cplb_unpack_jacobian(const cplb_problem *p, int64_t num_instances, const double *packed, double *full);
 
+/* ---- the caller of the path: lock-step solves --------------------------------------------------------------------------- */
+
+/* Replaces, for N instances of the problem at once, cpl::CentroidalPlanner::Solve (src/CentroidalPlanner.cpp:22-34:
+ * ifopt::IpoptSolver::Solve on one CplProblem, then CplProblem::GetSolution).  IPOPT is a host library that is not part of
+ * this repository; the production integration keeps it (one IPOPT thread per instance over the IFOPT views in lock-step mode,
+ * INTEGRATION.md).  cplb_solve_device is the same round with the solver written out and run on the GPU: the primal-dual
+ * interior-point method IPOPT implements (slack reformulation, log barrier, fraction-to-the-boundary rule, monotone barrier update,
+ * gradient-based scaling, bound push and relaxation, kappa_sigma safeguard, fixed variables removed, second-order correction; tol as
+ * ifopt sets it), with a forward-difference Lagrangian Hessian (the reference runs IPOPT's limited-memory approximation), an l1
+ * merit line search, Levenberg-Marquardt damping and a feasibility polish.  It is NOT IPOPT: iterates differ, solutions are local
+ * minima of the same NLP to the same tolerances.  Every round is four batched evaluations of the hot path and four kernels that
+ * keep one instance's KKT system in shared memory (csrc/cplb_solver.cu); x never leaves the device.
+ * Options carry IPOPT's names where the meaning is IPOPT's. */
+typedef struct cplb_solver_options {
+    double tol;                      /* 1e-3: ifopt's IpoptSolver default */
+    double mu_init;                  /* 0.1 */
+    double bound_push, bound_frac;   /* 1e-2, 1e-2 */
+    double nlp_scaling_max_gradient; /* 100 */
+    double constr_viol_tol;          /* 1e-4 */
+    double polish_viol_tol;          /* 1e-9: constraint violation after the feasibility polish */
+    double bound_relax_factor;       /* 1e-8 */
+    int32_t max_iter;                /* 500 */
+    int32_t max_backtracks;          /* 30 */
+} cplb_solver_options;
+void cplb_solver_default_options(cplb_solver_options *options);
+
+#define CPLB_SOLVE_SUCCEEDED 0              /* Ipopt::Solve_Succeeded */
+#define CPLB_SOLVE_MAX_ITERATIONS 1         /* Ipopt::Maximum_Iterations_Exceeded */
+#define CPLB_SOLVE_INVALID_NUMBER 2         /* Ipopt::Invalid_Number_Detected */
+
+/* Device arrays the solve fills (instance-major; lam and the three counters may be NULL). */
+typedef struct cplb_solve_outputs {
+    double *x;            /* [N n]  final iterates, clipped to the variable bounds (honor_original_bounds); CplProblem::GetSolution
+                             reads one instance's slice (cplb::BatchedProblem::GetSolution) */
+    int32_t *status;      /* [N]    CPLB_SOLVE_* */
+    int32_t *iterations;  /* [N] */
+    double *cost;         /* [N]    MinimizeCentroidalVariables::GetCost at x */
+    double *constr_viol;  /* [N]    max violation of the constraint bounds at x */
+    double *dual_inf;     /* [N]    scaled dual infeasibility at x */
+    double *lam;          /* [N m]  constraint multipliers, or NULL */
+    int32_t *rounds;              /* HOST: lock-step rounds executed, or NULL */
+    int64_t *evaluations;         /* HOST: batched evaluations launched, or NULL */
+    int64_t *instance_evaluations; /* HOST: instances evaluated in total, or NULL */
+} cplb_solve_outputs;
+
+/* x0 [N n]: starting points (DEVICE pointer, like every array of `out`), variable and constraint bounds as set on the problem.
+ * Synchronises `cuda_stream` (the host reads one counter per round).  Single-device problems only: one solve batch per GPU,
+ * instances shard across GPUs by running one batch per device. */
+cplb_status cplb_solve_device(cplb_problem *p, int64_t num_instances, const double *x0, const cplb_solver_options *options,
+                              const cplb_solve_outputs *out, void *cuda_stream);
+
 /* Pinned host memory for cplb_eval_host buffers (cudaHostAlloc / cudaFreeHost). */
 cplb_status cplb_host_alloc(size_t bytes, void **out);
 cplb_status cplb_host_free(void *ptr);

@@ -132,11 +132,11 @@ def solution_maps(problem_names, x):
     return out
 
 
-def solve_and_check(case, problem, names, par, x0):
+def solve_and_check(case, problem, names, par, x0, solver_cls=None):
     """Every instance must succeed, except on the superquadric problem: a |x|^10 surface with the contact normals tied to its
     gradient is where the stand-in's l1 line search (no restoration phase) can run out of iterations from an unlucky start --
     there the default start must succeed and at least 90 % of the perturbed ones; every success must pass every EXPECT."""
-    res = LockStepInteriorPoint(max_iter=1000 if case == "superquadric" else 500).Solve(problem, x0)
+    res = (solver_cls or LockStepInteriorPoint)(max_iter=1000 if case == "superquadric" else 500).Solve(problem, x0)
     ok = (res.status == SUCCESS).cpu().numpy()
     report = (res.status.tolist(), res.iterations.tolist())
     if case == "superquadric":
@@ -316,3 +316,69 @@ def test_instances_that_are_different_problems(cuda_device):
             assert -F.dot(n) <= RELAX and np.linalg.norm(F - n.dot(F) * n) - par["mu"] * F.dot(n) <= RELAX
         assert np.abs(F_sum - (wrench[i, :3] - mass[i] * np.array([0.0, 0.0, G]))).max() < 1e-6
         assert np.abs(T_sum - wrench[i, 3:]).max() < 1e-5
+
+
+# ---- the native solve round (cplb_solve_device: csrc/cplb_solver.cu, csrc/cplb_solver_core.hpp) ----------------------------------
+def test_native_solve_round_on_the_cpu_with_the_oracle(tmp_path):
+    """tests/native/solver_host_check.cpp runs the SAME per-instance code the GPU runs one CTA per instance (cplb_solver_core.hpp)
+    one thread per instance with the oracle behind the batched evaluations: the reference's three four-contact TEST_Fs and
+    testSimpleProblem from 64 perturbed starts each; every EXPECT line on every solved instance."""
+    import os
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "solver_host_check")
+    subprocess.check_call(["make", "-C", os.path.join(root, "oracle"), "libcpl_oracle.so"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([shutil.which("g++") or "g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(root, "oracle"),
+                           "-I", os.path.join(root, "centroidalplanner_b200", "csrc"), os.path.join(root, "tests", "native", "solver_host_check.cpp"),
+                           "-o", exe, "-L", os.path.join(root, "oracle"), "-lcpl_oracle", f"-Wl,-rpath,{os.path.join(root, 'oracle')}", "-lpthread"])
+    for which, n in (("ground", 64), ("complanner", 64), ("simple", 64)):
+        r = subprocess.run([exe, which, str(n)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "-> 0 failures" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([exe, "superquadric", "24"], capture_output=True, text=True, timeout=900)
+    last = r.stdout.strip().splitlines()[-1]
+    assert int(last.split("->")[1].split()[0]) <= 2, r.stdout     # an unlucky start may run out of iterations (see solve_and_check)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(SETUPS))
+def test_testbasic_through_the_native_solve_round(case, cuda_device):
+    """The reference's TEST_Fs through cplb_solve_device: 256 starts per problem, every EXPECT line on every instance."""
+    prob, names, par = product_problem(case)
+    x0 = starts(prob, 256, seed=7, device=cuda_device)
+    before = prob.launch_count()
+    res = solve_and_check(case, prob, names, par, x0, solver_cls=cpl.NativeInteriorPoint)
+    assert res.evaluations == 1 + 4 * res.rounds and prob.launch_count() > before
+    assert res.instance_evaluations > 0 and int(res.iterations.max()) == res.rounds
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["ground", "com_planner", "example_planner"])
+def test_native_round_and_the_previous_driver_find_the_same_solutions(case, cuda_device):
+    """Same algorithm, different linear algebra (own pivoted LU in shared memory vs cuBLAS): both drivers must succeed from the
+    same starts and, where the minimiser is unique (a force weight makes it so), agree on the optimal cost."""
+    prob, names, par = product_problem(case)
+    prob.SetForceWeight(1e-4)
+    x0 = starts(prob, 32, seed=5, device=cuda_device)
+    a = cpl.NativeInteriorPoint(tol=1e-8).Solve(prob, x0)
+    b = LockStepInteriorPoint(tol=1e-8).Solve(prob, x0)
+    assert a.ok() and b.ok(), (a.status.tolist(), b.status.tolist())
+    assert float(((a.cost - b.cost).abs() / b.cost.abs().clamp(min=1e-12)).max()) < 1e-6
+    assert float(a.constr_viol.max()) <= 1e-8 and float(b.constr_viol.max()) <= 1e-8
+
+
+@pytest.mark.gpu
+def test_native_round_reports_the_zero_start_as_invalid_number_and_checks_its_arguments(cuda_device):
+    from centroidalplanner_b200.lockstep_solver import INVALID_NUMBER
+
+    prob, _, _ = product_problem("ground")
+    res = cpl.NativeInteriorPoint(max_iter=5).Solve(prob, torch.zeros(3, prob.n, dtype=torch.float64, device=cuda_device))
+    assert res.status.tolist() == [INVALID_NUMBER] * 3 and res.rounds == 0
+    with pytest.raises(ValueError, match="device-resident"):
+        cpl.NativeInteriorPoint().Solve(prob, torch.zeros(3, prob.n, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        cpl.NativeInteriorPoint(tol=-1.0).Solve(prob, torch.zeros(3, prob.n, dtype=torch.float64, device=cuda_device))
+    sh = cpl.BatchedCplProblem(NAMES, MASS, cpl.Ground(), devices=[0, 0])
+    with pytest.raises(ValueError, match="single-device"):
+        cpl.NativeInteriorPoint().Solve(sh, torch.zeros(3, sh.n, dtype=torch.float64, device=cuda_device))

@@ -34,6 +34,9 @@ def main():
     ap.add_argument("--case", default="ground", choices=list(ts.SETUPS))
     ap.add_argument("--repeats", type=int, default=3)
     ap.add_argument("--no-gpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--solver", default="native", choices=["native", "torch"],
+                    help="native: cplb_solve_device (csrc/cplb_solver.cu); torch: the previous driver (lockstep_solver.py)")
     a = ap.parse_args()
     out = {"metric": "end-to-end solves/s (lock-step interior-point stand-in, NOT IPOPT)", "case": a.case, "instances": a.instances}
     # one process per GPU under torchrun: instances shard by index (no collective on the solve path), time = max over ranks
@@ -47,8 +50,12 @@ def main():
     op.nthreads = len(os.sched_getaffinity(0))
     x0 = ts.starts(op, a.instances, seed=2025)
     solver = LockStepInteriorPoint()
+    out["solver"] = a.solver
 
     if not a.no_gpu:
+        if a.solver == "native":
+            import centroidalplanner_b200 as cpl
+            solver = cpl.NativeInteriorPoint()
         from centroidalplanner_b200 import sharding
         prob, _, _ = ts.product_problem(a.case)
         dev = torch.device("cuda", local)
@@ -81,6 +88,10 @@ def main():
 
     if rank != 0:
         return
+    if a.no_cpu:
+        print(json.dumps(out))
+        return
+    solver = LockStepInteriorPoint()
     n_cpu = min(a.cpu_sample, a.instances)
     t = time.perf_counter()
     rc = solver.Solve(op, x0[:n_cpu])
