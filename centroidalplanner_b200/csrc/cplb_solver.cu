@@ -8,8 +8,8 @@
 //   [eval]        gradient + Jacobian at N (nf + 1) points
 //   kkt           Lagrangian Hessian from the differences, assembly of the (n + m)^2 KKT matrix, pivoted LU and solve inside an
 //                 inertia-free regularisation loop, feasibility-polish step, multiplier steps, fraction-to-the-boundary
-//                 step lengths, merit-function set-up, 16 line-search candidates
-//   [eval]        constraint values + cost at N x 16 candidates
+//                 step lengths, merit-function set-up, 30 line-search candidates
+//   [eval]        constraint values + cost at N x 30 candidates
 //   ls_first      merit test of the full step; where it fails, second-order correction with the stored factors
 //   [eval]        constraint values + cost at the corrected points
 //   ls_select     first acceptable point in the order of a sequential backtracking search, iterate and multiplier update
@@ -36,7 +36,8 @@ struct DeviceTeam {
     __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 128;     // vector phases
+constexpr int kThreadsLU = 256;   // phases that factor: a 16 x 16 thread grid on the trailing update
 
 struct KernelArgs {
     Shape S;
@@ -61,16 +62,16 @@ __global__ void __launch_bounds__(kThreads) k_round_begin(const __grid_constant_
     extern __shared__ __align__(16) double smem[];
     DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
     Scratch q;
-    q.carve(smem, A.S.n, A.S.m, A.S.nnz);
+    q.carve(smem, A.S.n, A.S.m, A.S.nnz, false);
     phase_round_begin(team, A.S, A.T, A.O, (long long)blockIdx.x, q, first, last, n_active);
 }
 
-__global__ void __launch_bounds__(kThreads) k_kkt(const __grid_constant__ KernelArgs A)
+__global__ void __launch_bounds__(kThreadsLU) k_kkt(const __grid_constant__ KernelArgs A)
 {
     extern __shared__ __align__(16) double smem[];
     DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
     Scratch q;
-    q.carve(smem, A.S.n, A.S.m, A.S.nnz);
+    q.carve(smem, A.S.n, A.S.m, A.S.nnz, true);
     phase_kkt(team, A.S, A.T, A.O, (long long)blockIdx.x, q);
 }
 
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kThreads) k_ls_first(const __grid_constant__ K
     extern __shared__ __align__(16) double smem[];
     DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
     Scratch q;
-    q.carve(smem, A.S.n, A.S.m, A.S.nnz);
+    q.carve(smem, A.S.n, A.S.m, A.S.nnz, true);
     phase_ls_first(team, A.S, A.T, A.O, (long long)blockIdx.x, q);
 }
 
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) k_ls_select(const __grid_constant__ 
     extern __shared__ __align__(16) double smem[];
     DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
     Scratch q;
-    q.carve(smem, A.S.n, A.S.m, A.S.nnz);
+    q.carve(smem, A.S.n, A.S.m, A.S.nnz, false);
     phase_ls_select(team, A.S, A.T, A.O, (long long)blockIdx.x, q);
 }
 
@@ -132,7 +133,7 @@ struct DeviceEngine {
     Workspace* W;
     const double* x0;
     double *x_out, *lam_out;
-    size_t smem;
+    size_t smem, smem_small;
     cudaError_t err = cudaSuccess;
 
     void check(cudaError_t e)
@@ -150,7 +151,7 @@ struct DeviceEngine {
     void run(K kern, size_t shared, Args... args)
     {
         if (err != cudaSuccess) return;
-        kern<<<(unsigned)N, kThreads, shared, st>>>(A, args...);
+        kern<<<(unsigned)N, (const void*)kern == (const void*)k_kkt ? kThreadsLU : kThreads, shared, st>>>(A, args...);
         check(cudaGetLastError());
     }
     void init_x() { run(k_init_x, 0, x0); }
@@ -159,14 +160,14 @@ struct DeviceEngine {
     {
         if (err != cudaSuccess) return 0;
         check(cudaMemsetAsync(W->n_active, 0, sizeof(int), st));
-        run(k_round_begin, smem, (int)first, (int)last, W->n_active);
+        run(k_round_begin, smem_small, (int)first, (int)last, W->n_active);
         check(cudaMemcpyAsync(W->n_active_host, W->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
         check(cudaStreamSynchronize(st));
         return err == cudaSuccess ? *W->n_active_host : 0;
     }
     void kkt() { run(k_kkt, smem); }
     void ls_first() { run(k_ls_first, smem); }
-    void ls_select() { run(k_ls_select, smem); }
+    void ls_select() { run(k_ls_select, smem_small); }
     void finish()
     {
         run(k_finish, 0, x_out, lam_out);
@@ -254,12 +255,13 @@ cudaError_t solve_device(const CplbParams& P, int im_kernel, const ShapeHost& SH
     A.T.out_dual = dual;
 
     Scratch probe;
-    const size_t smem = probe.carve(nullptr, S.n, S.m, S.nnz) * sizeof(double);
+    const size_t smem = probe.carve(nullptr, S.n, S.m, S.nnz, true) * sizeof(double);
+    const size_t smem_small = probe.carve(nullptr, S.n, S.m, S.nnz, false) * sizeof(double);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     for (const void* k : {(const void*)k_round_begin, (const void*)k_kkt, (const void*)k_ls_first, (const void*)k_ls_select})
         SOLVER_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 
-    DeviceEngine E{P, im_kernel, A, N, st, W, x0, x_out, lam_out, smem};
+    DeviceEngine E{P, im_kernel, A, N, st, W, x0, x_out, lam_out, smem, smem_small};
     const SolveStats s = solve_loop(E, O, N, SH.nf);
     if (stats) *stats = s;
     return E.err;

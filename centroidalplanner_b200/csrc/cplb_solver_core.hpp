@@ -64,7 +64,7 @@ struct State {
     double *dx, *ds, *dlam, *dvxl, *dvxu, *dvsl, *dvsu, *h, *r_x, *r_s, *D;
     double *a_p, *a_d, *merit0, *Dm, *nu, *R0, *quad;
     int32_t *tiny, *pol, *okK, *accepted0;
-    double *lu;                                                // [N nk nk]
+    double *lu, *lu_dinv;                                      // [N nk nk], [N nk]: factors kept for the second-order correction
     int32_t* piv;                                              // [N nk]
     // widened evaluation buffers
     double *x_fd, *grad_fd, *jac_fd;                           // [N (nf+1) n], [N (nf+1) n], [N (nf+1) nnz]
@@ -102,51 +102,83 @@ CPLB_HD double push_inside(double v, double lo, double hi, bool has_lo, bool has
 }
 
 // ---- dense LU with partial pivoting of an nk x nk matrix held in team-shared memory (row-major, leading dimension ld) -------
-// piv[k] = row swapped with row k at step k (LAPACK convention).  Zero pivots are not special-cased: the divisions then
-// produce inf / NaN, the solution is non-finite and the caller's regularisation loop takes over (as with torch's lu_factor).
+// piv[k] = row swapped with row k at step k (LAPACK convention); dinv[k] = 1 / u_kk.  Zero pivots are not special-cased: the
+// reciprocal is then inf, the factors and the solution non-finite, and the caller's regularisation loop takes over (as with
+// torch's lu_factor).  Multipliers are formed as a_ik * (1 / a_kk).  Three barriers per step: pivot search (on the GPU one
+// warp, strided rows + a shuffle reduction; NaN never wins, ties go to the lowest row), row swap, trailing update on a 2-D
+// thread grid.  `cand` needs 64 doubles.
 template <class Team>
-CPLB_HD void lu_factor(const Team& team, double* A, int ld, int nk, int32_t* piv)
+CPLB_HD void lu_factor(const Team& team, double* A, int ld, int nk, int32_t* piv, double* dinv, double* cand)
 {
+    const int ntx = team.size >= 16 ? 16 : team.size, nty = team.size / ntx;
+    const int tx = team.rank % ntx, ty = team.rank / ntx;
     for (int k = 0; k < nk; k++) {
+#if defined(__CUDA_ARCH__)
+        if (team.rank < 32) {
+            int p = k;
+            double best = -1.0;
+            for (int r = k + team.rank; r < nk; r += 32) {
+                const double v = dabs(A[r * ld + k]);
+                if (v > best) {
+                    best = v;
+                    p = r;
+                }
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ob = __shfl_down_sync(0xffffffffu, best, off);
+                const int op = __shfl_down_sync(0xffffffffu, p, off);
+                if (ob > best || (ob == best && op < p)) {
+                    best = ob;
+                    p = op;
+                }
+            }
+            if (team.rank == 0) {
+                piv[k] = p;
+                dinv[k] = 1.0 / A[p * ld + k];
+            }
+        }
+#else
+        (void)cand;
         if (team.rank == 0) {
             int p = k;
-            double best = dabs(A[k * ld + k]);
-            for (int i = k + 1; i < nk; i++) {
-                const double v = dabs(A[i * ld + k]);
-                if (v > best) {  // NaN never wins: a NaN column keeps p = k and poisons the row
+            double best = -1.0;
+            for (int r = k; r < nk; r++) {
+                const double v = dabs(A[r * ld + k]);
+                if (v > best) {
                     best = v;
-                    p = i;
+                    p = r;
                 }
             }
             piv[k] = p;
+            dinv[k] = 1.0 / A[p * ld + k];
         }
+#endif
         team.sync();
         const int p = piv[k];
         if (p != k)
-            for (int j = team.rank; j < nk; j += team.size) {
-                const double t = A[k * ld + j];
-                A[k * ld + j] = A[p * ld + j];
-                A[p * ld + j] = t;
+            for (int c = team.rank; c < nk; c += team.size) {
+                const double t = A[k * ld + c];
+                A[k * ld + c] = A[p * ld + c];
+                A[p * ld + c] = t;
             }
         team.sync();
-        const double pivot = A[k * ld + k];
-        for (int i = k + 1 + team.rank; i < nk; i += team.size) A[i * ld + k] = A[i * ld + k] / pivot;
-        team.sync();
-        // trailing update on a 2-D thread grid (16 columns wide): no integer division per element
-        const int ntx = team.size >= 16 ? 16 : team.size, nty = team.size / ntx;
-        const int tx = team.rank % ntx, ty = team.rank / ntx;
+        const double rp = dinv[k];
         if (ty < nty)
-            for (int i = k + 1 + ty; i < nk; i += nty) {
-                const double lik = A[i * ld + k];
-                for (int j = k + 1 + tx; j < nk; j += ntx) A[i * ld + j] = A[i * ld + j] - lik * A[k * ld + j];
+            for (int r = k + 1 + ty; r < nk; r += nty) {
+                const double lik = A[r * ld + k] * rp;
+                for (int c = k + 1 + tx; c < nk; c += ntx) A[r * ld + c] = A[r * ld + c] - lik * A[k * ld + c];
             }
         team.sync();
+        // the multipliers themselves (column k below the diagonal), after every reader of a_ik is done; the two barriers of the
+        // next step's pivot search and swap order these writes before any later access to column k
+        for (int r = k + 1 + team.rank; r < nk; r += team.size) A[r * ld + k] = A[r * ld + k] * rp;
     }
+    team.sync();
 }
 
-// solves A y = b in place (b -> y) with the factors of lu_factor
+// solves A y = b in place (b -> y) with the factors of lu_factor; one barrier per substitution step
 template <class Team>
-CPLB_HD void lu_solve(const Team& team, const double* A, int ld, int nk, const int32_t* piv, double* b)
+CPLB_HD void lu_solve(const Team& team, const double* A, int ld, int nk, const int32_t* piv, const double* dinv, double* b)
 {
     if (team.rank == 0)
         for (int k = 0; k < nk; k++) {
@@ -160,25 +192,28 @@ CPLB_HD void lu_solve(const Team& team, const double* A, int ld, int nk, const i
     team.sync();
     for (int k = 0; k < nk; k++) {  // L y = P b (unit lower triangle)
         const double yk = b[k];
-        for (int i = k + 1 + team.rank; i < nk; i += team.size) b[i] = b[i] - A[i * ld + k] * yk;
+        for (int r = k + 1 + team.rank; r < nk; r += team.size) b[r] = b[r] - A[r * ld + k] * yk;
         team.sync();
     }
-    for (int k = nk - 1; k >= 0; k--) {  // U x = y
-        if (team.rank == 0) b[k] = b[k] / A[k * ld + k];
+    for (int k = nk - 1; k >= 0; k--) {  // U x = y: every thread forms x_k itself, thread 0 stores it
+        const double xk = b[k] * dinv[k];
+        for (int r = team.rank; r < k; r += team.size) b[r] = b[r] - A[r * ld + k] * xk;
         team.sync();
-        const double xk = b[k];
-        for (int i = team.rank; i < k; i += team.size) b[i] = b[i] - A[i * ld + k] * xk;
-        team.sync();
+        if (team.rank == 0) b[k] = xk;
     }
+    team.sync();
 }
 
-// shared scratch of one team, carved out of one block of doubles (shared memory on the GPU)
+// shared scratch of one team, carved out of one block of doubles (shared memory on the GPU).  `full` = with the KKT matrix, the
+// dense Jacobian and the Hessian (phase_kkt, phase_ls_first); the other phases only need the vectors.
 struct Scratch {
-    double *K, *rhs, *sol, *Jd, *H0, *gxl, *gxu, *gsl, *gsu, *sigx, *sigs, *w, *glb, *tmp, *red;
+    double *K, *rhs, *sol, *Jd, *H0, *w, *glb;                       // full only
+    double *gxl, *gxu, *gsl, *gsu, *sigx, *sigs, *dx, *ds, *dl, *e, *red, *dinv;
     int32_t* piv;
     int ld;
+    static constexpr int kTerms = 8;  // per-element term arrays in `e` (kTerms x nk)
     // returns the number of doubles used; base may be nullptr (size query)
-    CPLB_HD size_t carve(double* base, int n, int m, int nnz)
+    CPLB_HD size_t carve(double* base, int n, int m, int nnz, bool full)
     {
         const int nk = n + m;
         ld = nk | 1;
@@ -188,24 +223,32 @@ struct Scratch {
             o += count;
             return p;
         };
-        K = take((size_t)nk * ld);
-        rhs = take(nk);
-        sol = take(nk);
-        Jd = take((size_t)m * n);
-        H0 = take((size_t)n * n);
         gxl = take(n);
         gxu = take(n);
         sigx = take(n);
-        glb = take(n);
+        dx = take(n);
         gsl = take(m);
         gsu = take(m);
         sigs = take(m);
-        w = take(nnz);
-        tmp = take(2 * (size_t)nk);
-        red = take(64);
+        ds = take(m);
+        dl = take(m);
+        e = take((size_t)kTerms * nk);
+        red = take(96);
+        dinv = take(nk);
         piv = reinterpret_cast<int32_t*>(take(((size_t)nk + 1) / 2));
+        K = rhs = sol = Jd = H0 = w = glb = nullptr;
+        if (full) {
+            K = take((size_t)nk * ld);
+            rhs = take(nk);
+            sol = take(nk);
+            Jd = take((size_t)m * n);
+            H0 = take((size_t)n * n);
+            w = take(nnz);
+            glb = take(n);
+        }
         return o;
     }
+    CPLB_HD double* term(int t, int nk) const { return e + (size_t)t * nk; }
 };
 
 // gaps to the bounds at (x, s) (1.0 where there is no bound)
@@ -234,7 +277,6 @@ CPLB_HD void dense_jacobian(const Team& team, const Shape& S, const double* jv, 
     }
 }
 
-
 // ---- per-instance pointers ---------------------------------------------------------------------------------------------------
 struct Inst {
     const Shape& S;
@@ -244,7 +286,6 @@ struct Inst {
     CPLB_HD double* vm(double* base) const { return base + i * S.m; }
 };
 
-// sequential dot-style helpers (one thread); sizes are tiny
 CPLB_HD double scaled_df(const Inst& I, int j) { return I.S.fixed[j] ? 0.0 : I.T.dobj[I.i] * I.T.df[I.i * I.S.n + j]; }
 
 // (J^T lam)_j with the scaled Jacobian; fixed columns contribute nothing
@@ -262,67 +303,22 @@ CPLB_HD double jt_lam(const Inst& I, int j, const double* lam)
     return acc;
 }
 
-struct Residuals {
-    double dual, prim, sd;
-};
-
-// Scaled optimality error of Waechter & Biegler eq. (5) without its mu-dependent part (kkt_residuals of the Python driver);
-// needs q.gxl .. q.gsu.  One thread.
-CPLB_HD Residuals kkt_residuals(const Inst& I, const Scratch& q)
+// thread 0 helpers over team-shared term arrays
+CPLB_HD double arr_nanmax(const double* a, int count, double init)
 {
-    const Shape& S = I.S;
-    const State& T = I.T;
-    const double *lam = I.vm(T.lam), *vxl = I.vn(T.vxl), *vxu = I.vn(T.vxu), *vsl = I.vm(T.vsl), *vsu = I.vm(T.vsu);
-    const double *c = I.vm(T.c), *s = I.vm(T.s), *dc = I.vm(T.dc);
-    double rmax = 0.0, sum = 0.0, prim = 0.0;
-    for (int j = 0; j < S.n; j++) {
-        const double rx = S.fixed[j] ? 0.0 : (scaled_df(I, j) + jt_lam(I, j, lam) - vxl[j] + vxu[j]);
-        rmax = nanmax(rmax, dabs(rx));
-        sum += vxl[j] + vxu[j];
-    }
-    for (int r = 0; r < S.m; r++) {
-        const double rs = S.is_eq[r] ? 0.0 : (-lam[r] - vsl[r] + vsu[r]);
-        rmax = nanmax(rmax, dabs(rs));
-        sum += dabs(lam[r]) + vsl[r] + vsu[r];
-        prim = nanmax(prim, dabs(dc[r] * c[r] - s[r]));
-    }
-    Residuals R;
-    R.sd = clamp_min(sum / (double)(S.m + 2 * S.n + 2 * S.m), 100.0) / 100.0;
-    R.dual = rmax / R.sd;
-    R.prim = prim;
-    return R;
+    for (int e = 0; e < count; e++) init = nanmax(init, a[e]);
+    return init;
 }
-
-// max |(gap * multiplier - mu)| over the bounded components, / sd
-CPLB_HD double complementarity(const Inst& I, const Scratch& q, double sd, double mu)
+CPLB_HD double arr_nanmin(const double* a, int count, double init)
 {
-    const Shape& S = I.S;
-    const State& T = I.T;
-    const double *vxl = I.vn(T.vxl), *vxu = I.vn(T.vxu), *vsl = I.vm(T.vsl), *vsu = I.vm(T.vsu);
-    double e = 0.0;
-    for (int j = 0; j < S.n; j++) {
-        if (S.x_lo[j]) e = nanmax(e, dabs(q.gxl[j] * vxl[j] - mu));
-        if (S.x_hi[j]) e = nanmax(e, dabs(q.gxu[j] * vxu[j] - mu));
-    }
-    for (int r = 0; r < S.m; r++) {
-        if (S.s_lo[r]) e = nanmax(e, dabs(q.gsl[r] * vsl[r] - mu));
-        if (S.s_hi[r]) e = nanmax(e, dabs(q.gsu[r] * vsu[r] - mu));
-    }
-    return e / sd;
+    for (int e = 0; e < count; e++) init = nanmin(init, a[e]);
+    return init;
 }
-
-// max unscaled violation of the (relaxed) row bounds
-CPLB_HD double row_violation(const Inst& I)
+CPLB_HD double arr_sum(const double* a, int count)
 {
-    const Shape& S = I.S;
-    const State& T = I.T;
-    const double *c = I.vm(T.c), *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su);
-    double v = 0.0;
-    for (int r = 0; r < S.m; r++) {
-        const double cs = dc[r] * c[r];
-        v = nanmax(v, (clamp_min(sl[r] - cs, 0.0) + clamp_min(cs - su[r], 0.0)) / dc[r]);
-    }
-    return v;
+    double acc = 0.0;
+    for (int e = 0; e < count; e++) acc += a[e];
+    return acc;
 }
 
 // ---- phase 0a: project the starting point (before the first evaluation) ------------------------------------------------------
@@ -400,78 +396,111 @@ CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T,
                                int last_round, int* n_active)
 {
     Inst I{S, T, i};
+    const int n = S.n, m = S.m, nk = S.nk;
+    if (T.status[i] >= 0) {  // finished earlier
+        if (team.rank == 0) T.active[i] = 0;
+        return;
+    }
     double *x = I.vn(T.x), *s = I.vm(T.s);
-    compute_gaps(team, S, x, s, I.vm(T.sl), I.vm(T.su), q);
+    double *vxl = I.vn(T.vxl), *vxu = I.vn(T.vxu), *vsl = I.vm(T.vsl), *vsu = I.vm(T.vsu);
+    const double *lam = I.vm(T.lam), *c = I.vm(T.c), *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su);
+    compute_gaps(team, S, x, s, sl, su, q);
     team.sync();
-    const bool was_active = T.status[i] < 0;
-    if (!first_round && T.active[i]) {
-        // kappa_sigma safeguard (Waechter & Biegler eq. 16) with the gaps at the new point
-        const double mu = T.mu[i], ks = 1e10;
-        for (int j = team.rank; j < S.n; j += team.size) {
-            double* vxl = I.vn(T.vxl);
-            double* vxu = I.vn(T.vxu);
-            vxl[j] = S.x_lo[j] ? nanmin(nanmax(vxl[j], mu / (ks * q.gxl[j])), ks * mu / q.gxl[j]) : 0.0;
-            vxu[j] = S.x_hi[j] ? nanmin(nanmax(vxu[j], mu / (ks * q.gxu[j])), ks * mu / q.gxu[j]) : 0.0;
+    // term arrays: 0 |residual|, 1 multiplier sums, 2 primal infeasibility / row violation, 3..6 gap x multiplier products
+    double *t_res = q.term(0, nk), *t_sum = q.term(1, nk), *t_prim = q.term(2, nk), *t_viol = q.term(3, nk);
+    double *p_xl = q.term(4, nk), *p_xu = q.term(5, nk), *p_sl = q.term(6, nk), *p_su = q.term(7, nk);
+    const double mu_old = T.mu[i], ks = 1e10;
+    for (int j = team.rank; j < n; j += team.size) {
+        double a = vxl[j], b = vxu[j];
+        if (!first_round) {  // kappa_sigma safeguard (Waechter & Biegler eq. 16) with the gaps at the new point
+            a = S.x_lo[j] ? nanmin(nanmax(a, mu_old / (ks * q.gxl[j])), ks * mu_old / q.gxl[j]) : 0.0;
+            b = S.x_hi[j] ? nanmin(nanmax(b, mu_old / (ks * q.gxu[j])), ks * mu_old / q.gxu[j]) : 0.0;
+            vxl[j] = a;
+            vxu[j] = b;
         }
-        for (int r = team.rank; r < S.m; r += team.size) {
-            double* vsl = I.vm(T.vsl);
-            double* vsu = I.vm(T.vsu);
-            vsl[r] = S.s_lo[r] ? nanmin(nanmax(vsl[r], mu / (ks * q.gsl[r])), ks * mu / q.gsl[r]) : 0.0;
-            vsu[r] = S.s_hi[r] ? nanmin(nanmax(vsu[r], mu / (ks * q.gsu[r])), ks * mu / q.gsu[r]) : 0.0;
+        const double rx = S.fixed[j] ? 0.0 : (scaled_df(I, j) + jt_lam(I, j, lam) - a + b);
+        t_res[j] = dabs(rx);
+        t_sum[j] = a + b;
+        p_xl[j] = S.x_lo[j] ? q.gxl[j] * a : -1.0;  // -1: no bound (products are >= 0 otherwise)
+        p_xu[j] = S.x_hi[j] ? q.gxu[j] * b : -1.0;
+    }
+    for (int r = team.rank; r < m; r += team.size) {
+        double a = vsl[r], b = vsu[r];
+        if (!first_round) {
+            a = S.s_lo[r] ? nanmin(nanmax(a, mu_old / (ks * q.gsl[r])), ks * mu_old / q.gsl[r]) : 0.0;
+            b = S.s_hi[r] ? nanmin(nanmax(b, mu_old / (ks * q.gsu[r])), ks * mu_old / q.gsu[r]) : 0.0;
+            vsl[r] = a;
+            vsu[r] = b;
         }
+        const double rs = S.is_eq[r] ? 0.0 : (-lam[r] - a + b);
+        const double cs = dc[r] * c[r];
+        t_res[n + r] = dabs(rs);
+        t_sum[n + r] = dabs(lam[r]) + a + b;
+        t_prim[r] = dabs(cs - s[r]);
+        t_viol[r] = (clamp_min(sl[r] - cs, 0.0) + clamp_min(cs - su[r], 0.0)) / dc[r];
+        p_sl[r] = S.s_lo[r] ? q.gsl[r] * a : -1.0;
+        p_su[r] = S.s_hi[r] ? q.gsu[r] * b : -1.0;
     }
     team.sync();
     if (team.rank == 0) {
-        int active = 0;
-        if (was_active) {
-            const Residuals R = kkt_residuals(I, q);
-            const double comp0 = complementarity(I, q, R.sd, 0.0);
-            const double E0 = nanmax(nanmax(R.dual, R.prim), comp0);
-            const double vmax = row_violation(I);
-            // IPOPT's test (scaled error <= tol, unscaled violation <= constr_viol_tol) switches the instance to the feasibility
-            // polish; it is done when the constraints hold to polish_viol_tol as well
-            if (E0 <= O.tol && vmax <= O.constr_viol_tol) T.polish[i] = 1;
-            if (T.polish[i] && vmax <= O.polish_viol_tol) T.status[i] = kSuccess;
-            else if (!finite_d(E0)) T.status[i] = kInvalidNumber;
-            T.out_dual[i] = R.dual;
-            T.out_viol[i] = vmax;
-            active = T.status[i] < 0;
-            if (active && last_round) {
-                T.status[i] = kMaxIter;
-                active = 0;
+        const double sd = clamp_min(arr_sum(t_sum, nk) / (double)(m + 2 * n + 2 * m), 100.0) / 100.0;
+        const double dual = arr_nanmax(t_res, nk, 0.0) / sd, prim = arr_nanmax(t_prim, m, 0.0);
+        auto comp = [&](double mu) {  // max |gap x multiplier - mu| over the bounded components, / sd
+            double e = 0.0;
+            for (int j = 0; j < n; j++) {
+                if (p_xl[j] != -1.0) e = nanmax(e, dabs(p_xl[j] - mu));
+                if (p_xu[j] != -1.0) e = nanmax(e, dabs(p_xu[j] - mu));
             }
-            if (active) {
-                T.iters[i] += 1;
-                // monotone barrier update (Waechter & Biegler eq. 7)
-                double mu = T.mu[i];
-                const double dp0 = nanmax(R.dual, R.prim);
-                for (int rep = 0; rep < 4; rep++) {
-                    const double Emu = nanmax(dp0, complementarity(I, q, R.sd, mu));
-                    if (Emu <= 10.0 * mu && mu > O.tol / 10.0) mu = dmax(dmin(0.2 * mu, pow(mu, 1.5)), O.tol / 10.0);
-                }
-                T.mu[i] = mu;
-                T.tau[i] = dmax(1.0 - mu, 0.99);
+            for (int r = 0; r < m; r++) {
+                if (p_sl[r] != -1.0) e = nanmax(e, dabs(p_sl[r] - mu));
+                if (p_su[r] != -1.0) e = nanmax(e, dabs(p_su[r] - mu));
             }
+            return e / sd;
+        };
+        const double E0 = nanmax(nanmax(dual, prim), comp(0.0));
+        const double vmax = arr_nanmax(t_viol, m, 0.0);
+        // IPOPT's test (scaled error <= tol, unscaled violation <= constr_viol_tol) switches the instance to the feasibility
+        // polish; it is done when the constraints hold to polish_viol_tol as well
+        if (E0 <= O.tol && vmax <= O.constr_viol_tol) T.polish[i] = 1;
+        if (T.polish[i] && vmax <= O.polish_viol_tol) T.status[i] = kSuccess;
+        else if (!finite_d(E0)) T.status[i] = kInvalidNumber;
+        T.out_dual[i] = dual;
+        T.out_viol[i] = vmax;
+        int active = T.status[i] < 0;
+        if (active && last_round) {
+            T.status[i] = kMaxIter;
+            active = 0;
         }
-        T.active[i] = active;
         if (active) {
+            T.iters[i] += 1;
+            // monotone barrier update (Waechter & Biegler eq. 7)
+            double mu = mu_old;
+            const double dp0 = nanmax(dual, prim);
+            for (int rep = 0; rep < 4; rep++) {
+                const double Emu = nanmax(dp0, comp(mu));
+                if (Emu <= 10.0 * mu && mu > O.tol / 10.0) mu = dmax(dmin(0.2 * mu, pow(mu, 1.5)), O.tol / 10.0);
+            }
+            T.mu[i] = mu;
+            T.tau[i] = dmax(1.0 - mu, 0.99);
 #if defined(__CUDA_ARCH__)
             atomicAdd(n_active, 1);
 #else
             *n_active += 1;
 #endif
         }
+        T.active[i] = active;
+        q.red[0] = (double)active;
     }
     team.sync();
     // forward-difference points of the Lagrangian Hessian: point a < nf perturbs free variable a, point nf is x itself
-    if (T.active[i]) {
-        double* X = T.x_fd + i * (long long)(S.nf + 1) * S.n;
-        for (int e = team.rank; e < (S.nf + 1) * S.n; e += team.size) {
-            const int a = e / S.n, j = e - a * S.n;
-            double v = x[j];
-            if (a < S.nf && S.free_idx[a] == j) v += 1e-7 * dmax(dabs(v), 1.0);
-            X[e] = v;
-        }
+    if (q.red[0] != 0.0) {
+        double* X = T.x_fd + i * (long long)(S.nf + 1) * n;
+        for (int a = 0; a <= S.nf; a++)
+            for (int j = team.rank; j < n; j += team.size) {
+                double v = x[j];
+                if (a < S.nf && S.free_idx[a] == j) v += 1e-7 * dmax(dabs(v), 1.0);
+                X[a * n + j] = v;
+            }
     }
 }
 
@@ -484,13 +513,16 @@ CPLB_HD void phase_kkt(const Team& team, const Shape& S, const State& T, const O
     double* Xls = T.x_ls + i * (long long)kCandidates * n;
     double *x = I.vn(T.x), *s = I.vm(T.s);
     if (!T.active[i]) {  // finished instances keep feeding finite points to the widened evaluations
-        for (int e = team.rank; e < kCandidates * n; e += team.size) Xls[e] = x[e % n];
+        for (int k = 0; k < kCandidates; k++)
+            for (int j = team.rank; j < n; j += team.size) Xls[k * n + j] = x[j];
         return;
     }
     const double *lam = I.vm(T.lam), *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su);
     const double *vxl = I.vn(T.vxl), *vxu = I.vn(T.vxu), *vsl = I.vm(T.vsl), *vsu = I.vm(T.vsu), *c = I.vm(T.c);
     const double mu = T.mu[i], tau = T.tau[i], dobj = T.dobj[i];
-    double *dx = I.vn(T.dx), *ds = I.vm(T.ds), *dlam = I.vm(T.dlam), *h = I.vm(T.h), *r_x = I.vn(T.r_x), *r_s = I.vm(T.r_s), *D = I.vm(T.D);
+    double *h = I.vm(T.h), *r_x = I.vn(T.r_x), *r_s = I.vm(T.r_s), *D = I.vm(T.D);
+    // shared copies of what the dense phases read repeatedly: term arrays 0 = r_x | r_s (nk), 1 = h (m) | D (m at +m... separate), see below
+    double *s_rx = q.term(0, nk), *s_rs = s_rx + n, *s_h = q.term(1, nk), *s_D = q.term(2, nk);
 
     compute_gaps(team, S, x, s, sl, su, q);
     dense_jacobian(team, S, T.jv + i * S.nnz, dc, q.Jd);
@@ -508,104 +540,116 @@ CPLB_HD void phase_kkt(const Team& team, const Shape& S, const State& T, const O
         return acc;
     };
     for (int j = team.rank; j < n; j += team.size) q.glb[j] = grad_lagrangian(S.nf, j);
-    for (int e = team.rank; e < n * n; e += team.size) q.H0[e] = 0.0;
     team.sync();
-    for (int e = team.rank; e < S.nf * n; e += team.size) {
-        const int a = e / n, j = e - a * n;
-        const double eps = 1e-7 * dmax(dabs(x[S.free_idx[a]]), 1.0);
-        q.K[S.free_idx[a] * ld + j] = S.fixed[j] ? 0.0 : (grad_lagrangian(a, j) - q.glb[j]) / eps;  // K's top-left block as staging
+    {
+        // thread grid (rows a, columns j): K's top-left block is the staging area for Hc
+        const int ntx = team.size >= 32 ? 32 : team.size, nty = team.size / ntx;
+        const int tx = team.rank % ntx, ty = team.rank / ntx;
+        if (ty < nty)
+            for (int a = ty; a < S.nf; a += nty) {
+                const int row = S.free_idx[a];
+                const double eps = 1e-7 * dmax(dabs(x[row]), 1.0);
+                for (int j = tx; j < n; j += ntx) q.K[row * ld + j] = S.fixed[j] ? 0.0 : (grad_lagrangian(a, j) - q.glb[j]) / eps;
+            }
     }
-    team.sync();
-    // W = (Hc + Hc^T) / 2 on the free variables;  H0 = W + diag(sigma_x on the free ones, 1 on the fixed ones)
     for (int j = team.rank; j < n; j += team.size) q.sigx[j] = (S.x_lo[j] ? vxl[j] / q.gxl[j] : 0.0) + (S.x_hi[j] ? vxu[j] / q.gxu[j] : 0.0);
     for (int r = team.rank; r < m; r += team.size) q.sigs[r] = (S.s_lo[r] ? vsl[r] / q.gsl[r] : 0.0) + (S.s_hi[r] ? vsu[r] / q.gsu[r] : 0.0);
     team.sync();
-    for (int e = team.rank; e < n * n; e += team.size) {
-        const int a = e / n, b = e - a * n;
-        double v = 0.0;
-        if (!S.fixed[a] && !S.fixed[b]) v = 0.5 * (q.K[a * ld + b] + q.K[b * ld + a]);
-        if (a == b) v += S.fixed[a] ? 1.0 : q.sigx[a];
-        q.H0[e] = v;
-    }
+    // W = (Hc + Hc^T) / 2 on the free variables;  H0 = W + diag(sigma_x on the free ones, 1 on the fixed ones)
+    for (int a = 0; a < n; a++)
+        for (int b = team.rank; b < n; b += team.size) {
+            double v = 0.0;
+            if (!S.fixed[a] && !S.fixed[b]) v = 0.5 * (q.K[a * ld + b] + q.K[b * ld + a]);
+            if (a == b) v += S.fixed[a] ? 1.0 : q.sigx[a];
+            q.H0[a * n + b] = v;
+        }
     // residuals of the barrier problem
     for (int j = team.rank; j < n; j += team.size)
-        r_x[j] = S.fixed[j] ? 0.0
-                            : (scaled_df(I, j) + jt_lam(I, j, lam) - (S.x_lo[j] ? mu / q.gxl[j] : 0.0) + (S.x_hi[j] ? mu / q.gxu[j] : 0.0));
+        s_rx[j] = S.fixed[j] ? 0.0
+                             : (scaled_df(I, j) + jt_lam(I, j, lam) - (S.x_lo[j] ? mu / q.gxl[j] : 0.0) + (S.x_hi[j] ? mu / q.gxu[j] : 0.0));
     for (int r = team.rank; r < m; r += team.size) {
-        r_s[r] = S.is_eq[r] ? 0.0 : (-lam[r] - (S.s_lo[r] ? mu / q.gsl[r] : 0.0) + (S.s_hi[r] ? mu / q.gsu[r] : 0.0));
-        h[r] = dc[r] * c[r] - s[r];
-        D[r] = S.is_eq[r] ? 0.0 : 1.0 / clamp_min(q.sigs[r], 1e-300);
+        s_rs[r] = S.is_eq[r] ? 0.0 : (-lam[r] - (S.s_lo[r] ? mu / q.gsl[r] : 0.0) + (S.s_hi[r] ? mu / q.gsu[r] : 0.0));
+        s_h[r] = dc[r] * c[r] - s[r];
+        s_D[r] = S.is_eq[r] ? 0.0 : 1.0 / clamp_min(q.sigs[r], 1e-300);
     }
     team.sync();
+    for (int j = team.rank; j < n; j += team.size) r_x[j] = s_rx[j];  // kept for the second-order correction
+    for (int r = team.rank; r < m; r += team.size) {
+        r_s[r] = s_rs[r];
+        h[r] = s_h[r];
+        D[r] = s_D[r];
+    }
     const double delta_c = 1e-8 * pow(mu, 0.25);
+    double* t_dx = q.term(3, nk);   // candidate step [dx | ds]
+    double* t_hdx = q.term(4, nk);  // H dx
 
     // inertia-free regularisation (Chiang & Zavala 2016): raise delta_w until the step sees positive curvature
     double delta = T.delta_lm[i];
     for (int reg = 0; reg < kMaxReg; reg++) {
         // K = [[H0 + delta I_free, Jf^T], [Jf, -(D + delta_c)]],  rhs = [-r_x, -h - D r_s]
-        for (int e = team.rank; e < nk * nk; e += team.size) {
-            const int a = e / nk, b = e - a * nk;
-            double v;
-            if (a < n && b < n) v = q.H0[a * n + b] + ((a == b && !S.fixed[a]) ? delta : 0.0);
-            else if (a < n) v = q.Jd[(b - n) * n + a];
-            else if (b < n) v = q.Jd[(a - n) * n + b];
-            else v = (a == b) ? -(D[a - n] + delta_c) : 0.0;
-            q.K[a * ld + b] = v;
-        }
-        for (int a = team.rank; a < nk; a += team.size) q.rhs[a] = a < n ? -r_x[a] : -h[a - n] - D[a - n] * r_s[a - n];
+        if (team.rank == 0) q.red[0] = 1.0;
         team.sync();
-        if (team.rank == 0) {
-            bool ok = true;
-            for (int a = 0; a < nk && ok; a++) {
-                if (!finite_d(q.rhs[a])) ok = false;
-                for (int b = 0; b < nk && ok; b++)
-                    if (!finite_d(q.K[a * ld + b])) ok = false;
+        bool fin = true;
+        for (int a = 0; a < nk; a++)
+            for (int b = team.rank; b < nk; b += team.size) {
+                double v;
+                if (a < n && b < n) v = q.H0[a * n + b] + ((a == b && !S.fixed[a]) ? delta : 0.0);
+                else if (a < n) v = q.Jd[(b - n) * n + a];
+                else if (b < n) v = q.Jd[(a - n) * n + b];
+                else v = (a == b) ? -(s_D[a - n] + delta_c) : 0.0;
+                q.K[a * ld + b] = v;
+                fin = fin && finite_d(v);
             }
-            q.red[0] = ok ? 1.0 : 0.0;
+        for (int a = team.rank; a < nk; a += team.size) {
+            const double v = a < n ? -s_rx[a] : -s_h[a - n] - s_D[a - n] * s_rs[a - n];
+            q.rhs[a] = v;
+            fin = fin && finite_d(v);
         }
+        if (!fin) q.red[0] = 0.0;
         team.sync();
         const bool okK = q.red[0] != 0.0;
         if (!okK) {  // identity system, zero right-hand side: a zero step (the Python driver's eyeK)
-            for (int e = team.rank; e < nk * nk; e += team.size) q.K[(e / nk) * ld + e % nk] = (e / nk == e % nk) ? 1.0 : 0.0;
+            for (int a = 0; a < nk; a++)
+                for (int b = team.rank; b < nk; b += team.size) q.K[a * ld + b] = (a == b) ? 1.0 : 0.0;
             for (int a = team.rank; a < nk; a += team.size) q.rhs[a] = 0.0;
             team.sync();
         }
-        lu_factor(team, q.K, ld, nk, q.piv);
+        lu_factor(team, q.K, ld, nk, q.piv, q.dinv, q.red + 16);
         for (int a = team.rank; a < nk; a += team.size) q.sol[a] = q.rhs[a];
         team.sync();
-        lu_solve(team, q.K, ld, nk, q.piv, q.sol);
+        lu_solve(team, q.K, ld, nk, q.piv, q.dinv, q.sol);
         // candidate step and the curvature it sees
-        for (int j = team.rank; j < n; j += team.size) q.tmp[j] = S.fixed[j] ? 0.0 : q.sol[j];                    // dx_t
-        for (int r = team.rank; r < m; r += team.size) q.tmp[n + r] = S.is_eq[r] ? 0.0 : D[r] * (q.sol[n + r] - r_s[r]);  // ds_t
+        for (int j = team.rank; j < n; j += team.size) t_dx[j] = S.fixed[j] ? 0.0 : q.sol[j];
+        for (int r = team.rank; r < m; r += team.size) t_dx[n + r] = S.is_eq[r] ? 0.0 : s_D[r] * (q.sol[n + r] - s_rs[r]);
         team.sync();
         for (int j = team.rank; j < n; j += team.size) {  // (H dx)_j, H = H0 + delta on the free diagonal
             double acc = 0.0;
-            for (int b = 0; b < n; b++) acc += (q.H0[j * n + b] + ((j == b && !S.fixed[j]) ? delta : 0.0)) * q.tmp[b];
-            q.tmp[nk + j] = acc;
+            for (int b = 0; b < n; b++) acc += (q.H0[j * n + b] + ((j == b && !S.fixed[j]) ? delta : 0.0)) * t_dx[b];
+            t_hdx[j] = acc;
         }
         team.sync();
         if (team.rank == 0) {
-            bool fin = true;
+            bool sfin = true;
             double quad = 0.0, nrm = 0.0;
-            for (int a = 0; a < nk; a++) fin = fin && finite_d(q.sol[a]);
+            for (int a = 0; a < nk; a++) sfin = sfin && finite_d(q.sol[a]);
             for (int j = 0; j < n; j++) {
-                quad += q.tmp[j] * q.tmp[nk + j];
-                nrm += q.tmp[j] * q.tmp[j];
+                quad += t_dx[j] * t_hdx[j];
+                nrm += t_dx[j] * t_dx[j];
             }
             for (int r = 0; r < m; r++) {
-                quad += q.sigs[r] * q.tmp[n + r] * q.tmp[n + r];
-                nrm += q.tmp[n + r] * q.tmp[n + r];
+                quad += q.sigs[r] * t_dx[n + r] * t_dx[n + r];
+                nrm += t_dx[n + r] * t_dx[n + r];
             }
-            const bool good = fin && quad >= 1e-8 * nrm;
+            const bool good = sfin && quad >= 1e-8 * nrm;
             q.red[1] = (good || reg == kMaxReg - 1) ? 1.0 : 0.0;
             q.red[2] = quad;
         }
         team.sync();
         if (q.red[1] != 0.0) {
-            for (int j = team.rank; j < n; j += team.size) dx[j] = q.tmp[j];
+            for (int j = team.rank; j < n; j += team.size) q.dx[j] = t_dx[j];
             for (int r = team.rank; r < m; r += team.size) {
-                ds[r] = q.tmp[n + r];
-                dlam[r] = q.sol[n + r];
+                q.ds[r] = t_dx[n + r];
+                q.dl[r] = q.sol[n + r];
             }
             if (team.rank == 0) {
                 T.quad[i] = q.red[2];
@@ -618,63 +662,109 @@ CPLB_HD void phase_kkt(const Team& team, const Shape& S, const State& T, const O
         team.sync();
     }
     team.sync();
+    const double quad = q.red[2];
     // the factors stay for the second-order correction
     {
         double* LU = T.lu + i * (long long)nk * nk;
-        for (int e = team.rank; e < nk * nk; e += team.size) LU[e] = q.K[(e / nk) * ld + e % nk];
-        for (int a = team.rank; a < nk; a += team.size) T.piv[i * nk + a] = q.piv[a];
+        for (int a = 0; a < nk; a++)
+            for (int b = team.rank; b < nk; b += team.size) LU[a * nk + b] = q.K[a * ld + b];
+        for (int a = team.rank; a < nk; a += team.size) {
+            T.piv[i * nk + a] = q.piv[a];
+            T.lu_dinv[i * nk + a] = q.dinv[a];
+        }
     }
     if (team.rank == 0) {
         bool bad = false;
-        for (int j = 0; j < n; j++) bad = bad || !finite_d(dx[j]);
-        for (int r = 0; r < m; r++) bad = bad || !finite_d(dlam[r]);
+        for (int j = 0; j < n; j++) bad = bad || !finite_d(q.dx[j]);
+        for (int r = 0; r < m; r++) bad = bad || !finite_d(q.dl[r]);
         q.red[3] = bad ? 1.0 : 0.0;
     }
     team.sync();
     if (q.red[3] != 0.0) {
-        for (int j = team.rank; j < n; j += team.size) dx[j] = 0.0;
-        for (int r = team.rank; r < m; r += team.size) ds[r] = dlam[r] = 0.0;
+        for (int j = team.rank; j < n; j += team.size) q.dx[j] = 0.0;
+        for (int r = team.rank; r < m; r += team.size) q.ds[r] = q.dl[r] = 0.0;
+        team.sync();
+    }
+
+    // multiplier steps and the fraction-to-the-boundary limit of the dual step (with the Newton step, also for polishing instances:
+    // their dual step length is zero anyway); merit-function quantities of the Newton step
+    double *dvxl = I.vn(T.dvxl), *dvxu = I.vn(T.dvxu), *dvsl = I.vm(T.dvsl), *dvsu = I.vm(T.dvsu);
+    double *t_ad = q.term(3, nk), *t_lb = q.term(4, nk), *t_dphi = q.term(5, nk), *t_h1 = q.term(6, nk), *t_lmax = q.term(7, nk);
+    auto ms = [&](double val, double dval, bool mask, double cur) {  // largest a with val + a dval >= (1 - tau) val
+        if (mask && dval < 0) cur = nanmin(cur, -tau * val / dval);
+        return cur;
+    };
+    for (int j = team.rank; j < n; j += team.size) {
+        const double a = S.x_lo[j] ? (mu / q.gxl[j] - vxl[j] - vxl[j] / q.gxl[j] * q.dx[j]) : 0.0;
+        const double b = S.x_hi[j] ? (mu / q.gxu[j] - vxu[j] + vxu[j] / q.gxu[j] * q.dx[j]) : 0.0;
+        dvxl[j] = a;
+        dvxu[j] = b;
+        t_ad[j] = ms(vxu[j], b, S.x_hi[j], ms(vxl[j], a, S.x_lo[j], INFINITY));
+        t_lb[j] = (S.x_lo[j] ? log(q.gxl[j]) : 0.0) + (S.x_hi[j] ? log(q.gxu[j]) : 0.0);
+        const double gphi = S.fixed[j] ? 0.0 : (scaled_df(I, j) - (S.x_lo[j] ? mu / q.gxl[j] : 0.0) + (S.x_hi[j] ? mu / q.gxu[j] : 0.0));
+        t_dphi[j] = gphi * q.dx[j];
+    }
+    for (int r = team.rank; r < m; r += team.size) {
+        const double a = S.s_lo[r] ? (mu / q.gsl[r] - vsl[r] - vsl[r] / q.gsl[r] * q.ds[r]) : 0.0;
+        const double b = S.s_hi[r] ? (mu / q.gsu[r] - vsu[r] + vsu[r] / q.gsu[r] * q.ds[r]) : 0.0;
+        dvsl[r] = a;
+        dvsu[r] = b;
+        t_ad[n + r] = ms(vsu[r], b, S.s_hi[r], ms(vsl[r], a, S.s_lo[r], INFINITY));
+        t_lb[n + r] = (S.s_lo[r] ? log(q.gsl[r]) : 0.0) + (S.s_hi[r] ? log(q.gsu[r]) : 0.0);
+        const double gphi = S.is_eq[r] ? 0.0 : (-(S.s_lo[r] ? mu / q.gsl[r] : 0.0) + (S.s_hi[r] ? mu / q.gsu[r] : 0.0));
+        t_dphi[n + r] = gphi * q.ds[r];
+        t_h1[r] = dabs(s_h[r]);
+        t_lmax[r] = dabs(lam[r] + q.dl[r]);
+    }
+    team.sync();
+    const bool pol = T.polish[i] != 0;
+    if (team.rank == 0) {
+        const double h1 = arr_sum(t_h1, m), dphi = arr_sum(t_dphi, nk), lb = arr_sum(t_lb, nk), lmax = arr_nanmax(t_lmax, m, 0.0);
+        const double phi0 = dobj * T.f[i] - mu * lb;
+        const double nu_need = (dphi + 0.5 * clamp_min(quad, 0.0)) / (0.9 * clamp_min(h1, 1e-300));
+        const double nu = nanmax(clamp_min(nu_need, 0.0), lmax) * 1.1 + 1e-3;
+        T.nu[i] = nu;
+        T.Dm[i] = dphi - nu * h1;
+        T.merit0[i] = phi0 + nu * h1;
+        T.a_d[i] = pol ? 0.0 : clamp_max(arr_nanmin(t_ad, nk, INFINITY), 1.0);
+        T.pol[i] = pol ? 1 : 0;
     }
     team.sync();
 
     // feasibility polish: minimum-norm Newton step on x only (multipliers stay), on the equality rows and on the inequality
     // rows that sit beyond their ORIGINAL bound
-    const bool pol = T.polish[i] != 0;
     if (pol) {
         const double *cu_s = I.vm(T.cu_s), *cl_s = I.vm(T.cl_s);
-        double* act = q.tmp;        // [m]
-        double* r_p = q.tmp + m;    // [m]
+        double* act = q.term(3, nk);  // [m]
+        double* r_p = q.term(4, nk);  // [m]
         for (int r = team.rank; r < m; r += team.size) {
             const double cs = dc[r] * c[r];
             const bool over = !S.is_eq[r] && S.s_hi[r] && cs > cu_s[r], under = !S.is_eq[r] && S.s_lo[r] && cs < cl_s[r];
             act[r] = (S.is_eq[r] || over || under) ? 1.0 : 0.0;
             r_p[r] = over ? cs - cu_s[r] : (under ? cs - cl_s[r] : (S.is_eq[r] ? cs - sl[r] : 0.0));
         }
+        if (team.rank == 0) q.red[4] = 1.0;
         team.sync();
-        for (int e = team.rank; e < m * m; e += team.size) {  // M = Je Je^T + diag((1 - act) + 1e-14)
-            const int a = e / m, b = e - a * m;
-            double acc = 0.0;
-            if (act[a] != 0.0 && act[b] != 0.0)
-                for (int j = 0; j < n; j++) acc += q.Jd[a * n + j] * q.Jd[b * n + j];
-            if (a == b) acc += (1.0 - act[a]) + 1e-14;
-            q.K[a * ld + b] = acc;
-        }
-        team.sync();
-        if (team.rank == 0) {
-            bool ok = true;
-            for (int a = 0; a < m && ok; a++)
-                for (int b = 0; b < m && ok; b++) ok = finite_d(q.K[a * ld + b]);
-            q.red[4] = ok ? 1.0 : 0.0;
-        }
+        bool fin = true;
+        for (int a = 0; a < m; a++)
+            for (int b = team.rank; b < m; b += team.size) {  // M = Je Je^T + diag((1 - act) + 1e-14)
+                double acc = 0.0;
+                if (act[a] != 0.0 && act[b] != 0.0)
+                    for (int j = 0; j < n; j++) acc += q.Jd[a * n + j] * q.Jd[b * n + j];
+                if (a == b) acc += (1.0 - act[a]) + 1e-14;
+                q.K[a * ld + b] = acc;
+                fin = fin && finite_d(acc);
+            }
+        if (!fin) q.red[4] = 0.0;
         team.sync();
         if (q.red[4] == 0.0) {
-            for (int e = team.rank; e < m * m; e += team.size) q.K[(e / m) * ld + e % m] = (e / m == e % m) ? 1.0 : 0.0;
+            for (int a = 0; a < m; a++)
+                for (int b = team.rank; b < m; b += team.size) q.K[a * ld + b] = (a == b) ? 1.0 : 0.0;
             team.sync();
         }
-        lu_factor(team, q.K, ld, m, q.piv);
         for (int r = team.rank; r < m; r += team.size) q.sol[r] = r_p[r];
-        team.sync();
-        lu_solve(team, q.K, ld, m, q.piv, q.sol);
+        lu_factor(team, q.K, ld, m, q.piv, q.dinv, q.red + 16);
+        lu_solve(team, q.K, ld, m, q.piv, q.dinv, q.sol);
         for (int j = team.rank; j < n; j += team.size) {
             double acc = 0.0;
             for (int r = 0; r < m; r++)
@@ -683,144 +773,106 @@ CPLB_HD void phase_kkt(const Team& team, const Shape& S, const State& T, const O
         }
         team.sync();
         if (team.rank == 0) {
-            bool fin = true;
-            for (int j = 0; j < n; j++) fin = fin && finite_d(q.rhs[j]);
-            q.red[5] = fin ? 1.0 : 0.0;
+            bool f2 = true;
+            for (int j = 0; j < n; j++) f2 = f2 && finite_d(q.rhs[j]);
+            q.red[5] = f2 ? 1.0 : 0.0;
         }
         team.sync();
-        for (int j = team.rank; j < n; j += team.size) dx[j] = q.red[5] != 0.0 ? q.rhs[j] : 0.0;
-        for (int r = team.rank; r < m; r += team.size) ds[r] = dlam[r] = 0.0;
+        for (int j = team.rank; j < n; j += team.size) q.dx[j] = q.red[5] != 0.0 ? q.rhs[j] : 0.0;
+        for (int r = team.rank; r < m; r += team.size) q.ds[r] = q.dl[r] = 0.0;
         team.sync();
     }
 
-    // multiplier steps, fraction-to-the-boundary step lengths, merit function quantities
-    double *dvxl = I.vn(T.dvxl), *dvxu = I.vn(T.dvxu), *dvsl = I.vm(T.dvsl), *dvsu = I.vm(T.dvsu);
+    // primal fraction-to-the-boundary step length, tiny-step flag, polish residual; the step goes to global memory
+    double *dx = I.vn(T.dx), *ds = I.vm(T.ds), *dlam = I.vm(T.dlam);
+    double *t_ap = q.term(3, nk), *t_tiny = q.term(4, nk), *t_R0 = q.term(5, nk);
+    const double *cu_s = I.vm(T.cu_s), *cl_s = I.vm(T.cl_s);
     for (int j = team.rank; j < n; j += team.size) {
-        dvxl[j] = S.x_lo[j] ? (mu / q.gxl[j] - vxl[j] - vxl[j] / q.gxl[j] * dx[j]) : 0.0;
-        dvxu[j] = S.x_hi[j] ? (mu / q.gxu[j] - vxu[j] + vxu[j] / q.gxu[j] * dx[j]) : 0.0;
+        dx[j] = q.dx[j];
+        t_ap[j] = ms(q.gxu[j], -q.dx[j], S.x_hi[j], ms(q.gxl[j], q.dx[j], S.x_lo[j], INFINITY));
+        t_tiny[j] = dabs(q.dx[j]) / (1.0 + dabs(x[j]));
     }
     for (int r = team.rank; r < m; r += team.size) {
-        dvsl[r] = S.s_lo[r] ? (mu / q.gsl[r] - vsl[r] - vsl[r] / q.gsl[r] * ds[r]) : 0.0;
-        dvsu[r] = S.s_hi[r] ? (mu / q.gsu[r] - vsu[r] + vsu[r] / q.gsu[r] * ds[r]) : 0.0;
+        ds[r] = q.ds[r];
+        dlam[r] = q.dl[r];
+        t_ap[n + r] = pol ? INFINITY : ms(q.gsu[r], -q.ds[r], S.s_hi[r], ms(q.gsl[r], q.ds[r], S.s_lo[r], INFINITY));
+        const double cs = dc[r] * c[r];
+        t_R0[r] = S.is_eq[r] ? dabs(cs - sl[r]) : ((S.s_hi[r] ? clamp_min(cs - cu_s[r], 0.0) : 0.0) + (S.s_lo[r] ? clamp_min(cl_s[r] - cs, 0.0) : 0.0));
     }
     team.sync();
     if (team.rank == 0) {
-        auto ms = [&](double val, double dval, bool mask, double cur) {  // largest a with val + a dval >= (1 - tau) val
-            if (mask && dval < 0) cur = nanmin(cur, -tau * val / dval);
-            return cur;
-        };
-        double a_p = INFINITY, a_d = INFINITY;
-        for (int j = 0; j < n; j++) {
-            a_p = ms(q.gxl[j], dx[j], S.x_lo[j], a_p);
-            a_p = ms(q.gxu[j], -dx[j], S.x_hi[j], a_p);
-            a_d = ms(vxl[j], dvxl[j], S.x_lo[j], a_d);
-            a_d = ms(vxu[j], dvxu[j], S.x_hi[j], a_d);
-        }
-        for (int r = 0; r < m; r++) {
-            if (!pol) {
-                a_p = ms(q.gsl[r], ds[r], S.s_lo[r], a_p);
-                a_p = ms(q.gsu[r], -ds[r], S.s_hi[r], a_p);
-            }
-            a_d = ms(vsl[r], dvsl[r], S.s_lo[r], a_d);
-            a_d = ms(vsu[r], dvsu[r], S.s_hi[r], a_d);
-        }
-        a_p = clamp_max(a_p, 1.0);
-        a_d = pol ? 0.0 : clamp_max(a_d, 1.0);
-        // l1 merit function phi + nu |h|_1 and its directional derivative
-        double lb = 0.0, h1 = 0.0, dphi = 0.0, lmax = 0.0, tiny = 0.0;
-        for (int j = 0; j < n; j++) {
-            if (S.x_lo[j]) lb += log(q.gxl[j]);
-            if (S.x_hi[j]) lb += log(q.gxu[j]);
-            const double gphi = S.fixed[j] ? 0.0 : (scaled_df(I, j) - (S.x_lo[j] ? mu / q.gxl[j] : 0.0) + (S.x_hi[j] ? mu / q.gxu[j] : 0.0));
-            dphi += gphi * dx[j];
-            tiny = nanmax(tiny, dabs(dx[j]) / (1.0 + dabs(x[j])));
-        }
-        for (int r = 0; r < m; r++) {
-            if (S.s_lo[r]) lb += log(q.gsl[r]);
-            if (S.s_hi[r]) lb += log(q.gsu[r]);
-            const double gphi = S.is_eq[r] ? 0.0 : (-(S.s_lo[r] ? mu / q.gsl[r] : 0.0) + (S.s_hi[r] ? mu / q.gsu[r] : 0.0));
-            dphi += gphi * ds[r];
-            h1 += dabs(h[r]);
-            lmax = nanmax(lmax, dabs(lam[r] + dlam[r]));
-        }
-        const double phi0 = dobj * T.f[i] - mu * lb;
-        const double nu_need = (dphi + 0.5 * clamp_min(T.quad[i], 0.0)) / (0.9 * clamp_min(h1, 1e-300));
-        const double nu = nanmax(clamp_min(nu_need, 0.0), lmax) * 1.1 + 1e-3;
-        T.nu[i] = nu;
-        T.Dm[i] = dphi - nu * h1;
-        T.merit0[i] = phi0 + nu * h1;
+        const double a_p = clamp_max(arr_nanmin(t_ap, nk, INFINITY), 1.0);
         T.a_p[i] = a_p;
-        T.a_d[i] = a_d;
-        T.tiny[i] = tiny < 1e-13 ? 1 : 0;
-        T.pol[i] = pol ? 1 : 0;
-        // what the polish drives to zero: equality residuals and the excess over the ORIGINAL inequality bounds
-        const double *cu_s = I.vm(T.cu_s), *cl_s = I.vm(T.cl_s);
-        double R0 = 0.0;
-        for (int r = 0; r < m; r++) {
-            const double cs = dc[r] * c[r];
-            if (S.is_eq[r]) R0 = nanmax(R0, dabs(cs - sl[r]));
-            else R0 = nanmax(R0, (S.s_hi[r] ? clamp_min(cs - cu_s[r], 0.0) : 0.0) + (S.s_lo[r] ? clamp_min(cl_s[r] - cs, 0.0) : 0.0));
-        }
-        T.R0[i] = R0;
+        T.tiny[i] = arr_nanmax(t_tiny, n, 0.0) < 1e-13 ? 1 : 0;
+        T.R0[i] = arr_nanmax(t_R0, m, 0.0);
         q.red[6] = a_p;
     }
     team.sync();
     // line-search candidates x + alpha0 2^-k dx, k = 0 .. kCandidates - 1
     const double a0 = q.red[6];
-    for (int e = team.rank; e < kCandidates * n; e += team.size) {
-        const int k = e / n, j = e - k * n;
-        Xls[e] = x[j] + (a0 * ldexp(1.0, -k)) * dx[j];
+    for (int k = 0; k < kCandidates; k++) {
+        const double al = a0 * ldexp(1.0, -k);
+        for (int j = team.rank; j < n; j += team.size) Xls[k * n + j] = x[j] + al * q.dx[j];
     }
 }
 
-// merit test of one trial point: row values ct (scaled), slacks by the reset rule; returns ok and writes the trial slacks
+// Merit test of one trial point by the whole team: row values ct (scaled), slacks by the reset rule.  Writes the trial slacks to
+// st_out (team-shared, m) and returns (to every thread) ok / ct_finite.  Needs term arrays 0..2 of q.
 struct Trial {
     bool ok, ct_finite;
 };
-CPLB_HD Trial merit_test(const Inst& I, const double* X, const double* g_raw, double cost_raw, const double* S_lin, double AL, double* st_out)
+template <class Team>
+CPLB_HD Trial merit_test(const Team& team, const Inst& I, Scratch& q, const double* X, const double* g_raw, double cost_raw, const double* S_lin,
+                         double AL, double* st_out)
 {
     const Shape& S = I.S;
     const State& T = I.T;
     const long long i = I.i;
+    const int n = S.n, m = S.m, nk = S.nk;
     const double *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su), *s = I.vm(T.s), *cu_s = I.vm(T.cu_s), *cl_s = I.vm(T.cl_s);
     const double mu = T.mu[i], nu = T.nu[i], keep = mu / nu;
     const bool pol = T.pol[i] != 0;
-    const double ft = T.dobj[i] * cost_raw;
-    double lb = 0.0, viol = 0.0, Rt = 0.0;
-    bool ct_fin = true;
-    for (int j = 0; j < S.n; j++) {
-        if (S.x_lo[j]) lb += log(X[j] - S.xl[j]);
-        if (S.x_hi[j]) lb += log(S.xu[j] - X[j]);
-    }
-    for (int r = 0; r < S.m; r++) {
+    double *t_lb = q.term(0, nk), *t_viol = q.term(1, nk), *t_bad = q.term(2, nk);
+    for (int j = team.rank; j < n; j += team.size) t_lb[j] = (S.x_lo[j] ? log(X[j] - S.xl[j]) : 0.0) + (S.x_hi[j] ? log(S.xu[j] - X[j]) : 0.0);
+    for (int r = team.rank; r < m; r += team.size) {
         const double ct = dc[r] * g_raw[r];
-        ct_fin = ct_fin && finite_d(ct);
-        double st = S_lin[r];
+        t_bad[r] = finite_d(ct) ? 0.0 : 1.0;
+        double st = S_lin[r], lbr = 0.0, vr = 0.0;
         // slack reset (Nocedal & Wright 2006, section 19.3): the row value itself, mu / nu inside its bound
         if (S.s_hi[r] && !S.s_lo[r]) st = nanmin(ct, su[r] - keep);
         if (S.s_lo[r] && !S.s_hi[r]) st = nanmax(ct, sl[r] + keep);
         if (pol) {
-            // polishing instances: the slack of a strictly satisfied inequality row is the row value
+            // polishing instances: the slack of a strictly satisfied inequality row is the row value; the merit is the residual
             const bool inside = (!S.s_lo[r] || ct > sl[r]) && (!S.s_hi[r] || ct < su[r]);
             st = (!S.is_eq[r] && inside) ? ct : s[r];
-            if (S.is_eq[r]) Rt = nanmax(Rt, dabs(ct - sl[r]));
-            else Rt = nanmax(Rt, (S.s_hi[r] ? clamp_min(ct - cu_s[r], 0.0) : 0.0) + (S.s_lo[r] ? clamp_min(cl_s[r] - ct, 0.0) : 0.0));
+            vr = S.is_eq[r] ? dabs(ct - sl[r]) : ((S.s_hi[r] ? clamp_min(ct - cu_s[r], 0.0) : 0.0) + (S.s_lo[r] ? clamp_min(cl_s[r] - ct, 0.0) : 0.0));
         } else {
-            if (S.s_lo[r]) lb += log(st - sl[r]);
-            if (S.s_hi[r]) lb += log(su[r] - st);
-            viol += dabs(ct - st);
+            lbr = (S.s_lo[r] ? log(st - sl[r]) : 0.0) + (S.s_hi[r] ? log(su[r] - st) : 0.0);
+            vr = dabs(ct - st);
         }
+        t_lb[n + r] = lbr;
+        t_viol[r] = vr;
         st_out[r] = st;
     }
-    Trial t;
-    t.ct_finite = ct_fin;
-    if (pol) {
-        t.ok = ct_fin && Rt < T.R0[i];
-    } else {
-        const double mt = (ft - mu * lb) + nu * viol;
-        const double m0 = T.merit0[i];
-        t.ok = finite_d(mt) && mt <= (m0 + 10.0 * 2.2e-16 * dabs(m0)) + 1e-4 * AL * T.Dm[i];
+    team.sync();
+    if (team.rank == 0) {
+        const bool ct_fin = arr_sum(t_bad, m) == 0.0;
+        bool ok;
+        if (pol) {
+            ok = ct_fin && arr_nanmax(t_viol, m, 0.0) < T.R0[i];
+        } else {
+            const double mt = (T.dobj[i] * cost_raw - mu * arr_sum(t_lb, nk)) + nu * arr_sum(t_viol, m);
+            const double m0 = T.merit0[i];
+            ok = finite_d(mt) && mt <= (m0 + 10.0 * 2.2e-16 * dabs(m0)) + 1e-4 * AL * T.Dm[i];
+        }
+        q.red[90] = ok ? 1.0 : 0.0;
+        q.red[91] = ct_fin ? 1.0 : 0.0;
     }
+    team.sync();
+    Trial t;
+    t.ok = q.red[90] != 0.0;
+    t.ct_finite = q.red[91] != 0.0;
+    team.sync();
     return t;
 }
 
@@ -846,17 +898,13 @@ CPLB_HD void phase_ls_first(const Team& team, const Shape& S, const State& T, co
     const double a0 = T.a_p[i];
     const double* X0 = T.x_ls + i * (long long)kCandidates * n;
     const double* g0 = T.g_ls + i * (long long)kCandidates * m;
-    for (int r = team.rank; r < m; r += team.size) q.tmp[r] = s[r] + a0 * ds[r];  // linearly stepped slacks of candidate 0
+    double *slin = q.term(3, nk), *st = q.term(4, nk);
+    for (int r = team.rank; r < m; r += team.size) slin[r] = s[r] + a0 * ds[r];  // linearly stepped slacks of candidate 0
     team.sync();
-    if (team.rank == 0) {
-        Trial t = merit_test(I, X0, g0, T.cost_ls[i * kCandidates], q.tmp, a0, q.tmp + m);
-        bool ok = t.ok || (T.tiny[i] && t.ct_finite);
-        if (O.max_backtracks < 1) ok = false;
-        T.accepted0[i] = ok ? 1 : 0;
-        q.red[0] = ok ? 1.0 : 0.0;
-    }
-    team.sync();
-    if (q.red[0] != 0.0 || T.pol[i]) {
+    const Trial t0 = merit_test(team, I, q, X0, g0, T.cost_ls[i * kCandidates], slin, a0, st);
+    const bool ok0 = (t0.ok || (T.tiny[i] && t0.ct_finite)) && O.max_backtracks >= 1;
+    if (team.rank == 0) T.accepted0[i] = ok0 ? 1 : 0;
+    if (ok0 || T.pol[i]) {
         for (int j = team.rank; j < n; j += team.size) Xsoc[j] = x[j];
         return;
     }
@@ -876,43 +924,49 @@ CPLB_HD void phase_ls_first(const Team& team, const Shape& S, const State& T, co
         q.sol[a] = v;
     }
     const double* LU = T.lu + i * (long long)nk * nk;
-    for (int e = team.rank; e < nk * nk; e += team.size) q.K[(e / nk) * q.ld + e % nk] = LU[e];
-    for (int a = team.rank; a < nk; a += team.size) q.piv[a] = T.piv[i * nk + a];
-    team.sync();
-    lu_solve(team, q.K, q.ld, nk, q.piv, q.sol);
-    double *dxc = T.dx_soc + i * n, *dsc = T.ds_soc + i * m, *dlc = T.dlam_soc + i * m;
-    for (int j = team.rank; j < n; j += team.size) dxc[j] = S.fixed[j] ? 0.0 : q.sol[j];
-    for (int r = team.rank; r < m; r += team.size) {
-        dlc[r] = q.sol[n + r];
-        dsc[r] = S.is_eq[r] ? 0.0 : D[r] * (q.sol[n + r] - r_s[r]);
+    for (int a = 0; a < nk; a++)
+        for (int b = team.rank; b < nk; b += team.size) q.K[a * q.ld + b] = LU[a * nk + b];
+    for (int a = team.rank; a < nk; a += team.size) {
+        q.piv[a] = T.piv[i * nk + a];
+        q.dinv[a] = T.lu_dinv[i * nk + a];
     }
+    team.sync();
+    lu_solve(team, q.K, q.ld, nk, q.piv, q.dinv, q.sol);
     compute_gaps(team, S, x, s, I.vm(T.sl), I.vm(T.su), q);
     team.sync();
+    double *dxc = T.dx_soc + i * n, *dsc = T.ds_soc + i * m, *dlc = T.dlam_soc + i * m;
+    const double tau = T.tau[i];
+    auto ms = [&](double val, double dval, bool mask, double cur) {
+        if (mask && dval < 0) cur = nanmin(cur, -tau * val / dval);
+        return cur;
+    };
+    double *t_ac = q.term(5, nk), *t_bad = q.term(6, nk);
+    for (int j = team.rank; j < n; j += team.size) {
+        const double d = S.fixed[j] ? 0.0 : q.sol[j];
+        dxc[j] = d;
+        q.dx[j] = d;
+        t_ac[j] = ms(q.gxu[j], -d, S.x_hi[j], ms(q.gxl[j], d, S.x_lo[j], INFINITY));
+        t_bad[j] = finite_d(q.sol[j]) ? 0.0 : 1.0;
+    }
+    for (int r = team.rank; r < m; r += team.size) {
+        const double dl = q.sol[n + r];
+        const double d = S.is_eq[r] ? 0.0 : D[r] * (dl - r_s[r]);
+        dlc[r] = dl;
+        dsc[r] = d;
+        t_ac[n + r] = ms(q.gsu[r], -d, S.s_hi[r], ms(q.gsl[r], d, S.s_lo[r], INFINITY));
+        t_bad[n + r] = finite_d(dl) ? 0.0 : 1.0;
+    }
+    team.sync();
     if (team.rank == 0) {
-        bool fin = true;
-        for (int a = 0; a < nk; a++) fin = fin && finite_d(q.sol[a]);
-        const double tau = T.tau[i];
-        auto ms = [&](double val, double dval, bool mask, double cur) {
-            if (mask && dval < 0) cur = nanmin(cur, -tau * val / dval);
-            return cur;
-        };
-        double a_c = INFINITY;
-        for (int j = 0; j < n; j++) {
-            a_c = ms(q.gxl[j], dxc[j], S.x_lo[j], a_c);
-            a_c = ms(q.gxu[j], -dxc[j], S.x_hi[j], a_c);
-        }
-        for (int r = 0; r < m; r++) {
-            a_c = ms(q.gsl[r], dsc[r], S.s_lo[r], a_c);
-            a_c = ms(q.gsu[r], -dsc[r], S.s_hi[r], a_c);
-        }
-        a_c = clamp_max(a_c, 1.0);
+        const double a_c = clamp_max(arr_nanmin(t_ac, nk, INFINITY), 1.0);
+        const bool fin = arr_sum(t_bad, nk) == 0.0;
         T.a_soc[i] = a_c;
         T.soc_valid[i] = fin ? 1 : 0;
         q.red[1] = a_c;
         q.red[2] = fin ? 1.0 : 0.0;
     }
     team.sync();
-    for (int j = team.rank; j < n; j += team.size) Xsoc[j] = q.red[2] != 0.0 ? x[j] + q.red[1] * dxc[j] : x[j];
+    for (int j = team.rank; j < n; j += team.size) Xsoc[j] = q.red[2] != 0.0 ? x[j] + q.red[1] * q.dx[j] : x[j];
 }
 
 // ---- phase 4: accept a point, update the iterate and the multipliers ------------------------------------------------------------
@@ -920,48 +974,49 @@ template <class Team>
 CPLB_HD void phase_ls_select(const Team& team, const Shape& S, const State& T, const Options& O, long long i, Scratch& q)
 {
     Inst I{S, T, i};
-    const int n = S.n, m = S.m;
+    const int n = S.n, m = S.m, nk = S.nk;
     if (!T.active[i]) return;
     double *x = I.vn(T.x), *s = I.vm(T.s), *lam = I.vm(T.lam);
     const double *dx = I.vn(T.dx), *ds = I.vm(T.ds);
     const double a0 = T.a_p[i];
     const bool pol = T.pol[i] != 0;
-    double* st = q.tmp;          // [m] trial slacks
-    double* slin = q.tmp + m;    // [m]
+    double *slin = q.term(3, nk), *st = q.term(4, nk);
+    // order of a sequential backtracking search: full step, second-order correction, 1/2, 1/4, ...
+    int choice = -1;  // candidate index; kCandidates = the corrected point
+    double alpha = a0;
+    if (T.accepted0[i]) {
+        choice = 0;
+        for (int r = team.rank; r < m; r += team.size) slin[r] = s[r] + a0 * ds[r];
+        team.sync();
+        merit_test(team, I, q, T.x_ls + i * (long long)kCandidates * n, T.g_ls + i * (long long)kCandidates * m, T.cost_ls[i * kCandidates], slin, a0, st);
+    } else {
+        if (T.soc_valid[i] && !pol) {
+            const double a_c = T.a_soc[i];
+            const double* dsc = T.ds_soc + i * m;
+            for (int r = team.rank; r < m; r += team.size) slin[r] = s[r] + a_c * dsc[r];
+            team.sync();
+            const Trial t = merit_test(team, I, q, T.x_soc + i * n, T.g_soc + i * m, T.cost_soc[i], slin, a0, st);
+            if (t.ok) choice = kCandidates;
+        }
+        const int kmax = O.max_backtracks < kCandidates ? O.max_backtracks : kCandidates;
+        for (int k = 1; k < kmax && choice < 0; k++) {
+            const double AL = a0 * ldexp(1.0, -k);
+            for (int r = team.rank; r < m; r += team.size) slin[r] = s[r] + AL * ds[r];
+            team.sync();
+            const Trial t = merit_test(team, I, q, T.x_ls + (i * kCandidates + k) * (long long)n, T.g_ls + (i * kCandidates + k) * (long long)m,
+                                       T.cost_ls[i * kCandidates + k], slin, AL, st);
+            if (t.ok || (T.tiny[i] && t.ct_finite)) {
+                choice = k;
+                alpha = AL;
+            }
+        }
+    }
+    if (choice < 0) {  // search exhausted: take the last (tiny) step
+        alpha = a0 * ldexp(1.0, -O.max_backtracks);
+        for (int r = team.rank; r < m; r += team.size) st[r] = s[r] + alpha * ds[r];
+        team.sync();
+    }
     if (team.rank == 0) {
-        // order of a sequential backtracking search: full step, second-order correction, 1/2, 1/4, ...
-        int choice = -1;         // candidate index, kCandidates = the corrected point
-        double alpha = a0;
-        if (T.accepted0[i]) {
-            choice = 0;
-            for (int r = 0; r < m; r++) slin[r] = s[r] + a0 * ds[r];
-            merit_test(I, T.x_ls + i * (long long)kCandidates * n, T.g_ls + i * (long long)kCandidates * m, T.cost_ls[i * kCandidates], slin, a0, st);
-        } else {
-            if (T.soc_valid[i] && !pol) {
-                const double a_c = T.a_soc[i];
-                const double* dsc = T.ds_soc + i * m;
-                for (int r = 0; r < m; r++) slin[r] = s[r] + a_c * dsc[r];
-                Trial t = merit_test(I, T.x_soc + i * n, T.g_soc + i * m, T.cost_soc[i], slin, a0, st);
-                bool finx = true;
-                for (int j = 0; j < n; j++) finx = finx && finite_d(T.x_soc[i * n + j]);
-                if (t.ok && finx) choice = kCandidates;
-            }
-            const int kmax = O.max_backtracks < kCandidates ? O.max_backtracks : kCandidates;
-            for (int k = 1; k < kmax && choice < 0; k++) {
-                const double AL = a0 * ldexp(1.0, -k);
-                for (int r = 0; r < m; r++) slin[r] = s[r] + AL * ds[r];
-                Trial t = merit_test(I, T.x_ls + (i * kCandidates + k) * (long long)n, T.g_ls + (i * kCandidates + k) * (long long)m,
-                                     T.cost_ls[i * kCandidates + k], slin, AL, st);
-                if (t.ok || (T.tiny[i] && t.ct_finite)) {
-                    choice = k;
-                    alpha = AL;
-                }
-            }
-        }
-        if (choice < 0) {  // search exhausted: take the last (tiny) step
-            alpha = a0 * ldexp(1.0, -O.max_backtracks);
-            for (int r = 0; r < m; r++) st[r] = s[r] + alpha * ds[r];
-        }
         // Levenberg-Marquardt damping of the next step: a search that had to backtrack asks for a shorter step next time
         double n_back = rint(log2(clamp_min(a0 / clamp_min(alpha, 1e-300), 1.0)));
         if (pol) n_back = 1.0;
@@ -969,12 +1024,8 @@ CPLB_HD void phase_ls_select(const Team& team, const Shape& S, const State& T, c
         double dlm = n_back >= 2 ? dmax(dl * 8.0, 1e-6) : (n_back >= 1 ? dmax(dl * 2.0, 1e-6) : dl / 4.0);
         if (dlm < 1e-12) dlm = 0.0;
         T.delta_lm[i] = dmin(dlm, 1.0);
-        q.red[0] = (double)choice;
-        q.red[1] = alpha;
     }
-    team.sync();
-    const int choice = (int)q.red[0];
-    const double alpha = q.red[1], a_d = T.a_d[i];
+    const double a_d = T.a_d[i];
     const double* dlam_used = (choice == kCandidates) ? T.dlam_soc + i * m : I.vm(T.dlam);
     const double* xnew = choice == kCandidates ? T.x_soc + i * n : (choice >= 0 ? T.x_ls + (i * kCandidates + choice) * (long long)n : nullptr);
     for (int j = team.rank; j < n; j += team.size) {
@@ -1001,7 +1052,6 @@ CPLB_HD void phase_finish(const Team& team, const Shape& S, const State& T, long
         for (int r = team.rank; r < S.m; r += team.size) lam_out[i * S.m + r] = I.vm(T.lam)[r] * I.vm(T.dc)[r] / T.dobj[i];
     if (team.rank == 0) T.out_cost[i] = T.f[i];
 }
-
 
 // ==== host side shared by the GPU driver (cplb_solver.cu) and the CPU replay (tests/native/solver_host_check.cpp) ================
 
@@ -1086,7 +1136,7 @@ inline std::vector<StateField> state_fields(State& T, const ShapeHost& S)
     D(T.dx, n); D(T.ds, m); D(T.dlam, m); D(T.dvxl, n); D(T.dvxu, n); D(T.dvsl, m); D(T.dvsu, m); D(T.h, m); D(T.r_x, n); D(T.r_s, m); D(T.D, m);
     D(T.a_p, 1); D(T.a_d, 1); D(T.merit0, 1); D(T.Dm, 1); D(T.nu, 1); D(T.R0, 1); D(T.quad, 1);
     I(T.tiny, 1); I(T.pol, 1); I(T.okK, 1); I(T.accepted0, 1);
-    D(T.lu, nk * nk); I(T.piv, nk);
+    D(T.lu, nk * nk); D(T.lu_dinv, nk); I(T.piv, nk);
     D(T.x_fd, P * n); D(T.grad_fd, P * n); D(T.jac_fd, P * nnz);
     D(T.x_ls, KC * n); D(T.g_ls, KC * m); D(T.cost_ls, KC);
     D(T.x_soc, n); D(T.g_soc, m); D(T.cost_soc, 1); D(T.dx_soc, n); D(T.ds_soc, m); D(T.dlam_soc, m); D(T.a_soc, 1);

@@ -48,8 +48,8 @@ struct HostEngine {
             }
         }
         Scratch probe;
-        scratch.assign(probe.carve(nullptr, S.n, S.m, S.nnz), 0.0);
-        q.carve(scratch.data(), S.n, S.m, S.nnz);
+        scratch.assign(probe.carve(nullptr, S.n, S.m, S.nnz, true), 0.0);
+        q.carve(scratch.data(), S.n, S.m, S.nnz, true);
         x_out.assign(N * S.n, 0.0);
         lam_out.assign(N * S.m, 0.0);
     }
