@@ -239,8 +239,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")  # a barrier that waits on the HOST (an NCCL barrier would spin on the waiting ranks' GPUs)
     stream = torch.cuda.current_stream(dev)
     W, K = max(3, args.warmup), max(1, args.steps)
     R = max(1, args.regions)
@@ -337,7 +339,7 @@ def run_ours(args):
     N = N_PER_GPU
     layout = cpl.INSTANCE_MAJOR if args.layout == "instance" else cpl.COMPONENT_MAJOR
     other = cpl.COMPONENT_MAJOR if layout == cpl.INSTANCE_MAJOR else cpl.INSTANCE_MAJOR
-    kname = {cpl.INSTANCE_MAJOR: "eval_instance_major", cpl.COMPONENT_MAJOR: "eval_component_major_split"}
+    kname = {cpl.INSTANCE_MAJOR: "eval_instance_major_cta", cpl.COMPONENT_MAJOR: "eval_component_major_split"}
     x_host = make_inputs(rank)
     ready = not args.no_inputs_ready
     launches0 = prob.launch_count()
@@ -378,6 +380,28 @@ def run_ours(args):
     bytes4_total = algorithmic_bytes_per_instance(prob8.n, prob8.m, prob8.nnz) * N_CONFIG4
     del x4
     launches_total = prob.launch_count() - launches0 + sq_prob.launch_count() + prob8.launch_count()
+
+    # ---- config 5 stand-in: 4,096 lock-step solves per GPU through cplb_solve_device (NOT IPOPT: IPOPT is absent from the image) ----
+    from centroidalplanner_b200.lockstep_solver import SUCCESS, default_start
+
+    n_solve = 4096
+    x0s = default_start(prob, n_solve)
+    x0s[1:] += torch.as_tensor(np.random.default_rng(2025 + rank).normal(0.0, 0.05, tuple(x0s[1:].shape)))
+    x0s = x0s.to(dev)
+    solver = cpl.NativeInteriorPoint()
+    solver.Solve(prob, x0s[:64])
+    solve_s = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        sres = solver.Solve(prob, x0s)
+        torch.cuda.synchronize(dev)
+        solve_s.append(max_over_ranks(time.perf_counter() - t0))
+    solved = int((sres.status == SUCCESS).sum())
+    solve_stats = {"rounds": sres.rounds, "evaluations": sres.evaluations, "instance_evaluations": sres.instance_evaluations,
+                   "succeeded_rank0": solved, "iterations_median": float(sres.iterations.double().median()),
+                   "max_constr_viol": float(sres.constr_viol[sres.status == SUCCESS].max()) if solved else None}
+    del x0s, sres
 
     # ---- e2e: host buffers through cplb_eval_host[_begin/_wait] -------------------------------------------------------
     lib = _cabi.load()
@@ -487,7 +511,8 @@ def run_ours(args):
     # thread); rank 0 only, the other ranks idle at the barrier meanwhile
     sharded = None
     if world > 1:
-        barrier()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=host_group)
         if rank == 0:
             env_s = cpl.Ground()
             shp = cpl.BatchedCplProblem(synthetic.NAMES4, 100.0, env_s, devices=list(range(world)))
@@ -521,7 +546,8 @@ def run_ours(args):
                        "h2d_bytes_per_step": 8 * n * NT, "d2h_bytes_per_step": 8 * (m + nv) * NT,
                        "api": "cplb_create_sharded + cplb_eval_host_begin / _wait with CPLB_JAC_PACKED: ONE process, one set of pinned host "
                               f"buffers for {world} x 65,536 instances, contiguous index ranges per GPU, no collective"}
-        barrier()
+            del shp
+        dist.barrier(group=host_group)
 
     # component-major host buffers, x-independent Jacobian slots (whole rows there) pre-filled once and not re-transferred
     cmask, _ = prob.GetJacobianConstants()
@@ -636,6 +662,11 @@ def run_ours(args):
                                          "kernel": "eval_component_major_whole<GROUND,8>"},
                             "plain_order": {"ms_per_step": c4_plain_ms, "roofline_frac": frac(c4_plain_ms, bytes4_total, world)},
                             "instance_major": {"ms_per_step": c4_im_ms, "roofline_frac": frac(c4_im_ms, bytes4_total, world)}},
+                "config5_standin": {"workload": "configs[4] stand-in: 4,096 lock-step solves per GPU of the TestBasic ground problem (configs[0] "
+                                                "parameters) from perturbed starting points through cplb_solve_device -- the interior-point scheme "
+                                                "IPOPT implements written out on the GPU; NOT an IPOPT measurement (IPOPT is not in the image)",
+                                    "scaling": "weak", "value": world * n_solve / statistics.median(solve_s), "unit": "solves/s",
+                                    "seconds": statistics.median(solve_s), "seconds_all": solve_s, **solve_stats},
             },
             "clocks": clocks,
         }

@@ -29,3 +29,15 @@ def cuda_device():
         pytest.skip("no CUDA device")
     torch.cuda.set_device(0)
     return torch.device("cuda:0")
+
+
+def pytest_terminal_summary(terminalreporter):
+    """How often the expanded-square allowance (tests/helpers.py) was actually needed in this session."""
+    try:
+        import helpers
+    except Exception:
+        return
+    a = helpers.ALLOWANCE
+    if a["pow_entries"]:
+        terminalreporter.write_line(f"parity: {a['pow_entries']} pow-downstream entries compared, {a['entries']} beyond the plain 1e-12 bar "
+                                    f"(passed through the Q5 allowance, factor {helpers.Q5_FACTOR}); worst entry {a['worst_vs_plain_bar']:.3g} x the plain bar")

@@ -133,6 +133,10 @@ def pow_downstream_masks(o):
     return gm, jm
 
 
+Q5_FACTOR = 32  # multiple of eps * amplification * |exact entry| granted to the three diagonal normal-Jacobian entries (see below)
+ALLOWANCE = {"entries": 0, "pow_entries": 0, "worst_vs_plain_bar": 0.0}  # running tally over every assert_parity call of the session
+
+
 def expanded_square_bound(o, x):
     """the diagonal entries of the superquadric normal Jacobian end in
     Q = C_u^2 W_u + C_v^2 W_v + p_u^2 W_u + p_v^2 W_v - 2 C_u p_u W_u - 2 C_v p_v W_v  (= (p_u-C_u)^2 W_u + (p_v-C_v)^2 W_v),
@@ -166,7 +170,7 @@ def expanded_square_bound(o, x):
                 exact = h[:, a] * (g[:, u] ** 2 + g[:, v] ** 2) / (s * np.sqrt(s))
                 slot = np.nonzero((iRow == 6 + 6 * j + 1 + a) & (jCol == 3 + 9 * k + 3 + a))[0]
                 assert slot.size == 1
-                bnd = 64 * 1.12e-16 * (num / den) * exact
+                bnd = Q5_FACTOR * 1.12e-16 * (num / den) * exact
                 bound[:, slot[0]] = np.where(np.isfinite(bnd), bnd, 0.0)
     return bound
 
@@ -181,9 +185,11 @@ def same_bits(a, b):
     return bool((a.view(np.int64)[~na] == b.view(np.int64)[~nb]).all())
 
 
-def assert_parity(got, want, o, what, x=None):
-    """got/want: dicts with instance-major arrays g (N,m), jac (N,nnz), cost (N,), grad (N,n)."""
+def assert_parity(got, want, o, what, x=None, allowance=True):
+    """got/want: dicts with instance-major arrays g (N,m), jac (N,nnz), cost (N,), grad (N,n).  Returns the number of entries
+    that passed only through the expanded-square allowance (0 when x is None or allowance=False: plain 1e-12 bar)."""
     gm, jm = pow_downstream_masks(o)
+    used = 0
     for key in ("g", "jac", "cost", "grad"):
         if want.get(key) is None or got.get(key) is None:
             continue
@@ -208,13 +214,21 @@ def assert_parity(got, want, o, what, x=None):
         # own rounding noise there (expanded_square_bound) -- the best any evaluation that is not bit-identical can do
         err = np.abs(aa - bb)
         tol = RTOL * scale
-        if key == "jac" and x is not None:
+        plain = (err / tol)[fin]
+        ALLOWANCE["pow_entries"] += int(plain.size)
+        if plain.size:
+            ALLOWANCE["worst_vs_plain_bar"] = max(ALLOWANCE["worst_vs_plain_bar"], float(plain.max()))
+        if key == "jac" and x is not None and allowance:
             tol = np.maximum(tol, expanded_square_bound(o, x)[:, mask])
+            n_used = int((plain > 1.0).sum())   # entries beyond the plain bar: they pass, if at all, through the allowance
+            used += n_used
+            ALLOWANCE["entries"] += n_used
         ratio = (err / tol)[fin]
         worst = float(ratio.max()) if ratio.size else 0.0
         err = err / scale
         assert worst <= 1.0, (f"{what}: {key} differs from the oracle by {float(err[fin].max()):.3e} relative "
                               f"({worst:.2f}x the tolerance)")
+    return used
 
 
 def to_instance_major(arr, layout):

@@ -521,6 +521,7 @@ def test_full_size_configs(case, N, cuda_device):
     got = {"g": a["g"][torch.from_numpy(sub).to(cuda_device)].cpu().numpy(),
            "jac": a["jac"][torch.from_numpy(sub).to(cuda_device)].cpu().numpy()}
     assert_parity(got, want, o, f"{case}/full")  # no x: the plain 1e-12 bar, no expanded-square allowance, on the benchmark configs
+    assert assert_parity(got, want, o, f"{case}/full", x[sub]) == 0   # ... and offering the allowance changes nothing: no entry needs it
     # size-independent property: the force-balance Jacobian rows are all 1.0 and row r of g equals
     # Sigma_k F_k[r] - w[r] + m g[r] up to summation-order rounding
     nc = o.nc

@@ -71,10 +71,15 @@ def main():
             t = time.perf_counter()
             res = solver.Solve(prob, xg)
             torch.cuda.synchronize()
-            dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+            dt = torch.tensor([time.perf_counter() - t, float(res.rounds)], dtype=torch.float64, device=dev)
             if world > 1:
+                every = [torch.zeros_like(dt) for _ in range(world)]
+                dist.all_gather(every, dt)
+                per_rank = [[round(float(e[0]), 4), int(e[1])] for e in every]      # (seconds, rounds) of every rank
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            dt = float(dt.item())
+            else:
+                per_rank = [[round(float(dt[0]), 4), int(dt[1])]]
+            dt = float(dt[0].item())
             best = dt if best is None else min(best, dt)
         ok = torch.tensor([int((res.status == SUCCESS).sum())], device=dev)
         if world > 1:
@@ -84,6 +89,7 @@ def main():
         out["gpu"] = {"n_gpus": world, "solves_per_s": a.instances / best, "seconds": best, "succeeded": ok, "rounds": res.rounds,
                       "kernel_launches": prob.launch_count() - l0, "instance_evaluations": res.instance_evaluations,
                       "iterations_median": float(res.iterations.double().median()), "iterations_max": int(res.iterations.max()),
+                      "per_rank_seconds_rounds": per_rank,
                       "max_constr_viol": float(res.constr_viol[res.status == SUCCESS].max())}
 
     if rank != 0:
