@@ -22,6 +22,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "cplb_kernels.h"
@@ -147,36 +148,38 @@ struct DeviceEngine {
         CplbIo io{x, g, jac, cost, grad, count, count};
         check(launch_instance_major(P, io, flags, nullptr, im_kernel, st));
     }
+    // one CTA per slot of the working set (or per instance for the phases outside the rounds)
     template <class K, class... Args>
-    void run(K kern, size_t shared, Args... args)
+    void run(K kern, long long ctas, size_t shared, Args... args)
     {
-        if (err != cudaSuccess) return;
-        kern<<<(unsigned)N, (const void*)kern == (const void*)k_kkt ? kThreadsLU : kThreads, shared, st>>>(A, args...);
+        if (err != cudaSuccess || ctas <= 0) return;
+        kern<<<(unsigned)ctas, (const void*)kern == (const void*)k_kkt ? kThreadsLU : kThreads, shared, st>>>(A, args...);
         check(cudaGetLastError());
     }
-    void init_x() { run(k_init_x, 0, x0); }
-    void init_scale() { run(k_init_scale, 0); }
-    int round_begin(bool first, bool last)
+    void init_x() { run(k_init_x, N, 0, x0); }
+    void init_scale() { run(k_init_scale, N, 0); }
+    long long round_begin(bool first, bool last, long long slots)
     {
         if (err != cudaSuccess) return 0;
         check(cudaMemsetAsync(W->n_active, 0, sizeof(int), st));
-        run(k_round_begin, smem_small, (int)first, (int)last, W->n_active);
+        run(k_round_begin, slots, smem_small, (int)first, (int)last, W->n_active);
         check(cudaMemcpyAsync(W->n_active_host, W->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
         check(cudaStreamSynchronize(st));
+        std::swap(A.T.list_cur, A.T.list_next);  // the instances still running, in the order their CTAs got there
         return err == cudaSuccess ? *W->n_active_host : 0;
     }
-    void kkt() { run(k_kkt, smem); }
-    void ls_first() { run(k_ls_first, smem); }
-    void ls_select() { run(k_ls_select, smem_small); }
+    void kkt(long long cnt) { run(k_kkt, cnt, smem); }
+    void ls_first(long long cnt) { run(k_ls_first, cnt, smem); }
+    void ls_select(long long cnt) { run(k_ls_select, cnt, smem_small); }
     void finish()
     {
-        run(k_finish, 0, x_out, lam_out);
+        run(k_finish, N, 0, x_out, lam_out);
         check(cudaStreamSynchronize(st));
     }
-    void eval_full() { eval(A.T.x, A.T.c, A.T.jv, A.T.f, A.T.df, N); }
-    void eval_fd() { eval(A.T.x_fd, nullptr, A.T.jac_fd, nullptr, A.T.grad_fd, N * (A.S.nf + 1)); }
-    void eval_ls() { eval(A.T.x_ls, A.T.g_ls, nullptr, A.T.cost_ls, nullptr, N * kCandidates); }
-    void eval_soc() { eval(A.T.x_soc, A.T.g_soc, nullptr, A.T.cost_soc, nullptr, N); }
+    void eval_full(long long cnt) { eval(A.T.xc, A.T.ev_c, A.T.ev_jv, A.T.ev_f, A.T.ev_df, cnt); }
+    void eval_fd(long long cnt) { eval(A.T.x_fd, nullptr, A.T.jac_fd, nullptr, A.T.grad_fd, cnt * (A.S.nf + 1)); }
+    void eval_ls(long long cnt) { eval(A.T.x_ls, A.T.g_ls, nullptr, A.T.cost_ls, nullptr, cnt * kCandidates); }
+    void eval_soc(long long cnt) { eval(A.T.x_soc, A.T.g_soc, nullptr, A.T.cost_soc, nullptr, cnt); }
 };
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }

@@ -59,6 +59,10 @@ struct State {
     double *mu, *tau, *delta_last, *delta_lm;                  // [N]
     int32_t *status, *iters, *polish, *active;                 // [N]
     double *f, *df, *c, *jv;                                   // raw evaluator outputs at x: cost [N], grad [N n], g [N m], jac [N nnz]
+    // Working set: only the instances still running take part in a round.  list_cur[b] = instance of slot b in the current round;
+    // every per-round buffer below (and xc / ev_*: the iterate handed to the evaluator and what it returned) is indexed by SLOT.
+    int32_t *list_cur, *list_next;                             // [N]
+    double *xc, *ev_f, *ev_df, *ev_c, *ev_jv;                  // [N n], [N], [N n], [N m], [N nnz]
     double *dc, *dobj, *sl, *su, *cu_s, *cl_s;                 // scaling and scaled slack bounds
     // step of the current round
     double *dx, *ds, *dlam, *dvxl, *dvxu, *dvsl, *dvsu, *h, *r_x, *r_s, *D;
@@ -328,8 +332,22 @@ CPLB_HD void phase_init_x(const Team& team, const Shape& S, const State& T, cons
     double* x = T.x + i * S.n;
     for (int j = team.rank; j < S.n; j += team.size) {
         double v = S.fixed[j] ? S.xl[j] : x0[i * S.n + j];
-        x[j] = push_inside(v, S.xl[j], S.xu[j], S.x_lo[j], S.x_hi[j], O.bound_push, O.bound_frac);
+        v = push_inside(v, S.xl[j], S.xu[j], S.x_lo[j], S.x_hi[j], O.bound_push, O.bound_frac);
+        x[j] = v;
+        T.xc[i * S.n + j] = v;  // slot = instance before the first round
     }
+    if (team.rank == 0) T.list_cur[i] = (int32_t)i;
+}
+
+// evaluator outputs of slot b -> the instance's own arrays
+template <class Team>
+CPLB_HD void fetch_evaluation(const Team& team, const Shape& S, const State& T, long long i, long long b)
+{
+    for (int j = team.rank; j < S.n; j += team.size) T.df[i * S.n + j] = T.ev_df[b * S.n + j];
+    for (int r = team.rank; r < S.m; r += team.size) T.c[i * S.m + r] = T.ev_c[b * S.m + r];
+    for (int e = team.rank; e < S.nnz; e += team.size) T.jv[i * S.nnz + e] = T.ev_jv[b * S.nnz + e];
+    if (team.rank == 0) T.f[i] = T.ev_f[b];
+    team.sync();
 }
 
 // ---- phase 0b: scaling, slacks, multipliers (after the first evaluation at x) -------------------------------------------------
@@ -337,6 +355,7 @@ template <class Team>
 CPLB_HD void phase_init_scale(const Team& team, const Shape& S, const State& T, const Options& O, long long i)
 {
     Inst I{S, T, i};
+    fetch_evaluation(team, S, T, i, i);
     const double *df = I.vn(T.df), *c = I.vm(T.c), *jv = T.jv + i * S.nnz;
     double *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su), *s = I.vm(T.s);
     // gradient-based scaling at the starting point (nlp_scaling_method = gradient-based, nlp_scaling_max_gradient)
@@ -392,15 +411,17 @@ CPLB_HD void phase_init_scale(const Team& team, const Shape& S, const State& T, 
 // (after the evaluation at the new x) kappa_sigma safeguard of the bound multipliers, convergence test, barrier update, and the
 // forward-difference points of the Hessian.  Returns through T.active[i]; *n_active counts the instances still running.
 template <class Team>
-CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T, const Options& O, long long i, Scratch& q, int first_round,
+CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T, const Options& O, long long b_prev, Scratch& q, int first_round,
                                int last_round, int* n_active)
 {
+    const long long i = T.list_cur[b_prev];  // the working set of the previous round, in its slot order
     Inst I{S, T, i};
     const int n = S.n, m = S.m, nk = S.nk;
-    if (T.status[i] >= 0) {  // finished earlier
+    if (T.status[i] >= 0) {  // finished earlier (only before the first round: a bad starting point)
         if (team.rank == 0) T.active[i] = 0;
         return;
     }
+    if (!first_round) fetch_evaluation(team, S, T, i, b_prev);  // (the first round's evaluation was fetched by phase_init_scale)
     double *x = I.vn(T.x), *s = I.vm(T.s);
     double *vxl = I.vn(T.vxl), *vxu = I.vn(T.vxu), *vsl = I.vm(T.vsl), *vsu = I.vm(T.vsu);
     const double *lam = I.vm(T.lam), *c = I.vm(T.c), *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su);
@@ -482,11 +503,14 @@ CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T,
             }
             T.mu[i] = mu;
             T.tau[i] = dmax(1.0 - mu, 0.99);
+            // slot in the working set of this round
 #if defined(__CUDA_ARCH__)
-            atomicAdd(n_active, 1);
+            const int slot = atomicAdd(n_active, 1);
 #else
-            *n_active += 1;
+            const int slot = (*n_active)++;
 #endif
+            T.list_next[slot] = (int32_t)i;
+            q.red[1] = (double)slot;
         }
         T.active[i] = active;
         q.red[0] = (double)active;
@@ -494,7 +518,7 @@ CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T,
     team.sync();
     // forward-difference points of the Lagrangian Hessian: point a < nf perturbs free variable a, point nf is x itself
     if (q.red[0] != 0.0) {
-        double* X = T.x_fd + i * (long long)(S.nf + 1) * n;
+        double* X = T.x_fd + (long long)q.red[1] * (S.nf + 1) * n;
         for (int a = 0; a <= S.nf; a++)
             for (int j = team.rank; j < n; j += team.size) {
                 double v = x[j];
@@ -506,17 +530,13 @@ CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T,
 
 // ---- phase 2: Hessian, KKT system, regularised Newton step, line-search set-up ------------------------------------------------
 template <class Team>
-CPLB_HD void phase_kkt(const Team& team, const Shape& S, const State& T, const Options& O, long long i, Scratch& q)
+CPLB_HD void phase_kkt(const Team& team, const Shape& S, const State& T, const Options& O, long long b, Scratch& q)
 {
+    const long long i = T.list_cur[b];
     Inst I{S, T, i};
     const int n = S.n, m = S.m, nk = S.nk, ld = q.ld;
-    double* Xls = T.x_ls + i * (long long)kCandidates * n;
+    double* Xls = T.x_ls + b * (long long)kCandidates * n;
     double *x = I.vn(T.x), *s = I.vm(T.s);
-    if (!T.active[i]) {  // finished instances keep feeding finite points to the widened evaluations
-        for (int k = 0; k < kCandidates; k++)
-            for (int j = team.rank; j < n; j += team.size) Xls[k * n + j] = x[j];
-        return;
-    }
     const double *lam = I.vm(T.lam), *dc = I.vm(T.dc), *sl = I.vm(T.sl), *su = I.vm(T.su);
     const double *vxl = I.vn(T.vxl), *vxu = I.vn(T.vxu), *vsl = I.vm(T.vsl), *vsu = I.vm(T.vsu), *c = I.vm(T.c);
     const double mu = T.mu[i], tau = T.tau[i], dobj = T.dobj[i];
@@ -530,8 +550,8 @@ CPLB_HD void phase_kkt(const Team& team, const Shape& S, const State& T, const O
     team.sync();
 
     // Lagrangian Hessian by forward differences: grad L at point a = dobj * grad f + sum_slots jac[slot] * (dc lam)[row(slot)]
-    const double* gfd = T.grad_fd + i * (long long)(S.nf + 1) * n;
-    const double* jfd = T.jac_fd + i * (long long)(S.nf + 1) * S.nnz;
+    const double* gfd = T.grad_fd + b * (long long)(S.nf + 1) * n;
+    const double* jfd = T.jac_fd + b * (long long)(S.nf + 1) * S.nnz;
     auto grad_lagrangian = [&](int a, int j) -> double {
         if (S.fixed[j]) return 0.0;
         double acc = dobj * gfd[(long long)a * n + j];
@@ -880,28 +900,25 @@ CPLB_HD Trial merit_test(const Team& team, const Inst& I, Scratch& q, const doub
 // Tests candidate 0; when it fails, solves the same KKT matrix with the constraint residual of the rejected point added to
 // the right-hand side (Waechter & Biegler 2006, section 2.4) and emits the corrected trial point for one more evaluation.
 template <class Team>
-CPLB_HD void phase_ls_first(const Team& team, const Shape& S, const State& T, const Options& O, long long i, Scratch& q)
+CPLB_HD void phase_ls_first(const Team& team, const Shape& S, const State& T, const Options& O, long long b, Scratch& q)
 {
+    const long long i = T.list_cur[b];
     Inst I{S, T, i};
     const int n = S.n, m = S.m, nk = S.nk;
-    double* Xsoc = T.x_soc + i * n;
+    double* Xsoc = T.x_soc + b * n;
     const double* x = I.vn(T.x);
     if (team.rank == 0) {
         T.accepted0[i] = 0;
         T.soc_valid[i] = 0;
     }
-    if (!T.active[i]) {
-        for (int j = team.rank; j < n; j += team.size) Xsoc[j] = x[j];
-        return;
-    }
     const double *s = I.vm(T.s), *ds = I.vm(T.ds), *dc = I.vm(T.dc);
     const double a0 = T.a_p[i];
-    const double* X0 = T.x_ls + i * (long long)kCandidates * n;
-    const double* g0 = T.g_ls + i * (long long)kCandidates * m;
+    const double* X0 = T.x_ls + b * (long long)kCandidates * n;
+    const double* g0 = T.g_ls + b * (long long)kCandidates * m;
     double *slin = q.term(3, nk), *st = q.term(4, nk);
     for (int r = team.rank; r < m; r += team.size) slin[r] = s[r] + a0 * ds[r];  // linearly stepped slacks of candidate 0
     team.sync();
-    const Trial t0 = merit_test(team, I, q, X0, g0, T.cost_ls[i * kCandidates], slin, a0, st);
+    const Trial t0 = merit_test(team, I, q, X0, g0, T.cost_ls[b * kCandidates], slin, a0, st);
     const bool ok0 = (t0.ok || (T.tiny[i] && t0.ct_finite)) && O.max_backtracks >= 1;
     if (team.rank == 0) T.accepted0[i] = ok0 ? 1 : 0;
     if (ok0 || T.pol[i]) {
@@ -971,11 +988,11 @@ CPLB_HD void phase_ls_first(const Team& team, const Shape& S, const State& T, co
 
 // ---- phase 4: accept a point, update the iterate and the multipliers ------------------------------------------------------------
 template <class Team>
-CPLB_HD void phase_ls_select(const Team& team, const Shape& S, const State& T, const Options& O, long long i, Scratch& q)
+CPLB_HD void phase_ls_select(const Team& team, const Shape& S, const State& T, const Options& O, long long b, Scratch& q)
 {
+    const long long i = T.list_cur[b];
     Inst I{S, T, i};
     const int n = S.n, m = S.m, nk = S.nk;
-    if (!T.active[i]) return;
     double *x = I.vn(T.x), *s = I.vm(T.s), *lam = I.vm(T.lam);
     const double *dx = I.vn(T.dx), *ds = I.vm(T.ds);
     const double a0 = T.a_p[i];
@@ -988,14 +1005,14 @@ CPLB_HD void phase_ls_select(const Team& team, const Shape& S, const State& T, c
         choice = 0;
         for (int r = team.rank; r < m; r += team.size) slin[r] = s[r] + a0 * ds[r];
         team.sync();
-        merit_test(team, I, q, T.x_ls + i * (long long)kCandidates * n, T.g_ls + i * (long long)kCandidates * m, T.cost_ls[i * kCandidates], slin, a0, st);
+        merit_test(team, I, q, T.x_ls + b * (long long)kCandidates * n, T.g_ls + b * (long long)kCandidates * m, T.cost_ls[b * kCandidates], slin, a0, st);
     } else {
         if (T.soc_valid[i] && !pol) {
             const double a_c = T.a_soc[i];
             const double* dsc = T.ds_soc + i * m;
             for (int r = team.rank; r < m; r += team.size) slin[r] = s[r] + a_c * dsc[r];
             team.sync();
-            const Trial t = merit_test(team, I, q, T.x_soc + i * n, T.g_soc + i * m, T.cost_soc[i], slin, a0, st);
+            const Trial t = merit_test(team, I, q, T.x_soc + b * n, T.g_soc + b * m, T.cost_soc[b], slin, a0, st);
             if (t.ok) choice = kCandidates;
         }
         const int kmax = O.max_backtracks < kCandidates ? O.max_backtracks : kCandidates;
@@ -1003,8 +1020,8 @@ CPLB_HD void phase_ls_select(const Team& team, const Shape& S, const State& T, c
             const double AL = a0 * ldexp(1.0, -k);
             for (int r = team.rank; r < m; r += team.size) slin[r] = s[r] + AL * ds[r];
             team.sync();
-            const Trial t = merit_test(team, I, q, T.x_ls + (i * kCandidates + k) * (long long)n, T.g_ls + (i * kCandidates + k) * (long long)m,
-                                       T.cost_ls[i * kCandidates + k], slin, AL, st);
+            const Trial t = merit_test(team, I, q, T.x_ls + (b * kCandidates + k) * (long long)n, T.g_ls + (b * kCandidates + k) * (long long)m,
+                                       T.cost_ls[b * kCandidates + k], slin, AL, st);
             if (t.ok || (T.tiny[i] && t.ct_finite)) {
                 choice = k;
                 alpha = AL;
@@ -1027,9 +1044,11 @@ CPLB_HD void phase_ls_select(const Team& team, const Shape& S, const State& T, c
     }
     const double a_d = T.a_d[i];
     const double* dlam_used = (choice == kCandidates) ? T.dlam_soc + i * m : I.vm(T.dlam);
-    const double* xnew = choice == kCandidates ? T.x_soc + i * n : (choice >= 0 ? T.x_ls + (i * kCandidates + choice) * (long long)n : nullptr);
+    const double* xnew = choice == kCandidates ? T.x_soc + b * n : (choice >= 0 ? T.x_ls + (b * kCandidates + choice) * (long long)n : nullptr);
     for (int j = team.rank; j < n; j += team.size) {
-        x[j] = xnew ? xnew[j] : x[j] + alpha * dx[j];
+        const double v = xnew ? xnew[j] : x[j] + alpha * dx[j];
+        x[j] = v;
+        T.xc[b * n + j] = v;  // what the evaluator sees next, in slot order
         I.vn(T.vxl)[j] += a_d * I.vn(T.dvxl)[j];
         I.vn(T.vxu)[j] += a_d * I.vn(T.dvxu)[j];
     }
@@ -1132,6 +1151,7 @@ inline std::vector<StateField> state_fields(State& T, const ShapeHost& S)
     D(T.mu, 1); D(T.tau, 1); D(T.delta_last, 1); D(T.delta_lm, 1);
     I(T.status, 1); I(T.iters, 1); I(T.polish, 1); I(T.active, 1);
     D(T.f, 1); D(T.df, n); D(T.c, m); D(T.jv, nnz);
+    I(T.list_cur, 1); I(T.list_next, 1); D(T.xc, n); D(T.ev_f, 1); D(T.ev_df, n); D(T.ev_c, m); D(T.ev_jv, nnz);
     D(T.dc, m); D(T.dobj, 1); D(T.sl, m); D(T.su, m); D(T.cu_s, m); D(T.cl_s, m);
     D(T.dx, n); D(T.ds, m); D(T.dlam, m); D(T.dvxl, n); D(T.dvxu, n); D(T.dvsl, m); D(T.dvsu, m); D(T.h, m); D(T.r_x, n); D(T.r_s, m); D(T.D, m);
     D(T.a_p, 1); D(T.a_d, 1); D(T.merit0, 1); D(T.Dm, 1); D(T.nu, 1); D(T.R0, 1); D(T.quad, 1);
@@ -1150,34 +1170,38 @@ struct SolveStats {
     long long evaluations = 0, instance_evaluations = 0;
 };
 
-// The lock-step round, engine-independent.  Engine: init_x(), init_scale(), round_begin(first, last) -> instances still running,
-// kkt(), ls_first(), ls_select(), finish(), and the four batched evaluations eval_full / eval_fd / eval_ls / eval_soc.
+// The lock-step round, engine-independent.  Engine: init_x(), init_scale(), round_begin(first, last, slots) -> instances still
+// running (the new working set; finished instances leave it: a round costs what its running instances cost), kkt(count),
+// ls_first(count), ls_select(count), finish(), and the four batched evaluations eval_full / eval_fd / eval_ls / eval_soc (count).
 template <class Engine>
 SolveStats solve_loop(Engine& E, const Options& O, long long N, int nf)
 {
     SolveStats st;
     E.init_x();
-    E.eval_full();
+    E.eval_full(N);
     st.evaluations++;
     st.instance_evaluations += N;
     E.init_scale();
+    long long working = N;  // slots of the previous round's working set
     for (int it = 0; it <= O.max_iter; it++) {
-        const int running = E.round_begin(it == 0, it == O.max_iter);
+        const long long running = E.round_begin(it == 0, it == O.max_iter, working);  // also swaps the working-set lists
         if (running == 0) break;
         st.rounds++;
-        E.eval_fd();   // gradient + Jacobian at the nf + 1 difference points of every instance
-        E.kkt();
-        E.eval_ls();   // constraint values + cost at the line-search candidates
-        E.ls_first();
-        E.eval_soc();  // ... and at the second-order-corrected points
-        E.ls_select();
-        E.eval_full();
+        E.eval_fd(running);   // gradient + Jacobian at the nf + 1 difference points of every running instance
+        E.kkt(running);
+        E.eval_ls(running);   // constraint values + cost at the line-search candidates
+        E.ls_first(running);
+        E.eval_soc(running);  // ... and at the second-order-corrected points
+        E.ls_select(running);
+        E.eval_full(running);
         st.evaluations += 4;
-        st.instance_evaluations += N * (long long)(nf + 1 + kCandidates + 2);
+        st.instance_evaluations += running * (long long)(nf + 1 + kCandidates + 2);
+        working = running;
     }
     E.finish();
     return st;
 }
+
 }  // namespace solver
 }  // namespace cplb
 #endif

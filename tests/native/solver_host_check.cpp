@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -56,20 +57,21 @@ struct HostEngine {
     HostTeam team;
     void init_x() { for (long long i = 0; i < N; i++) phase_init_x(team, S, T, O, i, x0.data()); }
     void init_scale() { for (long long i = 0; i < N; i++) phase_init_scale(team, S, T, O, i); }
-    int round_begin(bool first, bool last)
+    long long round_begin(bool first, bool last, long long slots)
     {
         int running = 0;
-        for (long long i = 0; i < N; i++) phase_round_begin(team, S, T, O, i, q, first, last, &running);
+        for (long long b = 0; b < slots; b++) phase_round_begin(team, S, T, O, b, q, first, last, &running);
+        std::swap(T.list_cur, T.list_next);
         return running;
     }
-    void kkt() { for (long long i = 0; i < N; i++) phase_kkt(team, S, T, O, i, q); }
-    void ls_first() { for (long long i = 0; i < N; i++) phase_ls_first(team, S, T, O, i, q); }
-    void ls_select() { for (long long i = 0; i < N; i++) phase_ls_select(team, S, T, O, i, q); }
+    void kkt(long long cnt) { for (long long b = 0; b < cnt; b++) phase_kkt(team, S, T, O, b, q); }
+    void ls_first(long long cnt) { for (long long b = 0; b < cnt; b++) phase_ls_first(team, S, T, O, b, q); }
+    void ls_select(long long cnt) { for (long long b = 0; b < cnt; b++) phase_ls_select(team, S, T, O, b, q); }
     void finish() { for (long long i = 0; i < N; i++) phase_finish(team, S, T, i, x_out.data(), lam_out.data()); }
-    void eval_full() { cpl_oracle_eval_batch(o, N, T.x, T.c, T.jv, T.f, T.df, threads); }
-    void eval_fd() { cpl_oracle_eval_batch(o, N * (S.nf + 1), T.x_fd, nullptr, T.jac_fd, nullptr, T.grad_fd, threads); }
-    void eval_ls() { cpl_oracle_eval_batch(o, N * kCandidates, T.x_ls, T.g_ls, nullptr, T.cost_ls, nullptr, threads); }
-    void eval_soc() { cpl_oracle_eval_batch(o, N, T.x_soc, T.g_soc, nullptr, T.cost_soc, nullptr, threads); }
+    void eval_full(long long cnt) { cpl_oracle_eval_batch(o, cnt, T.xc, T.ev_c, T.ev_jv, T.ev_f, T.ev_df, threads); }
+    void eval_fd(long long cnt) { cpl_oracle_eval_batch(o, cnt * (S.nf + 1), T.x_fd, nullptr, T.jac_fd, nullptr, T.grad_fd, threads); }
+    void eval_ls(long long cnt) { cpl_oracle_eval_batch(o, cnt * kCandidates, T.x_ls, T.g_ls, nullptr, T.cost_ls, nullptr, threads); }
+    void eval_soc(long long cnt) { cpl_oracle_eval_batch(o, cnt, T.x_soc, T.g_soc, nullptr, T.cost_soc, nullptr, threads); }
 };
 
 // lockstep_solver.default_start
