@@ -45,6 +45,22 @@ PYBIND11_MODULE(pycplb, m)
     py::class_<cplb::BatchedProblem, cplb::BatchedProblem::Ptr>(m, "BatchedProblem")
         .def(py::init<std::vector<std::string>, double, cplb::env::EnvironmentClass::Ptr, int>(), py::arg("contact_names"),
              py::arg("robot_mass"), py::arg("env") = cplb::env::EnvironmentClass::Ptr(), py::arg("device") = -1)
+        // the same problem sharded over several GPUs of the box (cplb_create_sharded)
+        .def(py::init([](std::vector<std::string> names, double mass, cplb::env::EnvironmentClass::Ptr env, std::vector<int> devices) {
+                 return std::make_shared<cplb::BatchedProblem>(std::move(names), mass, std::move(env), devices);
+             }),
+             py::arg("contact_names"), py::arg("robot_mass"), py::arg("env"), py::arg("devices"))
+        .def("GetNumberOfShards", &cplb::BatchedProblem::GetNumberOfShards)
+        .def("GetShard", [](const cplb::BatchedProblem& p, int shard, int64_t N) {
+            int device = -1;
+            int64_t b = 0, e = 0;
+            p.GetShard(shard, N, device, b, e);
+            return py::make_tuple(device, b, e);
+        })
+        .def("GetPackedJacobianMap", [](const cplb::BatchedProblem& p) {
+            const std::vector<int32_t> m = p.GetPackedJacobianMap();
+            return py::array_t<int32_t>(m.size(), m.data());
+        })
         .def_property_readonly("n", &cplb::BatchedProblem::GetNumberOfOptimizationVariables)
         .def_property_readonly("m", &cplb::BatchedProblem::GetNumberOfConstraints)
         .def_property_readonly("nnz", &cplb::BatchedProblem::GetNumberOfJacobianNonzeros)
@@ -92,26 +108,51 @@ PYBIND11_MODULE(pycplb, m)
         .def("SetForceThreshold", &cplb::BatchedProblem::SetForceThreshold)
         .def("GetForceThreshold", &cplb::BatchedProblem::GetForceThreshold)
         // host arrays, instance-major: x (N, n) -> dict of (N, m), (N, nnz), (N,), (N, n)
-        .def("eval", [](cplb::BatchedProblem& p, darray x, bool g, bool jac, bool cost, bool grad) {
+        .def("eval", [](cplb::BatchedProblem& p, darray x, bool g, bool jac, bool cost, bool grad, bool jac_packed) {
             if (x.ndim() != 2 || x.shape(1) != p.GetNumberOfOptimizationVariables()) throw std::invalid_argument("x must be (N, n)");
             const py::ssize_t N = x.shape(0);
             py::dict out;
             darray ag, aj, ac, agr;
             if (g) ag = darray({N, (py::ssize_t)p.GetNumberOfConstraints()});
-            if (jac) aj = darray({N, (py::ssize_t)p.GetNumberOfJacobianNonzeros()});
+            if (jac) aj = darray({N, jac_packed ? (py::ssize_t)p.GetPackedJacobianMap().size() : (py::ssize_t)p.GetNumberOfJacobianNonzeros()});
             if (cost) ac = darray({N});
             if (grad) agr = darray({N, (py::ssize_t)p.GetNumberOfOptimizationVariables()});
             {
                 py::gil_scoped_release nogil;
                 p.EvaluateHost(N, x.data(), g ? ag.mutable_data() : nullptr, jac ? aj.mutable_data() : nullptr,
-                               cost ? ac.mutable_data() : nullptr, grad ? agr.mutable_data() : nullptr);
+                               cost ? ac.mutable_data() : nullptr, grad ? agr.mutable_data() : nullptr, nullptr, jac_packed ? CPLB_JAC_PACKED : 0);
             }
             out["g"] = g ? py::object(ag) : py::none();
             out["jac"] = jac ? py::object(aj) : py::none();
             out["cost"] = cost ? py::object(ac) : py::none();
             out["grad"] = grad ? py::object(agr) : py::none();
             return out;
-        }, py::arg("x"), py::arg("g") = true, py::arg("jac") = true, py::arg("cost") = false, py::arg("grad") = false)
+        }, py::arg("x"), py::arg("g") = true, py::arg("jac") = true, py::arg("cost") = false, py::arg("grad") = false, py::arg("jac_packed") = false)
+        // raw device pointers of ONE shard of a sharded problem, on that shard's device and stream
+        .def("eval_device_shard", [](cplb::BatchedProblem& p, int shard, int64_t N, int layout, int64_t ld, uintptr_t x, uintptr_t g,
+                                     uintptr_t jac, uintptr_t cost, uintptr_t grad, uintptr_t stream) {
+            p.EvaluateDeviceShard(shard, N, (cplb_layout)layout, ld, reinterpret_cast<const double*>(x), reinterpret_cast<double*>(g),
+                                  reinterpret_cast<double*>(jac), reinterpret_cast<double*>(cost), reinterpret_cast<double*>(grad),
+                                  reinterpret_cast<void*>(stream));
+        }, py::arg("shard"), py::arg("num_instances"), py::arg("layout"), py::arg("ld"), py::arg("x"), py::arg("g") = 0, py::arg("jac") = 0,
+             py::arg("cost") = 0, py::arg("grad") = 0, py::arg("stream") = 0)
+        // N lock-step solves on the GPU (cplb_solve_device); every array argument is a raw device pointer
+        .def("solve_device", [](cplb::BatchedProblem& p, int64_t N, uintptr_t x0, uintptr_t x, uintptr_t status, uintptr_t iterations,
+                                uintptr_t cost, uintptr_t constr_viol, uintptr_t dual_inf, uintptr_t lam, uintptr_t stream, double tol, int max_iter) {
+            cplb_solver_options o;
+            cplb_solver_default_options(&o);
+            o.tol = tol;
+            o.max_iter = max_iter;
+            cplb::BatchedProblem::SolveCounters c;
+            {
+                py::gil_scoped_release nogil;
+                c = p.SolveDevice(N, reinterpret_cast<const double*>(x0), reinterpret_cast<double*>(x), reinterpret_cast<int32_t*>(status),
+                                  reinterpret_cast<int32_t*>(iterations), reinterpret_cast<double*>(cost), reinterpret_cast<double*>(constr_viol),
+                                  reinterpret_cast<double*>(dual_inf), reinterpret_cast<double*>(lam), reinterpret_cast<void*>(stream), &o);
+            }
+            return py::make_tuple(c.rounds, c.evaluations, c.instance_evaluations);
+        }, py::arg("num_instances"), py::arg("x0"), py::arg("x"), py::arg("status"), py::arg("iterations"), py::arg("cost"),
+             py::arg("constr_viol"), py::arg("dual_inf"), py::arg("lam") = 0, py::arg("stream") = 0, py::arg("tol") = 1e-3, py::arg("max_iter") = 500)
         // raw device pointers (e.g. torch.Tensor.data_ptr()), either layout, asynchronous on `stream`
         .def("eval_device", [](cplb::BatchedProblem& p, int64_t N, int layout, int64_t ld, uintptr_t x, uintptr_t g, uintptr_t jac,
                                uintptr_t cost, uintptr_t grad, uintptr_t stream) {

@@ -429,6 +429,31 @@ public:
         check(cplb_eval_device_shard(_p, shard, &a, stream));
     }
 
+    // N lock-step solves on the GPU (cplb_solve_device): the batched counterpart of cpl::CentroidalPlanner::Solve
+    // (src/CentroidalPlanner.cpp:22-34); all pointers are device pointers, lam may be nullptr.  NOT IPOPT (see the C header).
+    struct SolveCounters {
+        int32_t rounds = 0;
+        int64_t evaluations = 0, instance_evaluations = 0;
+    };
+    SolveCounters SolveDevice(int64_t N, const double* x0, double* x, int32_t* status, int32_t* iterations, double* cost, double* constr_viol,
+                              double* dual_inf, double* lam, void* stream, const cplb_solver_options* options = nullptr)
+    {
+        SolveCounters c;
+        cplb_solve_outputs out{};
+        out.x = x;
+        out.status = status;
+        out.iterations = iterations;
+        out.cost = cost;
+        out.constr_viol = constr_viol;
+        out.dual_inf = dual_inf;
+        out.lam = lam;
+        out.rounds = &c.rounds;
+        out.evaluations = &c.evaluations;
+        out.instance_evaluations = &c.instance_evaluations;
+        check(cplb_solve_device(_p, N, x0, options, &out, stream));
+        return c;
+    }
+
 private:
     std::vector<std::string> _contact_names;
     env::EnvironmentClass::Ptr _env;

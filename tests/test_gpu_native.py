@@ -93,3 +93,54 @@ def test_pybind11_module_matches_ctypes_path(cuda_device):
     r1, c1 = p1.GetJacobianStructure()
     r2, c2 = p2.GetJacobianStructure()
     assert np.array_equal(r1, r2) and np.array_equal(c1, c2)
+
+
+def test_pybind11_module_round_two_entry_points(cuda_device):
+    """The pybind11 module forwards the round-2 ABI too: sharded problems, packed Jacobian slices, native lock-step solves."""
+    import sys
+
+    import numpy as np
+    import torch
+
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "bindings", "python")], stdout=subprocess.DEVNULL)
+    sys.path.insert(0, os.path.join(ROOT, "centroidalplanner_b200"))
+    import pycplb
+
+    from centroidalplanner_b200 import synthetic
+
+    def ground():
+        e = pycplb.Ground()
+        e.SetGroundZ(0.1)
+        e.SetMu(0.5)
+        return e
+
+    x = synthetic.ground_batch(5000)
+    single = pycplb.BatchedProblem(synthetic.NAMES4, 100.0, ground())
+    sharded = pycplb.BatchedProblem(synthetic.NAMES4, 100.0, ground(), devices=[0, 0, 0])
+    assert sharded.GetNumberOfShards() == 3 and sharded.GetShard(1, 5000)[1] % 32 == 0
+    a = single.eval(x, g=True, jac=True)
+    b = sharded.eval(x, g=True, jac=True, jac_packed=True)
+    pmap = single.GetPackedJacobianMap()
+    assert np.array_equal(a["g"], b["g"]) and np.array_equal(a["jac"][:, pmap], b["jac"])
+    # native solve through the module: TestBasic's ground problem, equilibrium lines on every instance
+    single.SetCoMWeight(2.0)
+    single.SetForceWeight(0.0)
+    single.SetManipulationWrench([100.0, 0, 0, 0, 0, 100.0])
+    for nm in synthetic.NAMES4:
+        single.SetPosBounds(nm, [-0.3, -0.3, 0.0], [0.3, 0.3, 1.0])
+    N, n = 32, single.n
+    rng = np.random.default_rng(1)
+    x0 = np.zeros((N, n))
+    x0[:, 2] = 0.5
+    for k in range(4):
+        x0[:, 3 + 9 * k:6 + 9 * k] = [1.0 + 0.5 * k, -1.0 + 0.25 * k, 245.25]
+        x0[:, 6 + 9 * k:9 + 9 * k] = [0.24 * (1 if k in (0, 3) else -1), 0.24 * (1 if k < 2 else -1), 0.5]
+        x0[:, 9 + 9 * k:12 + 9 * k] = [0.0, 0.0, 1.0]
+    x0 += rng.normal(0, 0.02, x0.shape)
+    d = lambda *shape, dt=torch.float64: torch.empty(*shape, dtype=dt, device=cuda_device)  # noqa: E731
+    xd, xs, st, it, cost, viol, dual = torch.from_numpy(x0).to(cuda_device), d(N, n), d(N, dt=torch.int32), d(N, dt=torch.int32), d(N), d(N), d(N)
+    rounds, evals, _ = single.solve_device(N, xd.data_ptr(), xs.data_ptr(), st.data_ptr(), it.data_ptr(), cost.data_ptr(), viol.data_ptr(), dual.data_ptr())
+    assert rounds > 0 and evals == 1 + 4 * rounds and st.tolist() == [0] * N
+    sol = xs.cpu().numpy()
+    F = sol[:, 3:].reshape(N, 4, 9)[:, :, 0:3].sum(axis=1)
+    assert np.abs(F - [100.0, 0.0, 981.0]).max() < 1e-6
