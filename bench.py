@@ -460,9 +460,26 @@ def run_ours(args):
             pending = ticket
         prob.eval_host_wait(pending)
 
+    # computed Jacobian slices (CPLB_JAC_COMPUTED): additionally without the slots that are plain copies +-x[col] of the instance's
+    # own x (the caller holds x); what the IFOPT views consume
+    kind, _src = prob.GetJacobianSlotSources()
+    comp = np.nonzero(kind == cpl._cabi.SLOT_COMPUTED)[0]
+    nv2 = len(comp)
+    hjq, hjq2 = pin((N, nv2)), pin((N, nv2))
+    cp_sets = [(hx, {"g": hg, "jac": hjq}), (hx2, {"g": hg2, "jac": hjq2})]
+
+    def computed_calls():
+        pending = None
+        for k in range(e2e_steps):
+            ticket, _ = prob.eval_host_begin(cp_sets[k % 2][0], cp_sets[k % 2][1], g=True, jac=True, layout=e2e_layout, jac_packed="computed")
+            if pending is not None:
+                prob.eval_host_wait(pending)
+            pending = ticket
+        prob.eval_host_wait(pending)
+
     def packed_sync_calls():
         for _ in range(e2e_steps):
-            prob.eval(hx, g=True, jac=True, layout=e2e_layout, out={"g": hg, "jac": hjp}, jac_packed=True)
+            prob.eval(hx, g=True, jac=True, layout=e2e_layout, out={"g": hg, "jac": hjq}, jac_packed="computed")
 
     sync_calls()
     e2e_s, _ = wall(sync_calls)
@@ -476,35 +493,49 @@ def run_ours(args):
     pmap = prob.GetPackedJacobianMap()
     assert np.array_equal(hjp2.view(np.int64), hj2[:, pmap].view(np.int64)), "packed Jacobian slices differ from the full rows"
     assert np.array_equal(prob.UnpackJacobian(hjp2[:512]).view(np.int64), hj2[:512].view(np.int64))
+    computed_calls()
+    e2e_c_s, e2e_c_all = wall(computed_calls)
+    # ... and so are the computed slices, which expand (with x and the constants) to the full rows
+    assert np.array_equal(hjq2.view(np.int64), hj2[:, comp].view(np.int64)), "computed Jacobian slices differ from the full rows"
+    assert np.array_equal(prob.ExpandJacobian(hx2[:512], hjq2[:512]).view(np.int64), hj2[:512].view(np.int64))
     packed_sync_calls()
     e2e_ps_s, _ = wall(packed_sync_calls)
     h2d_bytes, d2h_bytes = 8 * n * N, 8 * (m + nnz) * N
     d2h_packed = 8 * (m + nv) * N
+    d2h_computed = 8 * (m + nv2) * N
 
     # raw PCIe ceiling of exactly these bytes, ALL ranks at once: one D2H copy of the g + Jacobian bytes and one H2D copy of the
     # x bytes per step on two streams, pinned buffers, nothing else -- what the host side of this box can move when every GPU asks
-    def pcie_ceiling(d2h_bytes):
-        d_out = torch.empty(d2h_bytes // 8, dtype=torch.float64, device=dev)
-        d_in = torch.empty(h2d_bytes // 8, dtype=torch.float64, device=dev)
-        h_out = torch.empty(d2h_bytes // 8, dtype=torch.float64).pin_memory()
-        h_in = torch.empty(h2d_bytes // 8, dtype=torch.float64).pin_memory()
+    # -- INTO / FROM THE VERY HOST BUFFERS the timed calls used (the same pinned pages on the same NUMA node: a ceiling measured on
+    # other pages can come out below what the calls achieve).
+    def pcie_ceiling(host_out, host_in):
+        h_out = [torch.from_numpy(a.reshape(-1)) for a in host_out]
+        h_in = torch.from_numpy(host_in.reshape(-1))
+        assert all(t.is_pinned() for t in h_out) and h_in.is_pinned()
+        d_out = [torch.empty(t.numel(), dtype=torch.float64, device=dev) for t in h_out]
+        d_in = torch.empty(h_in.numel(), dtype=torch.float64, device=dev)
         s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
         def steps():
             for _ in range(e2e_steps):
                 with torch.cuda.stream(s1):
-                    h_out.copy_(d_out, non_blocking=True)
+                    for h, d in zip(h_out, d_out):
+                        h.copy_(d, non_blocking=True)
                 with torch.cuda.stream(s2):
                     d_in.copy_(h_in, non_blocking=True)
             s1.synchronize()
             s2.synchronize()
 
+        keep = [t.clone() for t in h_out]      # the copies overwrite the results: put them back afterwards
         steps()
         med, _ = wall(steps)
+        for t, k in zip(h_out, keep):
+            t.copy_(k)
         return med
 
-    ceil_s = pcie_ceiling(d2h_bytes)
-    ceil_p_s = pcie_ceiling(d2h_packed)
+    ceil_s = pcie_ceiling([hg2, hj2], hx2)
+    ceil_p_s = pcie_ceiling([hg2, hjp2], hx2)
+    ceil_c_s = pcie_ceiling([hg2, hjq2], hx2)
 
     # the same queue of packed batches driven IN ONE PROCESS over all GPUs of the run through a sharded problem
     # (cplb_create_sharded: one set of host buffers for world x 65,536 instances, every device's pipeline driven by the calling
@@ -520,7 +551,7 @@ def run_ours(args):
             NT = world * N
             sx = [pin((NT, n)), pin((NT, n))]
             sg = [pin((NT, m)), pin((NT, m))]
-            sj = [pin((NT, nv)), pin((NT, nv))]
+            sj = [pin((NT, nv2)), pin((NT, nv2))]
             for b in range(2):
                 for r in range(world):
                     sx[b][r * N:(r + 1) * N] = x_host
@@ -528,7 +559,7 @@ def run_ours(args):
             def sharded_calls():
                 pending = None
                 for k in range(e2e_steps):
-                    ticket, _ = shp.eval_host_begin(sx[k % 2], {"g": sg[k % 2], "jac": sj[k % 2]}, g=True, jac=True, layout=e2e_layout, jac_packed=True)
+                    ticket, _ = shp.eval_host_begin(sx[k % 2], {"g": sg[k % 2], "jac": sj[k % 2]}, g=True, jac=True, layout=e2e_layout, jac_packed="computed")
                     if pending is not None:
                         shp.eval_host_wait(pending)
                     pending = ticket
@@ -540,11 +571,11 @@ def run_ours(args):
                 t0 = time.perf_counter()
                 sharded_calls()
                 ts.append((time.perf_counter() - t0) / e2e_steps)
-            assert np.array_equal(sj[1][:N].view(np.int64), hjp2.view(np.int64)) and np.array_equal(sj[1][-N:].view(np.int64), hjp2.view(np.int64))
+            assert np.array_equal(sj[1][:N].view(np.int64), hjq2.view(np.int64)) and np.array_equal(sj[1][-N:].view(np.int64), hjq2.view(np.int64))
             t_sh = statistics.median(ts)
             sharded = {"value": NT / t_sh, "ms_per_step": 1e3 * t_sh, "instances_per_step": NT, "devices": world,
-                       "h2d_bytes_per_step": 8 * n * NT, "d2h_bytes_per_step": 8 * (m + nv) * NT,
-                       "api": "cplb_create_sharded + cplb_eval_host_begin / _wait with CPLB_JAC_PACKED: ONE process, one set of pinned host "
+                       "h2d_bytes_per_step": 8 * n * NT, "d2h_bytes_per_step": 8 * (m + nv2) * NT,
+                       "api": "cplb_create_sharded + cplb_eval_host_begin / _wait with CPLB_JAC_COMPUTED: ONE process, one set of pinned host "
                               f"buffers for {world} x 65,536 instances, contiguous index ranges per GPU, no collective"}
             del shp
         dist.barrier(group=host_group)
@@ -604,22 +635,29 @@ def run_ours(args):
                              f"{head['sets'] * bytes_per_launch / 2**20:.0f} MiB total vs 126 MiB L2"},
             "plain_order": dict(spread(plain["ms"]), unit="ms_per_step", value=world * N / (plain_ms * 1e-3), roofline_frac=frac(plain_ms),
                                 note="plain stream order (x may be produced by the kernel launched just before): what a solver loop sees"),
-            "e2e": {"value": world * N / e2e_p_s, "unit": "instances/s", "h2d_bytes_per_step": world * h2d_bytes,
-                    "d2h_bytes_per_step": world * d2h_packed, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_p_s,
-                    "regions_ms_per_step": [1e3 * t for t in e2e_p_all],
-                    "api": "cplb_eval_host_begin / cplb_eval_host_wait with CPLB_JAC_PACKED: a queue of batches on two sets of instance-major "
-                           "pinned host buffers (begin k+1, wait k); every step uploads its x and downloads its g and the x-dependent Jacobian "
-                           f"slots ({nv} of {nnz} per instance; the others are constants the consumer holds: cplb_get_jacobian_constants, "
-                           "cplb_unpack_jacobian; the IFOPT views read packed batches through the slot map); chunked H2D/kernel/D2H on 3 streams",
-                    "packed_equals_full_rows": True,
-                    "pcie_ceiling": {"ms_per_step": 1e3 * ceil_p_s, "value": world * N / ceil_p_s,
-                                     "d2h_GBps_per_gpu": d2h_packed / ceil_p_s / 1e9, "h2d_GBps_per_gpu": h2d_bytes / ceil_p_s / 1e9,
-                                     "aggregate_GBps": world * (d2h_packed + h2d_bytes) / ceil_p_s / 1e9,
+            "e2e": {"value": world * N / e2e_c_s, "unit": "instances/s", "h2d_bytes_per_step": world * h2d_bytes,
+                    "d2h_bytes_per_step": world * d2h_computed, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_c_s,
+                    "regions_ms_per_step": [1e3 * t for t in e2e_c_all],
+                    "api": "cplb_eval_host_begin / cplb_eval_host_wait with CPLB_JAC_COMPUTED: a queue of batches on two sets of instance-major "
+                           "pinned host buffers (begin k+1, wait k); every step uploads its x and downloads its g and the Jacobian slots that "
+                           f"take arithmetic ({nv2} of {nnz} per instance; of the others {nnz - nv} are constants the consumer holds "
+                           f"(cplb_get_jacobian_constants) and {nv - nv2} are plain copies +-x[col] of the x the consumer sent "
+                           "(cplb_get_jacobian_slot_sources); cplb_expand_jacobian rebuilds the full rows, the IFOPT views read such batches in "
+                           "place); chunked H2D/kernel/D2H on 3 streams",
+                    "computed_expands_to_full_rows": True,
+                    "pcie_ceiling": {"ms_per_step": 1e3 * ceil_c_s, "value": world * N / ceil_c_s,
+                                     "d2h_GBps_per_gpu": d2h_computed / ceil_c_s / 1e9, "h2d_GBps_per_gpu": h2d_bytes / ceil_c_s / 1e9,
+                                     "aggregate_GBps": world * (d2h_computed + h2d_bytes) / ceil_c_s / 1e9,
                                      "note": f"raw pinned copies of the same bytes per step (one D2H + one H2D on two streams), all {world} "
                                              "rank(s) at once, max over ranks: the host-side ceiling of e2e on this box"},
-                    "frac_of_pcie_ceiling": ceil_p_s / e2e_p_s,
+                    "frac_of_pcie_ceiling": ceil_c_s / e2e_c_s,
                     "synchronous_call": {"value": world * N / e2e_ps_s, "ms_per_step": 1e3 * e2e_ps_s,
-                                         "api": "cplb_eval_host with CPLB_JAC_PACKED: one batch at a time, returns when its outputs have landed"},
+                                         "api": "cplb_eval_host with CPLB_JAC_COMPUTED: one batch at a time, returns when its outputs have landed"},
+                    "packed_rows": {"value": world * N / e2e_p_s, "ms_per_step": 1e3 * e2e_p_s, "d2h_bytes_per_step": world * d2h_packed,
+                                    "regions_ms_per_step": [1e3 * t for t in e2e_p_all],
+                                    "api": f"the same queue with CPLB_JAC_PACKED slices (all {nv} x-dependent slots: the copies travel too)",
+                                    "pcie_ceiling": {"ms_per_step": 1e3 * ceil_p_s, "value": world * N / ceil_p_s},
+                                    "frac_of_pcie_ceiling": ceil_p_s / e2e_p_s},
                     "full_rows": {"value": world * N / e2e_q_s, "ms_per_step": 1e3 * e2e_q_s, "d2h_bytes_per_step": world * d2h_bytes,
                                   "regions_ms_per_step": [1e3 * t for t in e2e_q_all],
                                   "api": "the same queue with full values[nnz] rows per instance (constants re-transferred every step)",

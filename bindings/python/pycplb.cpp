@@ -61,6 +61,11 @@ PYBIND11_MODULE(pycplb, m)
             const std::vector<int32_t> m = p.GetPackedJacobianMap();
             return py::array_t<int32_t>(m.size(), m.data());
         })
+        .def("GetJacobianSlotSources", [](const cplb::BatchedProblem& p) {
+            std::vector<int32_t> kind, source;
+            p.GetJacobianSlotSources(kind, source);
+            return py::make_tuple(py::array_t<int32_t>(kind.size(), kind.data()), py::array_t<int32_t>(source.size(), source.data()));
+        })
         .def_property_readonly("n", &cplb::BatchedProblem::GetNumberOfOptimizationVariables)
         .def_property_readonly("m", &cplb::BatchedProblem::GetNumberOfConstraints)
         .def_property_readonly("nnz", &cplb::BatchedProblem::GetNumberOfJacobianNonzeros)
@@ -108,26 +113,37 @@ PYBIND11_MODULE(pycplb, m)
         .def("SetForceThreshold", &cplb::BatchedProblem::SetForceThreshold)
         .def("GetForceThreshold", &cplb::BatchedProblem::GetForceThreshold)
         // host arrays, instance-major: x (N, n) -> dict of (N, m), (N, nnz), (N,), (N, n)
-        .def("eval", [](cplb::BatchedProblem& p, darray x, bool g, bool jac, bool cost, bool grad, bool jac_packed) {
+        .def("eval", [](cplb::BatchedProblem& p, darray x, bool g, bool jac, bool cost, bool grad, int jac_packed) {
+            // jac_packed: 0 full rows, 1 (True) CPLB_JAC_PACKED slices, 2 CPLB_JAC_COMPUTED slices
+            if (jac_packed < 0 || jac_packed > 2) throw std::invalid_argument("jac_packed must be 0, 1 or 2");
             if (x.ndim() != 2 || x.shape(1) != p.GetNumberOfOptimizationVariables()) throw std::invalid_argument("x must be (N, n)");
             const py::ssize_t N = x.shape(0);
             py::dict out;
             darray ag, aj, ac, agr;
             if (g) ag = darray({N, (py::ssize_t)p.GetNumberOfConstraints()});
-            if (jac) aj = darray({N, jac_packed ? (py::ssize_t)p.GetPackedJacobianMap().size() : (py::ssize_t)p.GetNumberOfJacobianNonzeros()});
+            if (jac) {
+                py::ssize_t len = (py::ssize_t)p.GetNumberOfJacobianNonzeros();
+                if (jac_packed == 1) len = (py::ssize_t)p.GetPackedJacobianMap().size();
+                if (jac_packed == 2) {
+                    std::vector<int32_t> kind, source;
+                    len = (py::ssize_t)p.GetJacobianSlotSources(kind, source);
+                }
+                aj = darray({N, len});
+            }
             if (cost) ac = darray({N});
             if (grad) agr = darray({N, (py::ssize_t)p.GetNumberOfOptimizationVariables()});
             {
                 py::gil_scoped_release nogil;
                 p.EvaluateHost(N, x.data(), g ? ag.mutable_data() : nullptr, jac ? aj.mutable_data() : nullptr,
-                               cost ? ac.mutable_data() : nullptr, grad ? agr.mutable_data() : nullptr, nullptr, jac_packed ? CPLB_JAC_PACKED : 0);
+                               cost ? ac.mutable_data() : nullptr, grad ? agr.mutable_data() : nullptr, nullptr,
+                               jac_packed == 2 ? CPLB_JAC_COMPUTED : (jac_packed == 1 ? CPLB_JAC_PACKED : 0));
             }
             out["g"] = g ? py::object(ag) : py::none();
             out["jac"] = jac ? py::object(aj) : py::none();
             out["cost"] = cost ? py::object(ac) : py::none();
             out["grad"] = grad ? py::object(agr) : py::none();
             return out;
-        }, py::arg("x"), py::arg("g") = true, py::arg("jac") = true, py::arg("cost") = false, py::arg("grad") = false, py::arg("jac_packed") = false)
+        }, py::arg("x"), py::arg("g") = true, py::arg("jac") = true, py::arg("cost") = false, py::arg("grad") = false, py::arg("jac_packed") = 0)
         // raw device pointers of ONE shard of a sharded problem, on that shard's device and stream
         .def("eval_device_shard", [](cplb::BatchedProblem& p, int shard, int64_t N, int layout, int64_t ld, uintptr_t x, uintptr_t g,
                                      uintptr_t jac, uintptr_t cost, uintptr_t grad, uintptr_t stream) {

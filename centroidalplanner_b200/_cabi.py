@@ -17,6 +17,8 @@ INSTANCE_MAJOR, COMPONENT_MAJOR = 0, 1
 HOST_JAC_CONSTANTS_PRESENT = 1
 DEVICE_INPUTS_READY = 2
 JAC_PACKED = 4
+JAC_COMPUTED = 8   # ... and without the slots that are copies +-x[col] (cplb_get_jacobian_slot_sources)
+SLOT_CONSTANT, SLOT_COPY, SLOT_NEGATED_COPY, SLOT_COMPUTED = 0, 1, 2, 3
 KERNEL_AUTO, KERNEL_PER_CONTACT, KERNEL_PER_INSTANCE = 0, 1, 2
 KERNEL_WARP_TILE, KERNEL_CTA_TILE = 1, 2
 BLOCK_COM, BLOCK_FORCE, BLOCK_POSITION, BLOCK_NORMAL = 0, 1, 2, 3
@@ -53,14 +55,16 @@ class SolverOptions(C.Structure):
     """cplb_solver_options"""
     _fields_ = [("tol", C.c_double), ("mu_init", C.c_double), ("bound_push", C.c_double), ("bound_frac", C.c_double),
                 ("nlp_scaling_max_gradient", C.c_double), ("constr_viol_tol", C.c_double), ("polish_viol_tol", C.c_double),
-                ("bound_relax_factor", C.c_double), ("max_iter", C.c_int32), ("max_backtracks", C.c_int32)]
+                ("bound_relax_factor", C.c_double), ("max_iter", C.c_int32), ("max_backtracks", C.c_int32),
+                ("tail_instances", C.c_int32)]
 
 
 class SolveOutputs(C.Structure):
     """cplb_solve_outputs"""
     _fields_ = [("x", C.c_void_p), ("status", C.c_void_p), ("iterations", C.c_void_p), ("cost", C.c_void_p), ("constr_viol", C.c_void_p),
                 ("dual_inf", C.c_void_p), ("lam", C.c_void_p), ("rounds", C.POINTER(C.c_int32)), ("evaluations", C.POINTER(C.c_int64)),
-                ("instance_evaluations", C.POINTER(C.c_int64))]
+                ("instance_evaluations", C.POINTER(C.c_int64)),
+                ("tail_instances", C.POINTER(C.c_int64))]
 
 
 # name -> (restype, argtypes); every symbol include/cpl_batched.h declares
@@ -82,6 +86,8 @@ PROTOTYPES = {
     "cplb_fill_jacobian_constants": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, dp]),
     "cplb_get_packed_jacobian_map": (C.c_int, [C.c_void_p, ip, ip]),
     "cplb_unpack_jacobian": (C.c_int, [C.c_void_p, C.c_int64, dp, dp]),
+    "cplb_get_jacobian_slot_sources": (C.c_int, [C.c_void_p, ip, ip, ip]),
+    "cplb_expand_jacobian": (C.c_int, [C.c_void_p, C.c_int64, dp, dp, dp]),
     "cplb_get_variable_bounds": (C.c_int, [C.c_void_p, dp, dp]),
     "cplb_get_constraint_bounds": (C.c_int, [C.c_void_p, dp, dp]),
     "cplb_set_mass": (C.c_int, [C.c_void_p, C.c_double]),

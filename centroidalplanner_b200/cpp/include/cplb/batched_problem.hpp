@@ -274,6 +274,16 @@ public:
         check(cplb_get_packed_jacobian_map(_p, &nv, map.data()));
         return map;
     }
+    // where each structural slot's value comes from (cplb_get_jacobian_slot_sources: CPLB_SLOT_* kinds); returns the number of
+    // doubles per instance of a CPLB_JAC_COMPUTED slice
+    int32_t GetJacobianSlotSources(std::vector<int32_t>& kind, std::vector<int32_t>& source) const
+    {
+        int32_t nv = 0;
+        kind.resize(_nnz);
+        source.resize(_nnz);
+        check(cplb_get_jacobian_slot_sources(_p, &nv, kind.data(), source.data()));
+        return nv;
+    }
     void GetJacobianConstants(std::vector<uint8_t>& is_constant, std::vector<double>& value) const
     {
         is_constant.resize(_nnz);
@@ -359,7 +369,8 @@ public:
 
     // ---- evaluation (host buffers, instance-major: instance i owns x[i*n..], g[i*m..], jac[i*nnz..]) ----
     // per_instance: optional per-instance parameter arrays (host pointers, instance-major), nullptr = shared parameters
-    // host_flags: 0 or CPLB_JAC_PACKED (jac then holds GetPackedJacobianMap().size() doubles per instance: the x-dependent slots only)
+    // host_flags: 0, CPLB_JAC_PACKED (jac then holds GetPackedJacobianMap().size() doubles per instance: the x-dependent slots only)
+    // or CPLB_JAC_COMPUTED (GetJacobianSlotSources(): only the slots that take arithmetic)
     void EvaluateHost(int64_t N, const double* x, double* g, double* jac, double* cost, double* grad,
                       const cplb_instance_params* per_instance = nullptr, int32_t host_flags = 0)
     {
@@ -433,7 +444,7 @@ public:
     // (src/CentroidalPlanner.cpp:22-34); all pointers are device pointers, lam may be nullptr.  NOT IPOPT (see the C header).
     struct SolveCounters {
         int32_t rounds = 0;
-        int64_t evaluations = 0, instance_evaluations = 0;
+        int64_t evaluations = 0, instance_evaluations = 0, tail_instances = 0;
     };
     SolveCounters SolveDevice(int64_t N, const double* x0, double* x, int32_t* status, int32_t* iterations, double* cost, double* constr_viol,
                               double* dual_inf, double* lam, void* stream, const cplb_solver_options* options = nullptr)
@@ -450,6 +461,7 @@ public:
         out.rounds = &c.rounds;
         out.evaluations = &c.evaluations;
         out.instance_evaluations = &c.instance_evaluations;
+        out.tail_instances = &c.tail_instances;
         check(cplb_solve_device(_p, N, x0, options, &out, stream));
         return c;
     }

@@ -34,28 +34,37 @@
 namespace cplb {
 namespace solver {
 
-// Host buffers of N instances (instance-major) plus the lazily refreshed outputs.  The Jacobian buffer is PACKED
-// (CPLB_JAC_PACKED): only the x-dependent slots travel device -> host; a view's FillJacobianBlock reads a slot through the
-// slot map and takes the x-independent ones (the 1.0 identities, a Ground's zeros: CentroidalStatics.cpp:93-95,
-// EnvironmentNormal.cpp:66-68, Ground.cpp:33-34,49) from cplb_get_jacobian_constants.  The problem may be sharded over
+// Host buffers of N instances (instance-major) plus the lazily refreshed outputs.  The Jacobian buffer holds COMPUTED slices
+// (CPLB_JAC_COMPUTED): only the slots that take arithmetic travel device -> host; a view's FillJacobianBlock reads those through
+// the slot-source map, takes the x-independent ones (the 1.0 identities, a Ground's zeros: CentroidalStatics.cpp:93-95,
+// EnvironmentNormal.cpp:66-68, Ground.cpp:33-34,49) from cplb_get_jacobian_constants and the plain copies (+-F in the moment rows,
+// -n / -F in FrictionCone's first row: CentroidalStatics.cpp:108-113, FrictionCone.cpp:82-84,93-95) from the instance's own x,
+// which the batch holds -- the same bits the reference writes, a negation being exact.  The problem may be sharded over
 // several GPUs (BatchedProblem's device-list constructor): the batch is then evaluated by all of them at once.
 class InstanceBatch {
 public:
     typedef std::shared_ptr<InstanceBatch> Ptr;
     struct Entry {
         int r, c, slot;
-        int packed;     // index into the instance's packed Jacobian slice, or -1: x-independent
-        double constant;  // its value then
+        int kind;         // CPLB_SLOT_*
+        int source;       // COMPUTED: index into the instance's computed Jacobian slice; (NEGATED_)COPY: column of x
+        double constant;  // CONSTANT: the value
+        double value(const double* computed, const double* x) const
+        {
+            switch (kind) {
+            case CPLB_SLOT_COMPUTED: return computed[source];
+            case CPLB_SLOT_COPY: return x[source];
+            case CPLB_SLOT_NEGATED_COPY: return -x[source];
+            default: return constant;
+            }
+        }
     };
 
     InstanceBatch(BatchedProblem::Ptr problem, int64_t num_instances)
         : _prob(std::move(problem)), _N(num_instances), _n(_prob->GetNumberOfOptimizationVariables()),
           _m(_prob->GetNumberOfConstraints()), _nnz(_prob->GetNumberOfJacobianNonzeros())
     {
-        const std::vector<int32_t> map = _prob->GetPackedJacobianMap();
-        _nv = (int)map.size();
-        _slot_to_packed.assign((size_t)_nnz, -1);
-        for (int q = 0; q < _nv; q++) _slot_to_packed[(size_t)map[(size_t)q]] = q;
+        _nv = _prob->GetJacobianSlotSources(_kind, _source);
         std::vector<uint8_t> is_const;
         _prob->GetJacobianConstants(is_const, _const_value);
         _x = pinned((size_t)_N * _n);
@@ -113,18 +122,18 @@ public:
         Refresh(i);
         return _g + i * _m;
     }
-    // instance i's PACKED Jacobian slice (jac_packed_size() doubles); Entry::packed indexes it
+    // instance i's COMPUTED Jacobian slice (jac_computed_size() doubles); Entry::source indexes it for the computed slots
     const double* jac(int64_t i)
     {
         Refresh(i);
         return _jac + i * _nv;
     }
-    int jac_packed_size() const { return _nv; }
-    // one structural slot of instance i's Jacobian, constants included (what IpoptAdapter::eval_jac_g's values[slot] holds)
+    int jac_computed_size() const { return _nv; }
+    // one structural slot of instance i's Jacobian, constants and copies included (what IpoptAdapter::eval_jac_g's values[slot] holds)
     double jac_value(int64_t i, int slot)
     {
-        const int q = _slot_to_packed[(size_t)slot];
-        return q < 0 ? _const_value[(size_t)slot] : jac(i)[q];
+        const Entry e{0, 0, slot, _kind[(size_t)slot], _source[(size_t)slot], _const_value[(size_t)slot]};
+        return e.value(jac(i), x(i));
     }
     const double* grad(int64_t i)
     {
@@ -166,7 +175,7 @@ public:
         std::vector<Entry> e;
         for (int s = 0; s < _nnz; s++)
             if (_iRow[s] >= row0 && _iRow[s] < row0 + rows && _jCol[s] >= 3 * v && _jCol[s] < 3 * v + 3)
-                e.push_back(Entry{_iRow[s] - row0, _jCol[s] - 3 * v, s, _slot_to_packed[(size_t)s], _const_value[(size_t)s]});
+                e.push_back(Entry{_iRow[s] - row0, _jCol[s] - 3 * v, s, _kind[(size_t)s], _source[(size_t)s], _const_value[(size_t)s]});
         return _blocks.emplace(key, std::move(e)).first->second;
     }
 
@@ -181,7 +190,7 @@ private:
     {
         if (_dirty_lo >= _dirty_hi) return;
         const int64_t lo = _dirty_lo, cnt = _dirty_hi - _dirty_lo;
-        _prob->EvaluateHost(cnt, _x + lo * _n, _g + lo * _m, _jac + lo * _nv, _cost + lo, _grad + lo * _n, nullptr, CPLB_JAC_PACKED);
+        _prob->EvaluateHost(cnt, _x + lo * _n, _g + lo * _m, _jac + lo * _nv, _cost + lo, _grad + lo * _n, nullptr, CPLB_JAC_COMPUTED);
         std::fill(_dirty.begin() + lo, _dirty.begin() + lo + cnt, 0);
         _dirty_lo = _dirty_hi = 0;
         _evaluations++;
@@ -225,7 +234,7 @@ private:
     BatchedProblem::Ptr _prob;
     int64_t _N;
     int _n, _m, _nnz, _nv = 0;
-    std::vector<int> _slot_to_packed;
+    std::vector<int32_t> _kind, _source;
     std::vector<double> _const_value;
     std::exception_ptr _failure;
     int64_t _failure_generation = -1;
@@ -316,8 +325,9 @@ private:
         jac_block.setZero();
         const int v = _batch->var_index(var_set);
         if (v < 0) return;
-        const double* vals = _batch->jac(_i);  // the packed slice
-        for (const auto& e : _batch->Block(_row0, GetRows(), v)) jac_block.coeffRef(e.r, e.c) = e.packed >= 0 ? vals[e.packed] : e.constant;
+        const double* vals = _batch->jac(_i);  // the computed slice (refreshes the instance if it is dirty)
+        const double* xi = _batch->x(_i);
+        for (const auto& e : _batch->Block(_row0, GetRows(), v)) jac_block.coeffRef(e.r, e.c) = e.value(vals, xi);
     }
     InstanceBatch::Ptr _batch;
     int64_t _i;

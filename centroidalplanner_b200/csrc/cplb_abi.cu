@@ -395,6 +395,42 @@ cplb_status cplb_unpack_jacobian(const cplb_problem* p, int64_t num_instances, c
     return CPLB_OK;
 }
 
+cplb_status cplb_get_jacobian_slot_sources(const cplb_problem* p, int32_t* num_computed, int32_t* kind, int32_t* source)
+{
+    CPLB_REQUIRE(p);
+    const cplb::Layout& L = p->layout;
+    if (num_computed) *num_computed = (int32_t)L.computed_to_slot.size();
+    if (kind) std::memcpy(kind, L.slot_kind.data(), sizeof(int32_t) * L.slot_kind.size());
+    if (source) std::memcpy(source, L.slot_source.data(), sizeof(int32_t) * L.slot_source.size());
+    return CPLB_OK;
+}
+
+cplb_status cplb_expand_jacobian(const cplb_problem* p, int64_t num_instances, const double* x, const double* computed, double* full)
+{
+    CPLB_REQUIRE(p);
+    if (num_instances < 0) return fail(CPLB_INVALID_ARGUMENT, "num_instances is negative");
+    if (num_instances == 0) return CPLB_OK;
+    CPLB_REQUIRE(x);
+    CPLB_REQUIRE(computed);
+    CPLB_REQUIRE(full);
+    const cplb::Layout& L = p->layout;
+    const int nv = (int)L.computed_to_slot.size();
+    for (long long i = 0; i < num_instances; i++) {
+        double* row = full + i * L.nnz;
+        const double* src = computed + i * nv;
+        const double* xi = x + i * L.n;
+        for (int s = 0; s < L.nnz; s++) {
+            switch (L.slot_kind[s]) {
+            case cplb::Layout::kConstant: row[s] = L.const_value[s]; break;
+            case cplb::Layout::kCopy: row[s] = xi[L.slot_source[s]]; break;
+            case cplb::Layout::kNegatedCopy: row[s] = -xi[L.slot_source[s]]; break;
+            default: row[s] = src[L.slot_source[s]]; break;
+            }
+        }
+    }
+    return CPLB_OK;
+}
+
 cplb_status cplb_get_variable_bounds(const cplb_problem* p, double* lower, double* upper)
 {
     CPLB_REQUIRE(p);
@@ -759,6 +795,11 @@ static cplb_status check_args(const cplb_problem* p, const cplb_eval_args* a, un
         if (a->layout != CPLB_INSTANCE_MAJOR) return fail(CPLB_INVALID_ARGUMENT, "CPLB_JAC_PACKED needs INSTANCE_MAJOR buffers (COMPONENT_MAJOR host calls skip whole rows with CPLB_HOST_JAC_CONSTANTS_PRESENT instead)");
         *flags |= CPLB_JAC_PACKED_K;
     }
+    if (a->host_flags & CPLB_JAC_COMPUTED) {
+        if (a->layout != CPLB_INSTANCE_MAJOR) return fail(CPLB_INVALID_ARGUMENT, "CPLB_JAC_COMPUTED needs INSTANCE_MAJOR buffers");
+        if (a->host_flags & CPLB_JAC_PACKED) return fail(CPLB_INVALID_ARGUMENT, "CPLB_JAC_PACKED and CPLB_JAC_COMPUTED name two different slice formats: pass one of them");
+        *flags |= CPLB_JAC_COMPUTED_K;
+    }
     (void)p;
     return CPLB_OK;
 }
@@ -906,7 +947,11 @@ cplb_status cplb_get_shard(const cplb_problem* p, int32_t shard, int64_t num_ins
 using HostPipe = cplb_problem::HostPipe;
 
 // doubles per instance of the Jacobian slice of this evaluation: every structural slot, or only the x-dependent ones
-static int jac_len(const cplb_problem* p, unsigned flags) { return (flags & CPLB_JAC_PACKED_K) ? (int)p->layout.packed_to_slot.size() : p->layout.nnz; }
+static int jac_len(const cplb_problem* p, unsigned flags)
+{
+    if (flags & CPLB_JAC_COMPUTED_K) return (int)p->layout.computed_to_slot.size();
+    return (flags & CPLB_JAC_PACKED_K) ? (int)p->layout.packed_to_slot.size() : p->layout.nnz;
+}
 
 static cplb_status ensure_host_pipeline(HostPipe& pipe, size_t bytes_per_stream)
 {
@@ -1329,6 +1374,7 @@ void cplb_solver_default_options(cplb_solver_options* o)
     o->bound_relax_factor = 1e-8;
     o->max_iter = 500;
     o->max_backtracks = 30;
+    o->tail_instances = -1;
 }
 
 cplb_status cplb_solve_device(cplb_problem* p, int64_t num_instances, const double* x0, const cplb_solver_options* options,
@@ -1362,7 +1408,7 @@ cplb_status cplb_solve_device(cplb_problem* p, int64_t num_instances, const doub
     cplb::solver::ShapeHost SH;
     SH.build(L.n, L.m, L.nnz, L.iRow.data(), L.jCol.data(), p->x_lb.data(), p->x_ub.data(), cl.data(), cu.data(), o.bound_relax_factor);
     const cplb::solver::Options O{o.tol, o.mu_init, o.bound_push, o.bound_frac, o.nlp_scaling_max_gradient, o.constr_viol_tol, o.polish_viol_tol,
-                                  o.bound_relax_factor, o.max_iter, o.max_backtracks};
+                                  o.bound_relax_factor, o.max_iter, o.max_backtracks, o.tail_instances};
     cplb::solver::SolveStats stats;
     const long long launches_per_round = 8;
     cudaError_t e = cplb::solver::solve_device(p->P, p->im_kernel, SH, O, num_instances, x0, out->x, out->status, out->iterations, out->cost,
@@ -1372,6 +1418,7 @@ cplb_status cplb_solve_device(cplb_problem* p, int64_t num_instances, const doub
     if (out->rounds) *out->rounds = stats.rounds;
     if (out->evaluations) *out->evaluations = stats.evaluations;
     if (out->instance_evaluations) *out->instance_evaluations = stats.instance_evaluations;
+    if (out->tail_instances) *out->tail_instances = stats.tail_instances;
     return CPLB_OK;
 }
 

@@ -424,7 +424,7 @@ template <int ENV>
 cudaError_t launch_im_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, int im_kernel, cudaStream_t st)
 {
     const bool cta_tile = im_kernel == CPLB_IM_CTA_TILE || (im_kernel == CPLB_IM_AUTO && instance_major_auto_is_cta_tile(P.nc)) ||
-                          (flags & CPLB_JAC_PACKED_K);  // packed Jacobian slices exist in the CTA-tile kernel only
+                          (flags & (CPLB_JAC_PACKED_K | CPLB_JAC_COMPUTED_K));  // packed Jacobian slices exist in the CTA-tile kernel only
     if (cta_tile) return launch_imc_env<ENV>(P, io, flags, Q, st);
     // lanes per instance: the smallest power of two >= nc (capped at 8; more contacts loop)
     if (P.nc <= 1) return launch_im_cfg<ENV, 1>(P, io, flags, Q, st);

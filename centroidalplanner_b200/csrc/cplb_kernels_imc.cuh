@@ -46,7 +46,7 @@ __device__ __forceinline__ void cta_copy(double* dst, const double* src, int cou
     for (int e = tid; e < count; e += nthreads) dst[e] = src[e];
 }
 
-template <int ENV, int TI, unsigned FLAGS, bool PERINST, bool PACKED>
+template <int ENV, int TI, unsigned FLAGS, bool PERINST, int PACKED>
 __global__ void __launch_bounds__(128) eval_instance_major_cta(const __grid_constant__ CplbParams P, const CplbIo io,
                                                                  const unsigned flags_rt, const int aligned16,
                                                                  const __grid_constant__ CplbInstParams Q)
@@ -288,7 +288,7 @@ inline cudaError_t resident_grid(const void* kern, int threads, size_t smem, int
     return cudaSuccess;
 }
 
-template <int ENV, int TI, unsigned FLAGS, bool PERINST, bool PACKED>
+template <int ENV, int TI, unsigned FLAGS, bool PERINST, int PACKED>
 cudaError_t launch_imc_kernel(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
     auto kern = eval_instance_major_cta<ENV, TI, FLAGS, PERINST, PACKED>;
@@ -313,14 +313,19 @@ template <int ENV, int TI>
 cudaError_t launch_imc_ti(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
     const unsigned gj = CPLB_WANT_G | CPLB_WANT_J;
-    if (flags & CPLB_JAC_PACKED_K) {
-        if (Q) return launch_imc_kernel<ENV, TI, 0u, true, true>(P, io, flags, Q, st);
-        if ((flags & 15u) == gj) return launch_imc_kernel<ENV, TI, gj, false, true>(P, io, flags, Q, st);
-        return launch_imc_kernel<ENV, TI, 0u, false, true>(P, io, flags, Q, st);
+    if (flags & CPLB_JAC_COMPUTED_K) {
+        if (Q) return launch_imc_kernel<ENV, TI, 0u, true, 2>(P, io, flags, Q, st);
+        if ((flags & 15u) == gj) return launch_imc_kernel<ENV, TI, gj, false, 2>(P, io, flags, Q, st);
+        return launch_imc_kernel<ENV, TI, 0u, false, 2>(P, io, flags, Q, st);
     }
-    if (Q) return launch_imc_kernel<ENV, TI, 0u, true, false>(P, io, flags, Q, st);
-    if ((flags & 15u) == gj) return launch_imc_kernel<ENV, TI, gj, false, false>(P, io, flags, Q, st);
-    return launch_imc_kernel<ENV, TI, 0u, false, false>(P, io, flags, Q, st);
+    if (flags & CPLB_JAC_PACKED_K) {
+        if (Q) return launch_imc_kernel<ENV, TI, 0u, true, 1>(P, io, flags, Q, st);
+        if ((flags & 15u) == gj) return launch_imc_kernel<ENV, TI, gj, false, 1>(P, io, flags, Q, st);
+        return launch_imc_kernel<ENV, TI, 0u, false, 1>(P, io, flags, Q, st);
+    }
+    if (Q) return launch_imc_kernel<ENV, TI, 0u, true, 0>(P, io, flags, Q, st);
+    if ((flags & 15u) == gj) return launch_imc_kernel<ENV, TI, gj, false, 0>(P, io, flags, Q, st);
+    return launch_imc_kernel<ENV, TI, 0u, false, 0>(P, io, flags, Q, st);
 }
 
 template <int ENV>

@@ -24,6 +24,10 @@ struct Layout {
     struct Run { int begin, end; };  // [begin, end) runs of x-dependent slots
     std::vector<Run> var_runs;
     std::vector<int32_t> packed_to_slot;  // the x-dependent slots in slot order: element q of a PACKED Jacobian slice is slot packed_to_slot[q]
+    // Where the value of a slot comes from: 0 constant (const_value), 1 copy x[source], 2 negated copy -x[source], 3 computed
+    // (source = its index in a COMPUTED Jacobian slice, which holds the computed slots in slot order: computed_to_slot).
+    enum SlotKind { kConstant = 0, kCopy = 1, kNegatedCopy = 2, kComputed = 3 };
+    std::vector<int32_t> slot_kind, slot_source, computed_to_slot;
 
     static int col_com() { return 0; }
     static int col_F(int k) { return 3 + 9 * k; }  // AddVariableSet order: F_, p_, n_ per name (CplProblem.cpp:31-33)
@@ -49,11 +53,20 @@ struct Layout {
         jCol.clear();
         is_const.clear();
         const_value.clear();
+        slot_kind.clear();
+        slot_source.clear();
         auto put = [&](int r, int c, bool constant = false, double value = 0.0) {
             iRow.push_back(r);
             jCol.push_back(c);
             is_const.push_back(constant ? 1 : 0);
             const_value.push_back(value);
+            slot_kind.push_back(constant ? kConstant : kComputed);
+            slot_source.push_back(-1);
+        };
+        auto put_copy = [&](int r, int c, bool negated, int source_col) {  // value is exactly +-x[source_col]
+            put(r, c);
+            slot_kind.back() = negated ? kNegatedCopy : kCopy;
+            slot_source.back() = source_col;
         };
         // CentroidalStatics rows 0..2: identity on every F block (CentroidalStatics.cpp:93-95)
         for (int r = 0; r < 3; r++)
@@ -66,8 +79,9 @@ struct Layout {
             for (int k = 0; k < nc; k++) {
                 put(3 + q, col_F(k) + c0);
                 put(3 + q, col_F(k) + c1);
-                put(3 + q, col_p(k) + c0);
-                put(3 + q, col_p(k) + c1);
+                // -skew(F_k) (:108-113): row 3 <- (F.z, -F.y), row 4 <- (-F.z, F.x), row 5 <- (F.y, -F.x)
+                put_copy(3 + q, col_p(k) + c0, q == 1, col_F(k) + (q == 2 ? 1 : 2));
+                put_copy(3 + q, col_p(k) + c1, q != 1, col_F(k) + (q == 0 ? 1 : 0));
             }
         }
         for (int j = 0; j < nc; j++) {
@@ -82,15 +96,21 @@ struct Layout {
                 }
                 row += 3;
             }
-            for (int i = 0; i < 2; i++) {                            // FrictionCone.cpp:82-87, :93-99
-                for (int c = 0; c < 3; c++) put(row + i, col_F(k) + c);
-                for (int c = 0; c < 3; c++) put(row + i, col_n(k) + c);
-            }
+            for (int c = 0; c < 3; c++) put_copy(row, col_F(k) + c, true, col_n(k) + c);  // FrictionCone.cpp:82-84: -n
+            for (int c = 0; c < 3; c++) put_copy(row, col_n(k) + c, true, col_F(k) + c);  // :93-95: -F
+            for (int c = 0; c < 3; c++) put(row + 1, col_F(k) + c);                       // :85-87
+            for (int c = 0; c < 3; c++) put(row + 1, col_n(k) + c);                       // :97-99
         }
         nnz = (int)iRow.size();
         packed_to_slot.clear();
         for (int s = 0; s < nnz; s++)
             if (!is_const[s]) packed_to_slot.push_back(s);
+        computed_to_slot.clear();
+        for (int s = 0; s < nnz; s++)
+            if (slot_kind[s] == kComputed) {
+                slot_source[s] = (int32_t)computed_to_slot.size();
+                computed_to_slot.push_back(s);
+            }
         var_runs.clear();
         for (int s = 0; s < nnz;) {
             if (is_const[s]) {

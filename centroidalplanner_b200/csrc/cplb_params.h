@@ -17,6 +17,7 @@
 #define CPLB_WANT_J 2u
 #define CPLB_WANT_COST 4u
 #define CPLB_WANT_GRAD 8u
+#define CPLB_JAC_COMPUTED_K 64u  // instance-major: like PACKED, also without the slots that are copies +-x[col] (JacMap<ENV, 2>)
 #define CPLB_JAC_PACKED_K 32u   // instance-major: the Jacobian slice holds only the x-dependent slots (JacMap<ENV, true>)
 #define CPLB_INPUTS_READY 16u  // x / per-instance arrays are not outputs of the preceding kernel: read them before griddepcontrol.wait
 

@@ -25,6 +25,7 @@
 #include <utility>
 #include <vector>
 
+#include "cplb_eval_inline.cuh"
 #include "cplb_kernels.h"
 #include "cplb_solver.h"
 #include "cplb_solver_core.hpp"
@@ -94,6 +95,37 @@ __global__ void __launch_bounds__(kThreads) k_ls_select(const __grid_constant__ 
     phase_ls_select(team, A.S, A.T, A.O, (long long)blockIdx.x, q);
 }
 
+// The tail: one CTA carries one instance through ALL its remaining iterations, the four evaluations of an iteration done in
+// place by eval_one_instance (one thread per evaluation point: the batched kernels' arithmetic as a device function).  Entered
+// once the working set no longer fills the GPU: from there a lock-step round costs its latency floor whatever the count, and
+// every round would be paid by the slowest instance; here each instance pays only its own iterations and the host waits once.
+__global__ void __launch_bounds__(kThreadsLU, 3) k_tail(const __grid_constant__ KernelArgs A, const __grid_constant__ CplbParams P, int it0,
+                                                     unsigned long long* instance_rounds)
+{
+    extern __shared__ __align__(16) double smem[];
+    DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
+    Scratch q;
+    q.carve(smem, A.S.n, A.S.m, A.S.nnz, true);
+    const long long b = (long long)blockIdx.x;
+    const int n = A.S.n, m = A.S.m, nnz = A.S.nnz;
+    auto eval = [&](const double* x, int count, unsigned flags, double* g, double* jac, double* cost, double* grad) {
+        for (int a = team.rank; a < count; a += team.size)
+            eval_one_instance(P, x + (long long)a * n, g ? g + (long long)a * m : nullptr, jac ? jac + (long long)a * nnz : nullptr,
+                              cost ? cost + a : nullptr, grad ? grad + (long long)a * n : nullptr, flags);
+    };
+    const long long inst = A.T.list_cur[b];
+    unsigned rounds = 0;
+    for (int it = it0;;) {
+        tail_iteration(team, A.S, A.T, A.O, b, q, eval);
+        rounds++;
+        it++;
+        phase_round_begin(team, A.S, A.T, A.O, b, q, 0, it == A.O.max_iter, nullptr, true);
+        team.sync();
+        if (!A.T.active[inst]) break;
+    }
+    if (team.rank == 0) atomicAdd(instance_rounds, (unsigned long long)rounds);
+}
+
 __global__ void __launch_bounds__(kThreads) k_finish(const __grid_constant__ KernelArgs A, double* x_out, double* lam_out)
 {
     DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
@@ -113,6 +145,8 @@ struct Workspace {
     size_t state_bytes = 0, shape_bytes = 0;
     int* n_active = nullptr;
     int* n_active_host = nullptr;
+    unsigned long long* tail_rounds = nullptr;  // device counter + its pinned mirror
+    unsigned long long* tail_rounds_host = nullptr;
 };
 
 void workspace_free(Workspace* w)
@@ -122,6 +156,8 @@ void workspace_free(Workspace* w)
     if (w->state_slab) cudaFree(w->state_slab);
     if (w->n_active) cudaFree(w->n_active);
     if (w->n_active_host) cudaFreeHost(w->n_active_host);
+    if (w->tail_rounds) cudaFree(w->tail_rounds);
+    if (w->tail_rounds_host) cudaFreeHost(w->tail_rounds_host);
     delete w;
 }
 
@@ -135,6 +171,7 @@ struct DeviceEngine {
     const double* x0;
     double *x_out, *lam_out;
     size_t smem, smem_small;
+    long long tail_limit;
     cudaError_t err = cudaSuccess;
 
     void check(cudaError_t e)
@@ -171,6 +208,17 @@ struct DeviceEngine {
     void kkt(long long cnt) { run(k_kkt, cnt, smem); }
     void ls_first(long long cnt) { run(k_ls_first, cnt, smem); }
     void ls_select(long long cnt) { run(k_ls_select, cnt, smem_small); }
+    long long tail_threshold() const { return tail_limit; }
+    long long tail(long long running, int it0)
+    {
+        if (err != cudaSuccess) return 0;
+        check(cudaMemsetAsync(W->tail_rounds, 0, sizeof(unsigned long long), st));
+        k_tail<<<(unsigned)running, kThreadsLU, smem, st>>>(A, P, it0, W->tail_rounds);
+        check(cudaGetLastError());
+        check(cudaMemcpyAsync(W->tail_rounds_host, W->tail_rounds, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        check(cudaStreamSynchronize(st));
+        return err == cudaSuccess ? (long long)*W->tail_rounds_host : 0;
+    }
     void finish()
     {
         run(k_finish, N, 0, x_out, lam_out);
@@ -193,6 +241,8 @@ cudaError_t solve_device(const CplbParams& P, int im_kernel, const ShapeHost& SH
     if (!W->n_active) {
         SOLVER_CUDA(cudaMalloc(&W->n_active, sizeof(int)));
         SOLVER_CUDA(cudaHostAlloc((void**)&W->n_active_host, sizeof(int), cudaHostAllocDefault));
+        SOLVER_CUDA(cudaMalloc(&W->tail_rounds, sizeof(unsigned long long)));
+        SOLVER_CUDA(cudaHostAlloc((void**)&W->tail_rounds_host, sizeof(unsigned long long), cudaHostAllocDefault));
     }
     KernelArgs A{};
     A.O = O;
@@ -261,10 +311,20 @@ cudaError_t solve_device(const CplbParams& P, int im_kernel, const ShapeHost& SH
     const size_t smem = probe.carve(nullptr, S.n, S.m, S.nnz, true) * sizeof(double);
     const size_t smem_small = probe.carve(nullptr, S.n, S.m, S.nnz, false) * sizeof(double);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    for (const void* k : {(const void*)k_round_begin, (const void*)k_kkt, (const void*)k_ls_first, (const void*)k_ls_select})
+    for (const void* k : {(const void*)k_round_begin, (const void*)k_kkt, (const void*)k_ls_first, (const void*)k_ls_select, (const void*)k_tail})
         SOLVER_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 
-    DeviceEngine E{P, im_kernel, A, N, st, W, x0, x_out, lam_out, smem, smem_small};
+    // The tail takes over when the working set fits the GPU in one wave of its CTAs (one per instance; `tail_instances` of the
+    // options: < 0 picks SMs x resident CTAs, 0 never).
+    long long tail_limit = O.tail_instances;
+    if (tail_limit < 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        SOLVER_CUDA(cudaGetDevice(&dev));
+        SOLVER_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        SOLVER_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail, kThreadsLU, smem));
+        tail_limit = (long long)sms * (per_sm > 0 ? per_sm : 1);
+    }
+    DeviceEngine E{P, im_kernel, A, N, st, W, x0, x_out, lam_out, smem, smem_small, tail_limit};
     const SolveStats s = solve_loop(E, O, N, SH.nf);
     if (stats) *stats = s;
     return E.err;

@@ -35,6 +35,7 @@ constexpr double kInfBound = 1.0e19;
 struct Options {
     double tol, mu_init, bound_push, bound_frac, max_gradient, constr_viol_tol, polish_viol_tol, bound_relax;
     int max_iter, max_backtracks;
+    int tail_instances;  // working-set size at which the tail takes over (-1: what the GPU holds at once, 0: never)
 };
 
 // Problem-level data shared by all instances (variable / constraint bounds and the Jacobian structure are the problem's).
@@ -412,7 +413,7 @@ CPLB_HD void phase_init_scale(const Team& team, const Shape& S, const State& T, 
 // forward-difference points of the Hessian.  Returns through T.active[i]; *n_active counts the instances still running.
 template <class Team>
 CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T, const Options& O, long long b_prev, Scratch& q, int first_round,
-                               int last_round, int* n_active)
+                               int last_round, int* n_active, bool fixed_slot = false)
 {
     const long long i = T.list_cur[b_prev];  // the working set of the previous round, in its slot order
     Inst I{S, T, i};
@@ -503,13 +504,16 @@ CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T,
             }
             T.mu[i] = mu;
             T.tau[i] = dmax(1.0 - mu, 0.99);
-            // slot in the working set of this round
+            // slot in the working set of this round (the tail kernel keeps an instance in its slot: nobody else is waiting)
+            int slot = (int)b_prev;
+            if (!fixed_slot) {
 #if defined(__CUDA_ARCH__)
-            const int slot = atomicAdd(n_active, 1);
+                slot = atomicAdd(n_active, 1);
 #else
-            const int slot = (*n_active)++;
+                slot = (*n_active)++;
 #endif
-            T.list_next[slot] = (int32_t)i;
+                T.list_next[slot] = (int32_t)i;
+            }
             q.red[1] = (double)slot;
         }
         T.active[i] = active;
@@ -1166,9 +1170,34 @@ inline std::vector<StateField> state_fields(State& T, const ShapeHost& S)
 }
 
 struct SolveStats {
-    int rounds = 0;
+    int rounds = 0;                 // lock-step rounds
     long long evaluations = 0, instance_evaluations = 0;
+    long long tail_instances = 0;   // instances that finished in the tail (on their own, after the lock-step rounds)
 };
+
+// One full iteration of a single instance between two phase_round_begin calls, with the four evaluations done by `eval(x, count,
+// flags, g, jac, cost, grad)` on the instance's slot buffers: what the tail runs.  Returns when the iteration is complete (the
+// new iterate evaluated into ev_*).
+template <class Team, class Eval>
+CPLB_HD void tail_iteration(const Team& team, const Shape& S, const State& T, const Options& O, long long b, Scratch& q, Eval&& eval)
+{
+    const int n = S.n, m = S.m, nnz = S.nnz, P = S.nf + 1;
+    eval(T.x_fd + b * (long long)P * n, P, 2u | 8u, nullptr, T.jac_fd + b * (long long)P * nnz, nullptr, T.grad_fd + b * (long long)P * n);
+    team.sync();
+    phase_kkt(team, S, T, O, b, q);
+    team.sync();
+    eval(T.x_ls + b * (long long)kCandidates * n, kCandidates, 1u | 4u, T.g_ls + b * (long long)kCandidates * m, nullptr,
+         T.cost_ls + b * (long long)kCandidates, nullptr);
+    team.sync();
+    phase_ls_first(team, S, T, O, b, q);
+    team.sync();
+    eval(T.x_soc + b * n, 1, 1u | 4u, T.g_soc + b * m, nullptr, T.cost_soc + b, nullptr);
+    team.sync();
+    phase_ls_select(team, S, T, O, b, q);
+    team.sync();
+    eval(T.xc + b * n, 1, 15u, T.ev_c + b * m, T.ev_jv + b * nnz, T.ev_f + b, T.ev_df + b * n);
+    team.sync();
+}
 
 // The lock-step round, engine-independent.  Engine: init_x(), init_scale(), round_begin(first, last, slots) -> instances still
 // running (the new working set; finished instances leave it: a round costs what its running instances cost), kkt(count),
@@ -1186,6 +1215,14 @@ SolveStats solve_loop(Engine& E, const Options& O, long long N, int nf)
     for (int it = 0; it <= O.max_iter; it++) {
         const long long running = E.round_begin(it == 0, it == O.max_iter, working);  // also swaps the working-set lists
         if (running == 0) break;
+        if (running <= E.tail_threshold()) {
+            // The few instances left iterate on their own from here (one thread team each, evaluations inline): a straggler no
+            // longer costs the whole batch a round trip per iteration, and its iterations cost no host round trip at all.
+            const long long tail_rounds = E.tail(running, it);  // instance-rounds executed
+            st.tail_instances += running;
+            st.instance_evaluations += tail_rounds * (long long)(nf + 1 + kCandidates + 2);
+            break;
+        }
         st.rounds++;
         E.eval_fd(running);   // gradient + Jacobian at the nf + 1 difference points of every running instance
         E.kkt(running);

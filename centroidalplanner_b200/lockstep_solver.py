@@ -55,6 +55,7 @@ class SolveResult:
     evaluations: int           # batched evaluator calls (kernel launches) in total: full + Hessian differences + line-search trials
     instance_evaluations: int  # instances evaluated in total over those calls
     lam: torch.Tensor          # (N, m) constraint multipliers (unscaled)
+    tail_instances: int = 0    # native round only: instances that finished on their own after the lock-step rounds
 
     def ok(self):
         return bool((self.status == SUCCESS).all())

@@ -22,10 +22,10 @@ class NativeInteriorPoint:
     `nlp_scaling_max_gradient`, `bound_relax_factor`)."""
 
     def __init__(self, tol=1e-3, max_iter=500, mu_init=0.1, bound_push=1e-2, bound_frac=1e-2, nlp_scaling_max_gradient=100.0,
-                 constr_viol_tol=1e-4, polish_viol_tol=1e-9, bound_relax_factor=1e-8, max_backtracks=30):
+                 constr_viol_tol=1e-4, polish_viol_tol=1e-9, bound_relax_factor=1e-8, max_backtracks=30, tail_instances=-1):
         self.options = _cabi.SolverOptions(float(tol), float(mu_init), float(bound_push), float(bound_frac), float(nlp_scaling_max_gradient),
                                            float(constr_viol_tol), float(polish_viol_tol), float(bound_relax_factor), int(max_iter),
-                                           int(max_backtracks))
+                                           int(max_backtracks), int(tail_instances))
 
     def Solve(self, problem, x0, per_instance=None):
         """Solve all N instances from the starting points x0 (N, n), a CUDA tensor on the problem's device."""
@@ -46,11 +46,11 @@ class NativeInteriorPoint:
         viol = torch.empty(N, dtype=f64, device=dev)
         dual = torch.empty(N, dtype=f64, device=dev)
         lam = torch.empty(N, problem.m, dtype=f64, device=dev)
-        rounds, evals, inst = C.c_int32(0), C.c_int64(0), C.c_int64(0)
+        rounds, evals, inst, tail = C.c_int32(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
         out = _cabi.SolveOutputs(x.data_ptr(), status.data_ptr(), iters.data_ptr(), cost.data_ptr(), viol.data_ptr(), dual.data_ptr(),
-                                 lam.data_ptr(), C.pointer(rounds), C.pointer(evals), C.pointer(inst))
+                                 lam.data_ptr(), C.pointer(rounds), C.pointer(evals), C.pointer(inst), C.pointer(tail))
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             _check(problem._lib.cplb_solve_device(problem._h, N, x0.data_ptr(), C.byref(self.options), C.byref(out), C.c_void_p(stream)))
         return SolveResult(x=x, status=status.to(torch.int64), iterations=iters.to(torch.int64), cost=cost, constr_viol=viol, dual_inf=dual,
-                           rounds=rounds.value, evaluations=evals.value, instance_evaluations=inst.value, lam=lam)
+                           rounds=rounds.value, evaluations=evals.value, instance_evaluations=inst.value, lam=lam, tail_instances=tail.value)

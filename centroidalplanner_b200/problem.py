@@ -382,6 +382,27 @@ class BatchedCplProblem:
         _check(self._lib.cplb_unpack_jacobian(self._h, a.shape[0], a.ctypes.data_as(_cabi.dp), full.ctypes.data_as(_cabi.dp)))
         return full
 
+    def GetJacobianSlotSources(self):
+        """(kind[nnz], source[nnz]) of cplb_get_jacobian_slot_sources: where each structural slot's value comes from
+        (_cabi.SLOT_CONSTANT / SLOT_COPY x[source] / SLOT_NEGATED_COPY -x[source] / SLOT_COMPUTED element `source` of a
+        jac_packed='computed' slice)."""
+        kind = np.zeros(self.nnz, dtype=np.int32)
+        src = np.zeros(self.nnz, dtype=np.int32)
+        nv = C.c_int32()
+        _check(self._lib.cplb_get_jacobian_slot_sources(self._h, C.byref(nv), kind.ctypes.data_as(_cabi.ip), src.ctypes.data_as(_cabi.ip)))
+        return kind, src
+
+    def ExpandJacobian(self, x, computed):
+        """cplb_expand_jacobian: (N, n) x and (N, nv) computed host slices -> (N, nnz) full rows, constants and copies included."""
+        xa = np.ascontiguousarray(x.numpy() if _is_torch(x) else x, dtype=np.float64)
+        a = np.ascontiguousarray(computed.numpy() if _is_torch(computed) else computed, dtype=np.float64)
+        nv = self._jac_len("computed")
+        if a.ndim != 2 or a.shape[1] != nv or xa.shape != (a.shape[0], self.n):
+            raise ValueError(f"x has shape {xa.shape}, computed {a.shape}; expected (N, {self.n}) and (N, {nv})")
+        full = np.empty((a.shape[0], self.nnz))
+        _check(self._lib.cplb_expand_jacobian(self._h, a.shape[0], xa.ctypes.data_as(_cabi.dp), a.ctypes.data_as(_cabi.dp), full.ctypes.data_as(_cabi.dp)))
+        return full
+
     def FillJacobianConstants(self, jac_host, layout=_cabi.INSTANCE_MAJOR):
         """Write the constant slots of a host jac buffer once; later host evaluations into the same buffer may then
         pass jac_constants_present=True and skip transferring them."""
@@ -434,7 +455,27 @@ class BatchedCplProblem:
             return self._eval_device(x, g, jac, cost, grad, layout, out, stream, per_instance, inputs_ready, jac_packed=jac_packed)
         return self._eval_host(x, g, jac, cost, grad, layout, out, jac_constants_present, per_instance, jac_packed=jac_packed)
 
+    @staticmethod
+    def _is_computed(jac_packed):
+        """jac_packed: False (full rows), True (x-dependent slots), 'computed' (only the slots that take arithmetic)."""
+        if isinstance(jac_packed, str):
+            if jac_packed != "computed":
+                raise ValueError(f"jac_packed={jac_packed!r}: expected False, True or 'computed'")
+            return True
+        return False
+
+    def _jac_flag(self, jac_packed):
+        if self._is_computed(jac_packed):
+            return _cabi.JAC_COMPUTED
+        return _cabi.JAC_PACKED if jac_packed else 0
+
     def _jac_len(self, jac_packed):
+        if self._is_computed(jac_packed):
+            if getattr(self, "_nv2", None) is None:
+                nv = C.c_int32()
+                _check(self._lib.cplb_get_jacobian_slot_sources(self._h, C.byref(nv), None, None))
+                self._nv2 = nv.value
+            return self._nv2
         if not jac_packed:
             return self.nnz
         if getattr(self, "_nv", None) is None:
@@ -471,7 +512,7 @@ class BatchedCplProblem:
         res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self._jac_len(jac_packed)), "cost": buf("cost", cost, None),
                "grad": buf("grad", grad, self.n)}
         pi, keep = self._instance_params(per_instance, N, layout, x.device)
-        args = _cabi.EvalArgs(N, layout, (_cabi.DEVICE_INPUTS_READY if inputs_ready else 0) | (_cabi.JAC_PACKED if jac_packed else 0), N, x.data_ptr(), *[None if res[k] is None else res[k].data_ptr()
+        args = _cabi.EvalArgs(N, layout, (_cabi.DEVICE_INPUTS_READY if inputs_ready else 0) | self._jac_flag(jac_packed), N, x.data_ptr(), *[None if res[k] is None else res[k].data_ptr()
                                                               for k in ("g", "jac", "cost", "grad")],
                               C.pointer(pi) if pi is not None else None)
         s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
@@ -525,7 +566,7 @@ class BatchedCplProblem:
 
         res = {"g": buf("g", g, self.m), "jac": buf("jac", jac, self._jac_len(jac_packed)), "cost": buf("cost", cost, None),
                "grad": buf("grad", grad, self.n)}
-        hflags = (_cabi.HOST_JAC_CONSTANTS_PRESENT if jac_constants_present else 0) | (_cabi.JAC_PACKED if jac_packed else 0)
+        hflags = (_cabi.HOST_JAC_CONSTANTS_PRESENT if jac_constants_present else 0) | self._jac_flag(jac_packed)
         pi, keep = self._instance_params(per_instance, N, layout, None)
         args = _cabi.EvalArgs(N, layout, hflags, N, xa.ctypes.data, *[None if res[k] is None else res[k].ctypes.data
                                                                      for k in ("g", "jac", "cost", "grad")],

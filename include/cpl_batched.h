@@ -249,6 +249,16 @@ typedef struct cplb_instance_params {
  * the same slots of a full evaluation.  Any other layout -> CPLB_INVALID_ARGUMENT. */
 #define CPLB_JAC_PACKED 4
 
+/* Same family, one step further (INSTANCE_MAJOR only, not together with CPLB_JAC_PACKED): `jac` is a COMPUTED slice per instance
+ * that also leaves out the slots whose value is a plain copy of an entry of the instance's own x, +x[col] or -x[col] -- the p_k
+ * entries of the moment rows (-skew(F_k), CentroidalStatics.cpp:108-113) and FrictionCone's first row (-n and -F,
+ * FrictionCone.cpp:82-84, :93-95): 12 per contact.  The caller holds x already, so they need not come back over the link.  What
+ * travels are the entries that take arithmetic: the 6 CoM sums, per contact the 6 moment-row entries +-(p - c), FrictionCone's
+ * second row (6) and a Superquadric's 12 -- 54 of 174 doubles for a 4-contact Ground problem, 102 of 174 for a Superquadric one.
+ * cplb_get_jacobian_slot_sources says for every structural slot where its value comes from; cplb_expand_jacobian rebuilds full
+ * rows on the host (bit-identical to a full evaluation: a negation is exact); the IFOPT views read such a batch in place. */
+#define CPLB_JAC_COMPUTED 8
+
 typedef struct cplb_eval_args {
     int64_t num_instances;
     int32_t layout; /* cplb_layout */
@@ -303,6 +313,19 @@ cplb_status cplb_get_packed_jacobian_map(const cplb_problem *p, int32_t *num_pac
  * values[] array IpoptAdapter::eval_jac_g hands to IPOPT, constants included. */
 cplb_status cplb_unpack_jacobian(const cplb_problem *p, int64_t num_instances, const double *packed, double *full);
 
+/* Where each structural slot's value comes from, for consumers of CPLB_JAC_COMPUTED slices.  kind[nnz], source[nnz] (either may
+ * be NULL): CPLB_SLOT_CONSTANT -> cplb_get_jacobian_constants' value (source -1); CPLB_SLOT_COPY -> x[source] of the same instance;
+ * CPLB_SLOT_NEGATED_COPY -> -x[source]; CPLB_SLOT_COMPUTED -> element `source` of the instance's computed slice (the computed slots
+ * appear in it in slot order).  *num_computed = doubles per instance of a computed slice. */
+#define CPLB_SLOT_CONSTANT 0
+#define CPLB_SLOT_COPY 1
+#define CPLB_SLOT_NEGATED_COPY 2
+#define CPLB_SLOT_COMPUTED 3
+cplb_status cplb_get_jacobian_slot_sources(const cplb_problem *p, int32_t *num_computed, int32_t *kind, int32_t *source);
+/* Host helper: expands num_instances computed slices (computed[i*nv + q]) and the x they were evaluated at (x[i*n + c]) into full
+ * instance-major rows full[i*nnz + s], constants and copies included. */
+cplb_status cplb_expand_jacobian(const cplb_problem *p, int64_t num_instances, const double *x, const double *computed, double *full);
+
 /* ---- the caller of the path: lock-step solves --------------------------------------------------------------------------- */
 
 /* Replaces, for N instances of the problem at once, cpl::CentroidalPlanner::Solve (src/CentroidalPlanner.cpp:22-34:
@@ -326,6 +349,9 @@ typedef struct cplb_solver_options {
     double bound_relax_factor;       /* 1e-8 */
     int32_t max_iter;                /* 500 */
     int32_t max_backtracks;          /* 30 */
+    int32_t tail_instances;          /* -1.  Once no more than this many instances are still running, they leave the lock-step rounds
+                                        and each finishes on its own inside one kernel (a straggler then costs only its own
+                                        iterations).  -1: as many as the GPU holds at once; 0: lock-step rounds to the end. */
 } cplb_solver_options;
 void cplb_solver_default_options(cplb_solver_options *options);
 
@@ -346,6 +372,7 @@ typedef struct cplb_solve_outputs {
     int32_t *rounds;              /* HOST: lock-step rounds executed, or NULL */
     int64_t *evaluations;         /* HOST: batched evaluations launched, or NULL */
     int64_t *instance_evaluations; /* HOST: instances evaluated in total, or NULL */
+    int64_t *tail_instances;      /* HOST: instances that finished on their own after the lock-step rounds, or NULL */
 } cplb_solve_outputs;
 
 /* x0 [N n]: starting points (DEVICE pointer, like every array of `out`), variable and constraint bounds as set on the problem.

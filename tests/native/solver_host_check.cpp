@@ -67,6 +67,29 @@ struct HostEngine {
     void kkt(long long cnt) { for (long long b = 0; b < cnt; b++) phase_kkt(team, S, T, O, b, q); }
     void ls_first(long long cnt) { for (long long b = 0; b < cnt; b++) phase_ls_first(team, S, T, O, b, q); }
     void ls_select(long long cnt) { for (long long b = 0; b < cnt; b++) phase_ls_select(team, S, T, O, b, q); }
+    long long tail_limit = 0;
+    long long tail_threshold() const { return tail_limit; }
+    long long tail(long long running, int it0)
+    {
+        long long rounds = 0;
+        auto eval = [&](const double* x, int count, unsigned flags, double* g, double* jac, double* cost, double* grad) {
+            (void)flags;
+            for (int a = 0; a < count; a++)
+                cpl_oracle_eval(o, x + (long long)a * S.n, g ? g + (long long)a * S.m : nullptr, jac ? jac + (long long)a * S.nnz : nullptr,
+                                cost ? cost + a : nullptr, grad ? grad + (long long)a * S.n : nullptr);
+        };
+        for (long long b = 0; b < running; b++) {
+            for (int it = it0;;) {
+                tail_iteration(team, S, T, O, b, q, eval);
+                rounds++;
+                it++;
+                int dummy = 0;
+                phase_round_begin(team, S, T, O, b, q, 0, it == O.max_iter, &dummy, true);
+                if (!T.active[T.list_cur[b]]) break;
+            }
+        }
+        return rounds;
+    }
     void finish() { for (long long i = 0; i < N; i++) phase_finish(team, S, T, i, x_out.data(), lam_out.data()); }
     void eval_full(long long cnt) { cpl_oracle_eval_batch(o, cnt, T.xc, T.ev_c, T.ev_jv, T.ev_f, T.ev_df, threads); }
     void eval_fd(long long cnt) { cpl_oracle_eval_batch(o, cnt * (S.nf + 1), T.x_fd, nullptr, T.jac_fd, nullptr, T.grad_fd, threads); }
@@ -158,8 +181,9 @@ int main(int argc, char** argv)
     HostEngine E;
     E.o = o;
     E.N = N;
-    E.O = Options{1e-3, 0.1, 1e-2, 1e-2, 100.0, 1e-4, 1e-9, 1e-8, 500, 30};
+    E.O = Options{1e-3, 0.1, 1e-2, 1e-2, 100.0, 1e-4, 1e-9, 1e-8, 500, 30, 0};
     if (getenv("SOLVER_TOL")) E.O.tol = atof(getenv("SOLVER_TOL"));
+    if (getenv("SOLVER_TAIL")) E.tail_limit = atoll(getenv("SOLVER_TAIL"));
     if (getenv("SOLVER_FORCE_WEIGHT"))
         for (int k = 0; k < nc; k++) cpl_oracle_set_force_weight(o, k, atof(getenv("SOLVER_FORCE_WEIGHT")));
     E.SH.build(n, m, nnz, iRow.data(), jCol.data(), xl.data(), xu.data(), cl.data(), cu.data(), E.O.bound_relax);

@@ -334,6 +334,36 @@ def test_packed_jacobian_map_and_host_unpack(case):
         prob.UnpackJacobian(jac)            # full rows are not packed slices
 
 
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_jacobian_slot_sources_against_the_oracle(case):
+    """cplb_get_jacobian_slot_sources: every slot marked as a copy holds exactly +-x[source] in the reference's values (the p_k
+    entries of the moment rows, CentroidalStatics.cpp:108-113; FrictionCone's first row, FrictionCone.cpp:82-84,93-95), the
+    constants are the constants, and cplb_expand_jacobian (host-only) rebuilds the oracle's full rows from x and the computed
+    slots alone.  No GPU involved."""
+    prob, o, gen = make_pair(case)
+    kind, src = prob.GetJacobianSlotSources()
+    mask, cval = prob.GetJacobianConstants()
+    nc = o.nc
+    assert np.array_equal(kind == _cabi.SLOT_CONSTANT, mask)
+    assert int((kind == _cabi.SLOT_COPY).sum() + (kind == _cabi.SLOT_NEGATED_COPY).sum()) == 12 * nc
+    comp = np.nonzero(kind == _cabi.SLOT_COMPUTED)[0]
+    expect = {orc.ENV_NONE: 6 + 12 * nc, orc.ENV_GROUND: 6 + 12 * nc, orc.ENV_SUPERQUADRIC: 6 + 24 * nc}[o.env_kind]
+    assert len(comp) == expect and np.array_equal(src[comp], np.arange(len(comp)))   # computed slots appear in slot order
+    x = gen(64)
+    x[0] = 0.0                                                                       # -0.0 and NaN rows of the default start
+    jac = o.eval_batch(x, want=("jac",))["jac"]
+    for s in np.nonzero(kind == _cabi.SLOT_COPY)[0]:
+        assert same_bits_host(jac[:, s], x[:, src[s]]), (case, s)
+    for s in np.nonzero(kind == _cabi.SLOT_NEGATED_COPY)[0]:
+        assert same_bits_host(jac[:, s], -x[:, src[s]]) and np.array_equal(np.signbit(jac[:, s]), np.signbit(-x[:, src[s]])), (case, s)
+    full = prob.ExpandJacobian(x, np.ascontiguousarray(jac[:, comp]))
+    assert same_bits_host(full, jac)
+    with pytest.raises(ValueError):
+        prob.ExpandJacobian(x, jac)
+    with pytest.raises(ValueError, match="computed"):
+        prob._jac_flag("dense")
+
+
 def same_bits_host(a, b):
     na, nb = np.isnan(a), np.isnan(b)
     return bool((na == nb).all() and (a[~na] == b[~nb]).all())

@@ -348,9 +348,27 @@ def test_testbasic_through_the_native_solve_round(case, cuda_device):
     prob, names, par = product_problem(case)
     x0 = starts(prob, 256, seed=7, device=cuda_device)
     before = prob.launch_count()
-    res = solve_and_check(case, prob, names, par, x0, solver_cls=cpl.NativeInteriorPoint)
+    import functools
+
+    # lock-step rounds to the end (tail_instances=0): a round per iteration of the slowest instance
+    res = solve_and_check(case, prob, names, par, x0, solver_cls=functools.partial(cpl.NativeInteriorPoint, tail_instances=0))
     assert res.evaluations == 1 + 4 * res.rounds and prob.launch_count() > before
-    assert res.instance_evaluations > 0 and int(res.iterations.max()) == res.rounds
+    assert res.instance_evaluations > 0 and int(res.iterations.max()) == res.rounds and res.tail_instances == 0
+    # The tail (one CTA carries an instance through all its remaining iterations, evaluations inline) runs the same arithmetic in
+    # the same order: whether it takes over from the first round (default: 256 instances fit the GPU at once), late (once 40 are
+    # left) or never, every instance must end at the same bits after the same number of iterations.
+    max_iter = 1000 if case == "superquadric" else 500
+    for tail, expect_all in ((-1, True), (40, False)):
+        alt = cpl.NativeInteriorPoint(max_iter=max_iter, tail_instances=tail).Solve(prob, x0)
+        assert torch.equal(alt.status, res.status) and torch.equal(alt.iterations, res.iterations), (case, tail)
+        assert torch.equal(alt.x.view(torch.int64), res.x.view(torch.int64)), (case, tail)
+        assert torch.equal(alt.lam.view(torch.int64), res.lam.view(torch.int64)) and torch.equal(alt.cost.view(torch.int64), res.cost.view(torch.int64))
+        assert alt.instance_evaluations == res.instance_evaluations, (case, tail)
+        if expect_all:
+            assert alt.rounds == 0 and alt.tail_instances == 256
+        else:
+            assert alt.rounds <= res.rounds and alt.tail_instances <= 40     # (all may converge in the same round: no tail then)
+            assert (alt.rounds < res.rounds) == (alt.tail_instances > 0)
 
 
 @pytest.mark.gpu

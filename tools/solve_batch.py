@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--solver", default="native", choices=["native", "torch"],
                     help="native: cplb_solve_device (csrc/cplb_solver.cu); torch: the previous driver (lockstep_solver.py)")
+    ap.add_argument("--tail", type=int, default=-1,
+                    help="native solver: working-set size at which the tail takes over (-1: what the GPU holds at once; 0: never)")
     a = ap.parse_args()
     out = {"metric": "end-to-end solves/s (lock-step interior-point stand-in, NOT IPOPT)", "case": a.case, "instances": a.instances}
     # one process per GPU under torchrun: instances shard by index (no collective on the solve path), time = max over ranks
@@ -55,7 +57,7 @@ def main():
     if not a.no_gpu:
         if a.solver == "native":
             import centroidalplanner_b200 as cpl
-            solver = cpl.NativeInteriorPoint()
+            solver = cpl.NativeInteriorPoint(tail_instances=a.tail)
         from centroidalplanner_b200 import sharding
         prob, _, _ = ts.product_problem(a.case)
         dev = torch.device("cuda", local)
@@ -89,7 +91,7 @@ def main():
         out["gpu"] = {"n_gpus": world, "solves_per_s": a.instances / best, "seconds": best, "succeeded": ok, "rounds": res.rounds,
                       "kernel_launches": prob.launch_count() - l0, "instance_evaluations": res.instance_evaluations,
                       "iterations_median": float(res.iterations.double().median()), "iterations_max": int(res.iterations.max()),
-                      "per_rank_seconds_rounds": per_rank,
+                      "per_rank_seconds_rounds": per_rank, "tail_instances": getattr(res, "tail_instances", 0),
                       "max_constr_viol": float(res.constr_viol[res.status == SUCCESS].max())}
 
     if rank != 0:
