@@ -124,7 +124,7 @@ PROTOTYPES = {
     "cplb_eval_host_begin": (C.c_int, [C.c_void_p, C.POINTER(EvalArgs), C.POINTER(C.c_int32)]),
     "cplb_eval_host_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "cplb_solver_default_options": (None, [C.POINTER(SolverOptions)]),
-    "cplb_solve_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(SolverOptions), C.POINTER(SolveOutputs), C.c_void_p]),
+    "cplb_solve_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(InstanceParams), C.POINTER(SolverOptions), C.POINTER(SolveOutputs), C.c_void_p]),
     "cplb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cplb_host_free": (C.c_int, [C.c_void_p]),
     "cplb_set_component_major_kernel": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -447,7 +447,8 @@ public:
         int64_t evaluations = 0, instance_evaluations = 0, tail_instances = 0;
     };
     SolveCounters SolveDevice(int64_t N, const double* x0, double* x, int32_t* status, int32_t* iterations, double* cost, double* constr_viol,
-                              double* dual_inf, double* lam, void* stream, const cplb_solver_options* options = nullptr)
+                              double* dual_inf, double* lam, void* stream, const cplb_solver_options* options = nullptr,
+                              const cplb_instance_params* per_instance = nullptr)
     {
         SolveCounters c;
         cplb_solve_outputs out{};
@@ -462,7 +463,7 @@ public:
         out.evaluations = &c.evaluations;
         out.instance_evaluations = &c.instance_evaluations;
         out.tail_instances = &c.tail_instances;
-        check(cplb_solve_device(_p, N, x0, options, &out, stream));
+        check(cplb_solve_device(_p, N, x0, per_instance, options, &out, stream));
         return c;
     }
 

@@ -1377,8 +1377,8 @@ void cplb_solver_default_options(cplb_solver_options* o)
     o->tail_instances = -1;
 }
 
-cplb_status cplb_solve_device(cplb_problem* p, int64_t num_instances, const double* x0, const cplb_solver_options* options,
-                              const cplb_solve_outputs* out, void* cuda_stream)
+cplb_status cplb_solve_device(cplb_problem* p, int64_t num_instances, const double* x0, const cplb_instance_params* per_instance,
+                              const cplb_solver_options* options, const cplb_solve_outputs* out, void* cuda_stream)
 {
     CPLB_REQUIRE(p);
     CPLB_REQUIRE(out);
@@ -1411,7 +1411,11 @@ cplb_status cplb_solve_device(cplb_problem* p, int64_t num_instances, const doub
                                   o.bound_relax_factor, o.max_iter, o.max_backtracks, o.tail_instances};
     cplb::solver::SolveStats stats;
     const long long launches_per_round = 8;
-    cudaError_t e = cplb::solver::solve_device(p->P, p->im_kernel, SH, O, num_instances, x0, out->x, out->status, out->iterations, out->cost,
+    CplbInstParams q{};
+    const bool per_inst = any_instance_param(per_instance);
+    if (per_inst)
+        for (const auto& f : kInstFields) q.*(f.dst) = per_instance->*(f.src);
+    cudaError_t e = cplb::solver::solve_device(p->P, p->im_kernel, per_inst ? &q : nullptr, SH, O, num_instances, x0, out->x, out->status, out->iterations, out->cost,
                                                out->constr_viol, out->dual_inf, out->lam, &stats, &p->solver_ws, static_cast<cudaStream_t>(cuda_stream));
     if (e != cudaSuccess) return cuda_fail(e, "cplb_solve_device");
     p->launches.fetch_add(stats.evaluations + launches_per_round / 2 * stats.rounds + 3, std::memory_order_relaxed);

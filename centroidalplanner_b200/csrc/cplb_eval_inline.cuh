@@ -20,11 +20,11 @@ struct PointerEmitter {
     __device__ __forceinline__ void grad(int col, double v) const { gradp[col] = v; }
 };
 
-template <int ENV>
-__device__ void eval_one_instance_env(const CplbParams& P, const double* x, double* g, double* jac, double* cost_out, double* grad, unsigned flags)
+template <int ENV, class PS>
+__device__ void eval_one_instance_env(const CplbParams& P, const PS& ps, const double* x, double* g, double* jac, double* cost_out, double* grad,
+                                      unsigned flags)
 {
     const int nc = P.nc;
-    const SharedParams ps{P};
     PointerEmitter em{g, jac, grad};
     const double c[3] = {x[0], x[1], x[2]};
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -51,7 +51,7 @@ __device__ void eval_one_instance_env(const CplbParams& P, const double* x, doub
     }
     if (flags & CPLB_WANT_G) {
 #pragma unroll
-        for (int r = 0; r < 6; r++) em.g(r, r < 3 ? (v[r] - P.wrench[r]) + P.mg[r] : v[r] - P.wrench[r]);  // :56-57
+        for (int r = 0; r < 6; r++) em.g(r, r < 3 ? (v[r] - ps.wrench(r)) + ps.mg(r) : v[r] - ps.wrench(r));  // :56-57
     }
     if (flags & CPLB_WANT_J) {
         const int L = jac_moment_row_len(nc), s3 = 3 * nc;
@@ -68,16 +68,30 @@ __device__ void eval_one_instance_env(const CplbParams& P, const double* x, doub
     }
     if (flags & CPLB_WANT_GRAD) {
 #pragma unroll
-        for (int q = 0; q < 3; q++) em.grad(q, P.W_com * (c[q] - P.com_ref[q]));
+        for (int q = 0; q < 3; q++) em.grad(q, ps.W_com() * (c[q] - ps.com_ref(q)));
     }
 }
 
-__device__ __noinline__ void eval_one_instance(const CplbParams& P, const double* x, double* g, double* jac, double* cost, double* grad, unsigned flags)
+template <class PS>
+__device__ __forceinline__ void eval_one_instance_ps(const CplbParams& P, const PS& ps, const double* x, double* g, double* jac, double* cost,
+                                                     double* grad, unsigned flags)
 {
     switch (P.env) {
-    case CPLB_ENV_NONE_K: eval_one_instance_env<CPLB_ENV_NONE_K>(P, x, g, jac, cost, grad, flags); break;
-    case CPLB_ENV_GROUND_K: eval_one_instance_env<CPLB_ENV_GROUND_K>(P, x, g, jac, cost, grad, flags); break;
-    default: eval_one_instance_env<CPLB_ENV_SUPERQUADRIC_K>(P, x, g, jac, cost, grad, flags); break;
+    case CPLB_ENV_NONE_K: eval_one_instance_env<CPLB_ENV_NONE_K>(P, ps, x, g, jac, cost, grad, flags); break;
+    case CPLB_ENV_GROUND_K: eval_one_instance_env<CPLB_ENV_GROUND_K>(P, ps, x, g, jac, cost, grad, flags); break;
+    default: eval_one_instance_env<CPLB_ENV_SUPERQUADRIC_K>(P, ps, x, g, jac, cost, grad, flags); break;
+    }
+}
+
+// Q == nullptr: the problem's shared parameters; else instance `inst` of the per-instance arrays (instance-major, as
+// cplb_instance_params lays them out), read the way the batched kernels read them (InstanceParams<false>)
+__device__ __noinline__ void eval_one_instance(const CplbParams& P, const CplbInstParams* Q, long long inst, const double* x, double* g, double* jac,
+                                               double* cost, double* grad, unsigned flags)
+{
+    if (Q == nullptr) {
+        eval_one_instance_ps(P, SharedParams{P}, x, g, jac, cost, grad, flags);
+    } else {
+        eval_one_instance_ps(P, InstanceParams<false>{P, *Q, inst, 0}, x, g, jac, cost, grad, flags);
     }
 }
 

@@ -99,8 +99,9 @@ __global__ void __launch_bounds__(kThreads) k_ls_select(const __grid_constant__ 
 // place by eval_one_instance (one thread per evaluation point: the batched kernels' arithmetic as a device function).  Entered
 // once the working set no longer fills the GPU: from there a lock-step round costs its latency floor whatever the count, and
 // every round would be paid by the slowest instance; here each instance pays only its own iterations and the host waits once.
-__global__ void __launch_bounds__(kThreadsLU, 3) k_tail(const __grid_constant__ KernelArgs A, const __grid_constant__ CplbParams P, int it0,
-                                                     unsigned long long* instance_rounds)
+__global__ void __launch_bounds__(kThreadsLU, 3) k_tail(const __grid_constant__ KernelArgs A, const __grid_constant__ CplbParams P,
+                                                        const __grid_constant__ CplbInstParams Q, int per_instance, int it0,
+                                                        unsigned long long* instance_rounds)
 {
     extern __shared__ __align__(16) double smem[];
     DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
@@ -108,12 +109,12 @@ __global__ void __launch_bounds__(kThreadsLU, 3) k_tail(const __grid_constant__ 
     q.carve(smem, A.S.n, A.S.m, A.S.nnz, true);
     const long long b = (long long)blockIdx.x;
     const int n = A.S.n, m = A.S.m, nnz = A.S.nnz;
+    const long long inst = A.T.list_cur[b];
     auto eval = [&](const double* x, int count, unsigned flags, double* g, double* jac, double* cost, double* grad) {
         for (int a = team.rank; a < count; a += team.size)
-            eval_one_instance(P, x + (long long)a * n, g ? g + (long long)a * m : nullptr, jac ? jac + (long long)a * nnz : nullptr,
-                              cost ? cost + a : nullptr, grad ? grad + (long long)a * n : nullptr, flags);
+            eval_one_instance(P, per_instance ? &Q : nullptr, inst, x + (long long)a * n, g ? g + (long long)a * m : nullptr,
+                              jac ? jac + (long long)a * nnz : nullptr, cost ? cost + a : nullptr, grad ? grad + (long long)a * n : nullptr, flags);
     };
-    const long long inst = A.T.list_cur[b];
     unsigned rounds = 0;
     for (int it = it0;;) {
         tail_iteration(team, A.S, A.T, A.O, b, q, eval);
@@ -124,6 +125,34 @@ __global__ void __launch_bounds__(kThreadsLU, 3) k_tail(const __grid_constant__ 
         if (!A.T.active[inst]) break;
     }
     if (team.rank == 0) atomicAdd(instance_rounds, (unsigned long long)rounds);
+}
+
+// Per-instance parameter arrays (cplb_instance_params) in the order of the working set: the batched evaluations of a round run
+// over slot-ordered buffers (one point per slot, nf + 1 difference points per slot, kCandidates line-search points per slot), so
+// every round the parameters of the running instances are laid out the same way -- one row per evaluated point.
+struct ParamGather {
+    const double* src[CPLB_NUM_INST_ARRAYS];
+    double* one[CPLB_NUM_INST_ARRAYS];  // [slots][len]
+    double* fd[CPLB_NUM_INST_ARRAYS];   // [slots][reps_fd][len]
+    double* ls[CPLB_NUM_INST_ARRAYS];   // [slots][reps_ls][len]
+    int len[CPLB_NUM_INST_ARRAYS];
+    int reps_fd, reps_ls;
+};
+
+__global__ void __launch_bounds__(kThreads) k_gather_params(const __grid_constant__ ParamGather G, const int32_t* list)
+{
+    const long long b = (long long)blockIdx.x, i = list[b];
+    for (int a = 0; a < CPLB_NUM_INST_ARRAYS; a++) {
+        if (G.src[a] == nullptr) continue;
+        const int len = G.len[a], rows = 1 + G.reps_fd + G.reps_ls;
+        for (int t = (int)threadIdx.x; t < rows * len; t += (int)blockDim.x) {
+            const int row = t / len, e = t - row * len;
+            const double v = G.src[a][i * len + e];
+            if (row == 0) G.one[a][b * len + e] = v;
+            else if (row <= G.reps_fd) G.fd[a][(b * G.reps_fd + (row - 1)) * (long long)len + e] = v;
+            else G.ls[a][(b * G.reps_ls + (row - 1 - G.reps_fd)) * (long long)len + e] = v;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) k_finish(const __grid_constant__ KernelArgs A, double* x_out, double* lam_out)
@@ -147,6 +176,8 @@ struct Workspace {
     int* n_active_host = nullptr;
     unsigned long long* tail_rounds = nullptr;  // device counter + its pinned mirror
     unsigned long long* tail_rounds_host = nullptr;
+    void* param_slab = nullptr;  // slot-ordered copies of the per-instance parameter arrays
+    size_t param_bytes = 0;
 };
 
 void workspace_free(Workspace* w)
@@ -157,6 +188,7 @@ void workspace_free(Workspace* w)
     if (w->n_active) cudaFree(w->n_active);
     if (w->n_active_host) cudaFreeHost(w->n_active_host);
     if (w->tail_rounds) cudaFree(w->tail_rounds);
+    if (w->param_slab) cudaFree(w->param_slab);
     if (w->tail_rounds_host) cudaFreeHost(w->tail_rounds_host);
     delete w;
 }
@@ -172,18 +204,22 @@ struct DeviceEngine {
     double *x_out, *lam_out;
     size_t smem, smem_small;
     long long tail_limit;
+    const CplbInstParams* Qsrc;  // per-instance parameter arrays in instance order, or nullptr
+    ParamGather G;
+    CplbInstParams Q_one, Q_fd, Q_ls;
+    bool gathered = false;
     cudaError_t err = cudaSuccess;
 
     void check(cudaError_t e)
     {
         if (err == cudaSuccess && e != cudaSuccess) err = e;
     }
-    void eval(const double* x, double* g, double* jac, double* cost, double* grad, long long count)
+    void eval(const double* x, double* g, double* jac, double* cost, double* grad, long long count, const CplbInstParams* Q)
     {
         if (err != cudaSuccess) return;
         unsigned flags = (g ? CPLB_WANT_G : 0u) | (jac ? CPLB_WANT_J : 0u) | (cost ? CPLB_WANT_COST : 0u) | (grad ? CPLB_WANT_GRAD : 0u);
         CplbIo io{x, g, jac, cost, grad, count, count};
-        check(launch_instance_major(P, io, flags, nullptr, im_kernel, st));
+        check(launch_instance_major(P, io, flags, Qsrc ? Q : nullptr, im_kernel, st));
     }
     // one CTA per slot of the working set (or per instance for the phases outside the rounds)
     template <class K, class... Args>
@@ -203,7 +239,13 @@ struct DeviceEngine {
         check(cudaMemcpyAsync(W->n_active_host, W->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
         check(cudaStreamSynchronize(st));
         std::swap(A.T.list_cur, A.T.list_next);  // the instances still running, in the order their CTAs got there
-        return err == cudaSuccess ? *W->n_active_host : 0;
+        const long long running = err == cudaSuccess ? *W->n_active_host : 0;
+        if (Qsrc && running > tail_limit) {  // the lock-step evaluations of this round read the parameters in slot order
+            k_gather_params<<<(unsigned)running, kThreads, 0, st>>>(G, A.T.list_cur);
+            check(cudaGetLastError());
+            gathered = true;
+        }
+        return running;
     }
     void kkt(long long cnt) { run(k_kkt, cnt, smem); }
     void ls_first(long long cnt) { run(k_ls_first, cnt, smem); }
@@ -213,7 +255,7 @@ struct DeviceEngine {
     {
         if (err != cudaSuccess) return 0;
         check(cudaMemsetAsync(W->tail_rounds, 0, sizeof(unsigned long long), st));
-        k_tail<<<(unsigned)running, kThreadsLU, smem, st>>>(A, P, it0, W->tail_rounds);
+        k_tail<<<(unsigned)running, kThreadsLU, smem, st>>>(A, P, Qsrc ? *Qsrc : CplbInstParams{}, Qsrc ? 1 : 0, it0, W->tail_rounds);
         check(cudaGetLastError());
         check(cudaMemcpyAsync(W->tail_rounds_host, W->tail_rounds, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         check(cudaStreamSynchronize(st));
@@ -224,15 +266,17 @@ struct DeviceEngine {
         run(k_finish, N, 0, x_out, lam_out);
         check(cudaStreamSynchronize(st));
     }
-    void eval_full(long long cnt) { eval(A.T.xc, A.T.ev_c, A.T.ev_jv, A.T.ev_f, A.T.ev_df, cnt); }
-    void eval_fd(long long cnt) { eval(A.T.x_fd, nullptr, A.T.jac_fd, nullptr, A.T.grad_fd, cnt * (A.S.nf + 1)); }
-    void eval_ls(long long cnt) { eval(A.T.x_ls, A.T.g_ls, nullptr, A.T.cost_ls, nullptr, cnt * kCandidates); }
-    void eval_soc(long long cnt) { eval(A.T.x_soc, A.T.g_soc, nullptr, A.T.cost_soc, nullptr, cnt); }
+    // (before the first round the slots are the instances: the caller's arrays serve as they are)
+    void eval_full(long long cnt) { eval(A.T.xc, A.T.ev_c, A.T.ev_jv, A.T.ev_f, A.T.ev_df, cnt, gathered ? &Q_one : Qsrc); }
+    void eval_fd(long long cnt) { eval(A.T.x_fd, nullptr, A.T.jac_fd, nullptr, A.T.grad_fd, cnt * (A.S.nf + 1), &Q_fd); }
+    void eval_ls(long long cnt) { eval(A.T.x_ls, A.T.g_ls, nullptr, A.T.cost_ls, nullptr, cnt * kCandidates, &Q_ls); }
+    void eval_soc(long long cnt) { eval(A.T.x_soc, A.T.g_soc, nullptr, A.T.cost_soc, nullptr, cnt, &Q_one); }
 };
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-cudaError_t solve_device(const CplbParams& P, int im_kernel, const ShapeHost& SH, const Options& O, long long N, const double* x0, double* x_out,
+cudaError_t solve_device(const CplbParams& P, int im_kernel, const CplbInstParams* per_instance, const ShapeHost& SH, const Options& O, long long N,
+                         const double* x0, double* x_out,
                          int32_t* status, int32_t* iterations, double* cost, double* viol, double* dual, double* lam_out, SolveStats* stats,
                          Workspace** wsp, cudaStream_t st)
 {
@@ -324,7 +368,52 @@ cudaError_t solve_device(const CplbParams& P, int im_kernel, const ShapeHost& SH
         SOLVER_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail, kThreadsLU, smem));
         tail_limit = (long long)sms * (per_sm > 0 ? per_sm : 1);
     }
-    DeviceEngine E{P, im_kernel, A, N, st, W, x0, x_out, lam_out, smem, smem_small, tail_limit};
+    // ---- per-instance parameters: slot-ordered copies, one row per evaluated point ----
+    ParamGather G{};
+    CplbInstParams Q_one{}, Q_fd{}, Q_ls{};
+    if (per_instance) {
+        const double* const src[CPLB_NUM_INST_ARRAYS] = {per_instance->mass, per_instance->wrench, per_instance->mu, per_instance->F_thr,
+                                                         per_instance->ground_z, per_instance->com_ref, per_instance->W_com, per_instance->p_ref,
+                                                         per_instance->F_ref, per_instance->W_p, per_instance->W_F};
+        const int nc = P.nc, len[CPLB_NUM_INST_ARRAYS] = {1, 6, 1, nc, 1, 3, 1, 3 * nc, 3 * nc, nc, nc};
+        G.reps_fd = S.nf + 1;
+        G.reps_ls = kCandidates;
+        const size_t rows = 1 + (size_t)G.reps_fd + (size_t)G.reps_ls;
+        size_t param_bytes = 0;
+        for (int a = 0; a < CPLB_NUM_INST_ARRAYS; a++)
+            if (src[a]) param_bytes += 3 * 256 + rows * (size_t)len[a] * (size_t)N * sizeof(double);
+        if (param_bytes > W->param_bytes) {
+            if (W->param_slab) SOLVER_CUDA(cudaFree(W->param_slab));
+            W->param_slab = nullptr;
+            W->param_bytes = 0;
+            SOLVER_CUDA(cudaMalloc(&W->param_slab, param_bytes));
+            W->param_bytes = param_bytes;
+        }
+        unsigned char* base = static_cast<unsigned char*>(W->param_slab);
+        auto carve = [&](size_t doubles) {
+            double* p = reinterpret_cast<double*>(base);
+            base += align_up(doubles * sizeof(double));
+            return p;
+        };
+        const double** one[CPLB_NUM_INST_ARRAYS] = {&Q_one.mass, &Q_one.wrench, &Q_one.mu, &Q_one.F_thr, &Q_one.ground_z, &Q_one.com_ref, &Q_one.W_com,
+                                                     &Q_one.p_ref, &Q_one.F_ref, &Q_one.W_p, &Q_one.W_F};
+        const double** fd[CPLB_NUM_INST_ARRAYS] = {&Q_fd.mass, &Q_fd.wrench, &Q_fd.mu, &Q_fd.F_thr, &Q_fd.ground_z, &Q_fd.com_ref, &Q_fd.W_com,
+                                                    &Q_fd.p_ref, &Q_fd.F_ref, &Q_fd.W_p, &Q_fd.W_F};
+        const double** ls[CPLB_NUM_INST_ARRAYS] = {&Q_ls.mass, &Q_ls.wrench, &Q_ls.mu, &Q_ls.F_thr, &Q_ls.ground_z, &Q_ls.com_ref, &Q_ls.W_com,
+                                                    &Q_ls.p_ref, &Q_ls.F_ref, &Q_ls.W_p, &Q_ls.W_F};
+        for (int a = 0; a < CPLB_NUM_INST_ARRAYS; a++) {
+            G.src[a] = src[a];
+            G.len[a] = len[a];
+            if (!src[a]) continue;
+            G.one[a] = carve((size_t)N * len[a]);
+            G.fd[a] = carve((size_t)N * G.reps_fd * len[a]);
+            G.ls[a] = carve((size_t)N * G.reps_ls * len[a]);
+            *one[a] = G.one[a];
+            *fd[a] = G.fd[a];
+            *ls[a] = G.ls[a];
+        }
+    }
+    DeviceEngine E{P, im_kernel, A, N, st, W, x0, x_out, lam_out, smem, smem_small, tail_limit, per_instance, G, Q_one, Q_fd, Q_ls};
     const SolveStats s = solve_loop(E, O, N, SH.nf);
     if (stats) *stats = s;
     return E.err;

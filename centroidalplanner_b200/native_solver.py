@@ -28,9 +28,9 @@ class NativeInteriorPoint:
                                            int(max_backtracks), int(tail_instances))
 
     def Solve(self, problem, x0, per_instance=None):
-        """Solve all N instances from the starting points x0 (N, n), a CUDA tensor on the problem's device."""
-        if per_instance:
-            raise NotImplementedError("per-instance parameters: use LockStepInteriorPoint (the native round solves one parameter set per batch)")
+        """Solve all N instances from the starting points x0 (N, n), a CUDA tensor on the problem's device.  per_instance: dict of
+        per-instance parameter arrays (contiguous float64 CUDA tensors, (N,) / (N, len): cplb_instance_params), every instance then
+        solves its own planning problem."""
         x0 = torch.as_tensor(x0)
         if not x0.is_cuda:
             raise ValueError("cplb_solve_device needs device-resident starting points (there is no CPU solve path)")
@@ -50,7 +50,10 @@ class NativeInteriorPoint:
         out = _cabi.SolveOutputs(x.data_ptr(), status.data_ptr(), iters.data_ptr(), cost.data_ptr(), viol.data_ptr(), dual.data_ptr(),
                                  lam.data_ptr(), C.pointer(rounds), C.pointer(evals), C.pointer(inst), C.pointer(tail))
         stream = torch.cuda.current_stream(dev).cuda_stream
+        pi, keep = problem._instance_params(per_instance, N, _cabi.INSTANCE_MAJOR, dev)
         with torch.cuda.device(dev):
-            _check(problem._lib.cplb_solve_device(problem._h, N, x0.data_ptr(), C.byref(self.options), C.byref(out), C.c_void_p(stream)))
+            _check(problem._lib.cplb_solve_device(problem._h, N, x0.data_ptr(), None if pi is None else C.byref(pi), C.byref(self.options),
+                                                  C.byref(out), C.c_void_p(stream)))
+        del keep
         return SolveResult(x=x, status=status.to(torch.int64), iterations=iters.to(torch.int64), cost=cost, constr_viol=viol, dual_inf=dual,
                            rounds=rounds.value, evaluations=evals.value, instance_evaluations=inst.value, lam=lam, tail_instances=tail.value)

@@ -376,10 +376,13 @@ typedef struct cplb_solve_outputs {
 } cplb_solve_outputs;
 
 /* x0 [N n]: starting points (DEVICE pointer, like every array of `out`), variable and constraint bounds as set on the problem.
+ * per_instance: NULL, or per-instance parameter arrays as for cplb_eval_device (DEVICE pointers, instance-major, row i = instance
+ * i): every instance then solves ITS planning problem -- its own wrench, mass, friction coefficient, references ... -- which is what
+ * a sweep over planning scenarios is; the bounds stay the problem's.
  * Synchronises `cuda_stream` (the host reads one counter per round).  Single-device problems only: one solve batch per GPU,
  * instances shard across GPUs by running one batch per device. */
-cplb_status cplb_solve_device(cplb_problem *p, int64_t num_instances, const double *x0, const cplb_solver_options *options,
-                              const cplb_solve_outputs *out, void *cuda_stream);
+cplb_status cplb_solve_device(cplb_problem *p, int64_t num_instances, const double *x0, const cplb_instance_params *per_instance,
+                              const cplb_solver_options *options, const cplb_solve_outputs *out, void *cuda_stream);
 
 /* Pinned host memory for cplb_eval_host buffers (cudaHostAlloc / cudaFreeHost). */
 cplb_status cplb_host_alloc(size_t bytes, void **out);

@@ -3,6 +3,7 @@
 // Replays the parameter sets of the reference's tests (tests/TestBasic.cpp:64-135 testGroundEnv, :138-222 testSuperquadricEnv,
 // :225-292 testCoMPlanner) from a batch of perturbed starting points and checks the reference's EXPECT lines on every instance.
 //   usage: solver_host_check [ground|superquadric|complanner|simple] [N]
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -66,7 +67,36 @@ struct HostEngine {
     }
     void kkt(long long cnt) { for (long long b = 0; b < cnt; b++) phase_kkt(team, S, T, O, b, q); }
     void ls_first(long long cnt) { for (long long b = 0; b < cnt; b++) phase_ls_first(team, S, T, O, b, q); }
-    void ls_select(long long cnt) { for (long long b = 0; b < cnt; b++) phase_ls_select(team, S, T, O, b, q); }
+    long long trace = -1;  // SOLVER_TRACE=<instance>: one line per iteration of that instance
+    void ls_select(long long cnt)
+    {
+        for (long long b = 0; b < cnt; b++) {
+            const long long i = T.list_cur[b];
+            double alpha_sel = 0.0;
+            if (i == trace) {
+                double viol = 0.0;
+                for (int r = 0; r < S.m; r++) {
+                    const double c = T.c[i * S.m + r] * T.dc[i * S.m + r];
+                    (void)c;
+                }
+                printf("  it %3d mu %.2e a_p %.3e a_d %.3e tiny %d pol %d okK %d acc0 %d delta %.2e |dx| ", T.iters[i], T.mu[i], T.a_p[i], T.a_d[i], T.tiny[i],
+                       T.pol[i], T.okK[i], T.accepted0[i], T.delta_last[i]);
+                double nd = 0.0;
+                for (int j = 0; j < S.n; j++) nd = std::fmax(nd, std::fabs(T.dx[i * S.n + j]));
+                printf("%.3e", nd);
+                (void)viol;
+                (void)alpha_sel;
+            }
+            const double f_before = T.f[i];
+            std::vector<double> xb(T.x + i * S.n, T.x + (i + 1) * S.n);
+            phase_ls_select(team, S, T, O, b, q);
+            if (i == trace) {
+                double step = 0.0;
+                for (int j = 0; j < S.n; j++) step = std::fmax(step, std::fabs(T.x[i * S.n + j] - xb[j]));
+                printf(" step %.3e f %.6e\n", step, f_before);
+            }
+        }
+    }
     long long tail_limit = 0;
     long long tail_threshold() const { return tail_limit; }
     long long tail(long long running, int it0)
@@ -184,6 +214,7 @@ int main(int argc, char** argv)
     E.O = Options{1e-3, 0.1, 1e-2, 1e-2, 100.0, 1e-4, 1e-9, 1e-8, 500, 30, 0};
     if (getenv("SOLVER_TOL")) E.O.tol = atof(getenv("SOLVER_TOL"));
     if (getenv("SOLVER_TAIL")) E.tail_limit = atoll(getenv("SOLVER_TAIL"));
+    if (getenv("SOLVER_TRACE")) E.trace = atoll(getenv("SOLVER_TRACE"));
     if (getenv("SOLVER_FORCE_WEIGHT"))
         for (int k = 0; k < nc; k++) cpl_oracle_set_force_weight(o, k, atof(getenv("SOLVER_FORCE_WEIGHT")));
     E.SH.build(n, m, nnz, iRow.data(), jCol.data(), xl.data(), xu.data(), cl.data(), cu.data(), E.O.bound_relax);
@@ -231,6 +262,18 @@ int main(int argc, char** argv)
                         printf("instance %lld: environment row %d of contact %d = %.3e\n", i, r, j, g[6 + per * j + r]);
                     }
         }
+    }
+    if (getenv("SOLVER_HIST")) {
+        std::vector<int> hist(20, 0);
+        for (long long i = 0; i < N; i++) hist[std::min(19, E.T.iters[i] / 10)]++;
+        printf("iterations histogram (bins of 10):");
+        for (int h : hist) printf(" %d", h);
+        printf("\nslowest:");
+        std::vector<long long> idx(N);
+        for (long long i = 0; i < N; i++) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](long long a, long long b) { return E.T.iters[a] > E.T.iters[b]; });
+        for (int k = 0; k < 8 && k < N; k++) printf(" %lld(%d)", idx[k], E.T.iters[idx[k]]);
+        printf("\n");
     }
     printf("%s: N %lld, %d rounds, %lld batched evaluations (%lld instance evaluations), max iterations %d, worst statics residual %.2e -> %d failures\n",
            which.c_str(), N, st.rounds, st.evaluations, st.instance_evaluations, max_it, worst_viol, failures);

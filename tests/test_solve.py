@@ -372,6 +372,49 @@ def test_testbasic_through_the_native_solve_round(case, cuda_device):
 
 
 @pytest.mark.gpu
+def test_native_round_with_per_instance_parameters(cuda_device):
+    """A sweep: every instance solves ITS planning problem (own manipulation wrench and mass) through cplb_solve_device, and must
+    balance its own wrench and weight (the equilibrium lines of TEST_F testGroundEnv, tests/TestBasic.cpp:131-136).  Lock-step
+    rounds (the parameter arrays are gathered into working-set order every round), the tail (reads them by instance) and a mix
+    must end at the same bits."""
+    prob, names, par = product_problem("ground")
+    N = 300
+    rng = np.random.default_rng(5)
+    wrench = np.tile(par["wrench"], (N, 1)) + rng.normal(0.0, 20.0, (N, 6)) * np.array([1, 1, 1, 0.2, 0.2, 1.0])
+    mass = rng.uniform(60.0, 140.0, N)
+    mu = rng.uniform(0.4, 0.8, N)
+    per_instance = {"wrench": torch.as_tensor(wrench, device=cuda_device), "mass": torch.as_tensor(mass, device=cuda_device),
+                    "mu": torch.as_tensor(mu, device=cuda_device)}
+    x0 = starts(prob, N, seed=3, device=cuda_device)
+    res = cpl.NativeInteriorPoint(tail_instances=0).Solve(prob, x0, per_instance=per_instance)
+    ok = (res.status == SUCCESS).cpu().numpy()
+    # (random wrenches and friction coefficients: the stand-in's line search, which has no restoration phase, may run out of
+    # iterations on a few of them; every instance it reports as solved must pass every line)
+    assert ok.mean() >= 0.95, (res.status.tolist(), res.iterations.tolist())
+    for i, (com, cmap) in enumerate(solution_maps(names, res.x.cpu().numpy())):
+        if not ok[i]:
+            continue
+        F_sum, T_sum = np.zeros(3), np.zeros(3)
+        for F, p, n in cmap.values():
+            F_sum += F
+            T_sum += np.cross(p - com, F)
+            assert abs(p[2] - par["ground_z"]) < 1e-6 and abs(n[2] - 1.0) < 1e-6
+            assert -F.dot(n) <= RELAX and np.linalg.norm(F - n.dot(F) * n) - mu[i] * F.dot(n) <= RELAX
+        assert np.abs(F_sum - (wrench[i, :3] - mass[i] * np.array([0.0, 0.0, G]))).max() < 1e-6
+        assert np.abs(T_sum - wrench[i, 3:]).max() < 1e-5
+    for tail in (-1, 100):
+        alt = cpl.NativeInteriorPoint(tail_instances=tail).Solve(prob, x0, per_instance=per_instance)
+        assert torch.equal(alt.status, res.status) and torch.equal(alt.iterations, res.iterations), tail
+        assert torch.equal(alt.x.view(torch.int64), res.x.view(torch.int64)), tail
+        assert alt.tail_instances == (N if tail < 0 else alt.tail_instances) and alt.tail_instances <= max(N, tail)
+    # the shared-parameter solve of the same starts is a different problem: the sweep really used the arrays
+    shared = cpl.NativeInteriorPoint().Solve(prob, x0)
+    assert not torch.equal(shared.x, res.x)
+    with pytest.raises(ValueError, match="elements"):
+        cpl.NativeInteriorPoint().Solve(prob, x0, per_instance={"mass": per_instance["mass"][:10].contiguous()})
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", ["ground", "com_planner", "example_planner"])
 def test_native_round_and_the_previous_driver_find_the_same_solutions(case, cuda_device):
     """Same algorithm, different linear algebra (own pivoted LU in shared memory vs cuBLAS): both drivers must succeed from the
