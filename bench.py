@@ -389,9 +389,9 @@ def run_ours(args):
     x0s[1:] += torch.as_tensor(np.random.default_rng(2025 + rank).normal(0.0, 0.05, tuple(x0s[1:].shape)))
     x0s = x0s.to(dev)
     solver = cpl.NativeInteriorPoint()
-    solver.Solve(prob, x0s[:64])
+    solver.Solve(prob, x0s)      # warm-up at full size: state slabs, every kernel of the lock-step rounds and of the tail
     solve_s = []
-    for _ in range(3):
+    for _ in range(5):
         barrier()
         t0 = time.perf_counter()
         sres = solver.Solve(prob, x0s)

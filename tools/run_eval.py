@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--im-kernel", default="auto", choices=["auto", "warp", "cta"], help="cplb_set_instance_major_kernel")
     ap.add_argument("--cm-kernel", default="auto", choices=["auto", "split", "whole"], help="cplb_set_component_major_kernel")
     ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays of one rotation over the buffer sets (no Python launch path in the step)")
+    ap.add_argument("--slices", default="full", choices=["full", "packed", "computed"],
+                    help="instance-major Jacobian slice format: all structural slots, CPLB_JAC_PACKED, CPLB_JAC_COMPUTED")
     ap.add_argument("--perinst", action="store_true", help="per-instance constraint parameters (mass, wrench, mu, thresholds, ground z)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
@@ -41,7 +43,9 @@ def main():
     if a.n > x.shape[0]:
         x = np.tile(x, ((a.n + x.shape[0] - 1) // x.shape[0], 1))[: a.n]
     layout = cpl.INSTANCE_MAJOR if a.layout == "instance" else cpl.COMPONENT_MAJOR
-    per = 8 * (prob.n + prob.m + prob.nnz) * a.n
+    jp = {"full": False, "packed": True, "computed": "computed"}[a.slices]
+    jac_len = prob._jac_len(jp)
+    per = 8 * (prob.n + prob.m + jac_len) * a.n   # bytes the launch has to move (x in, g and the Jacobian slices out)
     sets = a.sets or max(2, int(np.ceil(8 * 126 * 2**20 / per)))
     xd = torch.from_numpy(x).cuda()
     if layout == cpl.COMPONENT_MAJOR:
@@ -49,7 +53,7 @@ def main():
     xs = [xd.clone() for _ in range(sets)]
     shp = (lambda L: (a.n, L)) if layout == cpl.INSTANCE_MAJOR else (lambda L: (L, a.n))
     outs = [{"g": torch.empty(shp(prob.m), dtype=torch.float64, device="cuda"),
-             "jac": torch.empty(shp(prob.nnz), dtype=torch.float64, device="cuda")} for _ in range(sets)]
+             "jac": torch.empty(shp(jac_len), dtype=torch.float64, device="cuda")} for _ in range(sets)]
     if a.all:
         for o in outs:
             o["cost"] = torch.empty(a.n, dtype=torch.float64, device="cuda")
@@ -65,11 +69,11 @@ def main():
             pi["ground_z"] = rng.uniform(-0.2, 0.4, a.n)
         pi = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in pi.items()}
     for i in range(a.warmup):
-        prob.eval(xs[i % sets], g=True, jac=True, cost=a.all, grad=a.all, layout=layout, out=outs[i % sets], per_instance=pi)
+        prob.eval(xs[i % sets], g=True, jac=True, cost=a.all, grad=a.all, layout=layout, out=outs[i % sets], per_instance=pi, jac_packed=jp)
     torch.cuda.synchronize()
     def step(i):
         s = (a.warmup + i) % sets
-        prob.eval(xs[s], g=True, jac=True, cost=a.all, grad=a.all, layout=layout, out=outs[s], inputs_ready=a.ready, per_instance=pi)
+        prob.eval(xs[s], g=True, jac=True, cost=a.all, grad=a.all, layout=layout, out=outs[s], inputs_ready=a.ready, per_instance=pi, jac_packed=jp)
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if a.graph:
@@ -101,7 +105,7 @@ def main():
     if a.graph:
         a.case += " [graph]"
     tag = f" im={a.im_kernel}" if a.layout == "instance" else f" cm={a.cm_kernel}"
-    print(f"{a.case} {a.layout}{tag}{' perinst' if a.perinst else ''}{' all4' if a.all else ''} N={a.n} steps={a.steps} sets={sets}: {ms*1e3:.2f} us/step, "
+    print(f"{a.case} {a.layout}{tag}{' perinst' if a.perinst else ''}{' all4' if a.all else ''}{'' if a.slices == 'full' else ' ' + a.slices} N={a.n} steps={a.steps} sets={sets}: {ms*1e3:.2f} us/step, "
           f"{a.n/ms/1e3:.1f} M inst/s, {alg/ms/1e6:.0f} GB/s algorithmic ({alg/ms/1e6/6449.7*100:.1f}% of 6449.7)")
 
 
