@@ -46,8 +46,8 @@ __device__ __forceinline__ void cta_copy(double* dst, const double* src, int cou
     for (int e = tid; e < count; e += nthreads) dst[e] = src[e];
 }
 
-template <int ENV, int TI, unsigned FLAGS, bool PERINST, int PACKED>
-__global__ void __launch_bounds__(128) eval_instance_major_cta(const __grid_constant__ CplbParams P, const CplbIo io,
+template <int ENV, int TI, unsigned FLAGS, bool PERINST, int PACKED, int ROLES>
+__global__ void __launch_bounds__(128 * ROLES) eval_instance_major_cta(const __grid_constant__ CplbParams P, const CplbIo io,
                                                                  const unsigned flags_rt, const int aligned16,
                                                                  const __grid_constant__ CplbInstParams Q)
 {
@@ -58,7 +58,14 @@ __global__ void __launch_bounds__(128) eval_instance_major_cta(const __grid_cons
     const int tid = threadIdx.x, nthreads = blockDim.x;
     using M = JacMap<ENV, PACKED>;
     const int nc = P.nc, n = P.n, m = P.m, nnz = PACKED ? M::per_instance(P.nc) : P.nnz;  // nnz: doubles per instance of the jac slice
-    const int inst = tid % TI, j = tid / TI;  // j: sorted rank of this thread's contact; j >= nc: padding thread (barriers only)
+    // ROLES == 2: every (instance, contact) pair has two threads with complementary shares of the contact's rows (the first half of
+    // the CTA takes CentroidalStatics' entries and the cheaper of {environment rows, FrictionCone}, the second half the other) --
+    // twice the warps per SM on the same shared memory, which is what the kernel's latency chains need
+    constexpr int kPartsA = ROLES == 1 ? kPartAll : (ENV == CPLB_ENV_SUPERQUADRIC_K ? (kPartStatics | kPartFriction) : (kPartStatics | kPartEnvironment));
+    constexpr int kPartsB = kPartAll & ~kPartsA;
+    const int per_role = nthreads / ROLES;
+    const int role = ROLES == 1 ? 0 : tid / per_role, idx = ROLES == 1 ? tid : tid - role * per_role;
+    const int inst = idx % TI, j = idx / TI;  // j: sorted rank of this thread's contact; j >= nc: padding thread (barriers only)
     const bool has_contact = j < nc;
     const int k = has_contact ? P.perm[j] : 0;
 
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(128) eval_instance_major_cta(const __grid_cons
         if (range_valid(0) && is_bulk(0)) issue_load(0, 0);
     }
     TileEmitter em{gs ? gs + (size_t)inst * m : nullptr, js ? js + (size_t)inst * nnz : nullptr, grads ? grads + (size_t)inst * n : nullptr};
-    if (!PACKED && (flags & CPLB_WANT_J) && has_contact) contact_constant_slots<ENV>(em, nc, j, k);  // once: the tile buffer persists
+    if (!PACKED && (flags & CPLB_WANT_J) && has_contact && role == 0) contact_constant_slots<ENV>(em, nc, j, k);  // once: the tile buffer persists
     __syncthreads();  // mbarrier inits visible to every thread before anyone polls them
     if (flags_rt & CPLB_INPUTS_READY) pdl_wait();  // the first tile's x is already on its way; nothing is stored before this
 
@@ -151,13 +158,15 @@ __global__ void __launch_bounds__(128) eval_instance_major_cta(const __grid_cons
                 nn[q] = xk[6 + q];
             }
             double* mine = exch + (size_t)j * ER * TI + inst;
-            if (flags & (CPLB_WANT_G | CPLB_WANT_J)) {
+            if (role != 0) {
+                // the exchange is the first thread's
+            } else if (flags & (CPLB_WANT_G | CPLB_WANT_J)) {
                 const double d0 = p[0] - c[0], d1 = p[1] - c[1], d2 = p[2] - c[2];
                 mine[0 * TI] = d1 * F[2] - d2 * F[1];  // (p - CoM).cross(F), CentroidalStatics.cpp:53
                 mine[1 * TI] = d2 * F[0] - d0 * F[2];
                 mine[2 * TI] = d0 * F[1] - d1 * F[0];
             }
-            if (flags & CPLB_WANT_COST) mine[cost_row * TI] = contact_cost(ps, P.reduction_order, k, F, p);
+            if ((flags & CPLB_WANT_COST) && role == 0) mine[cost_row * TI] = contact_cost(ps, P.reduction_order, k, F, p);
             if constexpr (PERINST) {
                 // FrictionCone / Ground parameters were fetched above; the rest of ps is read where it is used
                 struct Hoisted {
@@ -171,16 +180,18 @@ __global__ void __launch_bounds__(128) eval_instance_major_cta(const __grid_cons
                     __device__ __forceinline__ double F_ref(int kk, int q) const { return base.F_ref(kk, q); }
                     __device__ __forceinline__ double p_ref(int kk, int q) const { return base.p_ref(kk, q); }
                 } hp{ps, mu, F_thr, gz};
-                contact_rows<ENV, false, PACKED>(P, hp, em, nc, j, k, c, F, p, nn, flags);
+                if (role == 0) contact_rows<ENV, false, PACKED, kPartsA>(P, hp, em, nc, j, k, c, F, p, nn, flags);
+                else contact_rows<ENV, false, PACKED, kPartsB>(P, hp, em, nc, j, k, c, F, p, nn, flags);
             } else {
-                contact_rows<ENV, false, PACKED>(P, ps, em, nc, j, k, c, F, p, nn, flags);
+                if (role == 0) contact_rows<ENV, false, PACKED, kPartsA>(P, ps, em, nc, j, k, c, F, p, nn, flags);
+                else contact_rows<ENV, false, PACKED, kPartsB>(P, ps, em, nc, j, k, c, F, p, nn, flags);
             }
         }
         __syncthreads();  // exchange complete; every thread is done with this tile's x buffer
 
         if (live) {
             if (flags & (CPLB_WANT_G | CPLB_WANT_J)) {
-                for (int r = j; r < 6; r += nc) {
+                for (int r = j + role * nc; r < 6; r += ROLES * nc) {
                     // row r's running sum visits the contacts in sorted-name order (CentroidalStatics.cpp:44-54): force rows
                     // read the forces back from the x tile (still intact: the prefetch went to the other buffer)
                     double v = 0.0;
@@ -207,7 +218,7 @@ __global__ void __launch_bounds__(128) eval_instance_major_cta(const __grid_cons
                     }
                 }
             }
-            if (j == 0) {
+            if (j == 0 && role == 0) {
                 if (flags & CPLB_WANT_COST) {  // MinimizeCentroidalVariables.cpp:126-147: contacts in sorted order, then the CoM term
                     double cost = 0.0;
                     for (int jj = 0; jj < nc; jj++) cost += exch[(size_t)jj * ER * TI + cost_row * TI + inst];
@@ -288,11 +299,11 @@ inline cudaError_t resident_grid(const void* kern, int threads, size_t smem, int
     return cudaSuccess;
 }
 
-template <int ENV, int TI, unsigned FLAGS, bool PERINST, int PACKED>
-cudaError_t launch_imc_kernel(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
+template <int ENV, int TI, unsigned FLAGS, bool PERINST, int PACKED, int ROLES>
+cudaError_t launch_imc_roles(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
-    auto kern = eval_instance_major_cta<ENV, TI, FLAGS, PERINST, PACKED>;
-    const int threads = ((TI * P.nc + 31) / 32) * 32;
+    auto kern = eval_instance_major_cta<ENV, TI, FLAGS, PERINST, PACKED, ROLES>;
+    const int threads = ROLES * (((TI * P.nc + 31) / 32) * 32);
     const int jac_len = PACKED ? JacMap<ENV, PACKED>::per_instance(P.nc) : P.nnz;
     const size_t smem = cta_tile_doubles(TI, P.nc, P.n, P.m, jac_len, flags & 15u) * sizeof(double) + 2 * sizeof(uint64_t);
     int resident = 0;
@@ -304,6 +315,17 @@ cudaError_t launch_imc_kernel(const CplbParams& P, const CplbIo& io, unsigned fl
     // complete tiles hold TI (even) instances: TI*n*8, TI*m*8, TI*nnz*8 bytes are multiples of 16
     const int aligned16 = al16(io.x) && al16(io.g) && al16(io.jac) && al16(io.grad) && (TI % 2 == 0);
     return launch_pdl(kern, blocks, (unsigned)threads, smem, st, P, io, flags, aligned16, Q ? *Q : kNoInstParams);
+}
+
+template <int ENV, int TI, unsigned FLAGS, bool PERINST, int PACKED>
+cudaError_t launch_imc_kernel(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
+{
+    // Two threads per (instance, contact) where it pays (measured, profiles/r02_instance_major.md): full Jacobian rows with shared
+    // parameters (+1 point Ground, +4 points Superquadric at 65,536 instances).  Packed / computed slices keep one thread: their
+    // smaller tiles let more CTAs share an SM, which the doubled register footprint would undo (computed: 89.8 % -> 79 %), and
+    // per-instance parameters would be fetched twice (73.9 % -> 64 %).
+    constexpr int kRoles = (PACKED == 0 && !PERINST) ? 2 : 1;
+    return launch_imc_roles<ENV, TI, FLAGS, PERINST, PACKED, kRoles>(P, io, flags, Q, st);
 }
 
 // tile size by contact count: threads = TI * nc stays <= 256, the CTA's shared memory <= ~75 KB (3 CTAs per SM)
