@@ -333,9 +333,22 @@ def test_native_solve_round_on_the_cpu_with_the_oracle(tmp_path):
     subprocess.check_call([shutil.which("g++") or "g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(root, "oracle"),
                            "-I", os.path.join(root, "centroidalplanner_b200", "csrc"), os.path.join(root, "tests", "native", "solver_host_check.cpp"),
                            "-o", exe, "-L", os.path.join(root, "oracle"), "-lcpl_oracle", f"-Wl,-rpath,{os.path.join(root, 'oracle')}", "-lpthread"])
+    summary = {}
     for which, n in (("ground", 64), ("complanner", 64), ("simple", 64)):
         r = subprocess.run([exe, which, str(n)], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "-> 0 failures" in r.stdout, r.stdout + r.stderr
+        summary[which] = r.stdout.strip().splitlines()[-1]
+    # the tail (tail_iteration: an instance on its own through all its remaining iterations) taking over at 16 running instances
+    # and from the first round: same instances evaluated, same iteration counts, same residuals as the lock-step rounds
+    import re
+
+    def key(line):
+        return re.search(r"\((\d+) instance evaluations\), max iterations (\d+), worst statics residual (\S+)", line).groups()
+
+    for tail in ("16", "1000"):
+        r = subprocess.run([exe, "ground", "64"], capture_output=True, text=True, timeout=600, env=dict(os.environ, SOLVER_TAIL=tail))
+        assert r.returncode == 0 and "-> 0 failures" in r.stdout, r.stdout + r.stderr
+        assert key(r.stdout.strip().splitlines()[-1]) == key(summary["ground"]), (r.stdout, summary["ground"])
     r = subprocess.run([exe, "superquadric", "24"], capture_output=True, text=True, timeout=900)
     last = r.stdout.strip().splitlines()[-1]
     assert int(last.split("->")[1].split()[0]) <= 2, r.stdout     # an unlucky start may run out of iterations (see solve_and_check)
