@@ -36,6 +36,26 @@ namespace solver {
 struct DeviceTeam {
     int rank, size;
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    // the first warp of the CTA folds (cplb_solver_core.hpp: arr_sum / arr_nanmax / arr_nanmin); butterfly: every lane gets the result
+    __device__ __forceinline__ int lanes() const { return 32; }
+    __device__ __forceinline__ double lane_sum(double v) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ double lane_nanmax(double v) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    __device__ __forceinline__ double lane_nanmin(double v) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = nanmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
 };
 
 constexpr int kThreads = 128;     // vector phases
@@ -108,12 +128,10 @@ __global__ void __launch_bounds__(kThreadsLU, 3) k_tail(const __grid_constant__ 
     Scratch q;
     q.carve(smem, A.S.n, A.S.m, A.S.nnz, true);
     const long long b = (long long)blockIdx.x;
-    const int n = A.S.n, m = A.S.m, nnz = A.S.nnz;
+    const int n = A.S.n;
     const long long inst = A.T.list_cur[b];
     auto eval = [&](const double* x, int count, unsigned flags, double* g, double* jac, double* cost, double* grad) {
-        for (int a = team.rank; a < count; a += team.size)
-            eval_one_instance(P, per_instance ? &Q : nullptr, inst, x + (long long)a * n, g ? g + (long long)a * m : nullptr,
-                              jac ? jac + (long long)a * nnz : nullptr, cost ? cost + a : nullptr, grad ? grad + (long long)a * n : nullptr, flags);
+        eval_points(team.rank, team.size, P, per_instance ? &Q : nullptr, inst, x, count, g, jac, cost, grad, flags);
     };
     unsigned rounds = 0;
     for (int it = it0;;) {

@@ -80,9 +80,16 @@ struct State {
     double *out_cost, *out_viol, *out_dual;
 };
 
+// A team is the set of threads that carry one instance through a phase.  rank / size / sync() as usual; the first lanes() threads
+// form the team's "first warp", which folds team-shared term arrays with lane_* reductions (every lane gets the result; a fixed
+// tree, so the result does not depend on timing).  On the host a team is one thread.
 struct HostTeam {
     int rank = 0, size = 1;
     void sync() const {}
+    int lanes() const { return 1; }
+    double lane_sum(double v) const { return v; }
+    double lane_nanmax(double v) const { return v; }
+    double lane_nanmin(double v) const { return v; }
 };
 
 CPLB_HD bool finite_d(double v) { return v == v && v - v == 0.0; }
@@ -308,22 +315,27 @@ CPLB_HD double jt_lam(const Inst& I, int j, const double* lam)
     return acc;
 }
 
-// thread 0 helpers over team-shared term arrays
-CPLB_HD double arr_nanmax(const double* a, int count, double init)
+// Folds over team-shared term arrays by the team's first warp (callers: threads with rank < lanes() only, all of them): each lane
+// folds a strided share, the lanes combine in a fixed tree.  One thread doing these alone costs ~100 cycles per element (dependent
+// fp64 compares behind shared-memory loads) -- the serial blocks were a tenth of an iteration's latency.
+template <class Team>
+CPLB_HD double arr_nanmax(const Team& team, const double* a, int count, double init)
 {
-    for (int e = 0; e < count; e++) init = nanmax(init, a[e]);
-    return init;
+    for (int e = team.rank; e < count; e += team.lanes()) init = nanmax(init, a[e]);
+    return team.lane_nanmax(init);
 }
-CPLB_HD double arr_nanmin(const double* a, int count, double init)
+template <class Team>
+CPLB_HD double arr_nanmin(const Team& team, const double* a, int count, double init)
 {
-    for (int e = 0; e < count; e++) init = nanmin(init, a[e]);
-    return init;
+    for (int e = team.rank; e < count; e += team.lanes()) init = nanmin(init, a[e]);
+    return team.lane_nanmin(init);
 }
-CPLB_HD double arr_sum(const double* a, int count)
+template <class Team>
+CPLB_HD double arr_sum(const Team& team, const double* a, int count)
 {
     double acc = 0.0;
-    for (int e = 0; e < count; e++) acc += a[e];
-    return acc;
+    for (int e = team.rank; e < count; e += team.lanes()) acc += a[e];
+    return team.lane_sum(acc);
 }
 
 // ---- phase 0a: project the starting point (before the first evaluation) ------------------------------------------------------
@@ -464,23 +476,33 @@ CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T,
         p_su[r] = S.s_hi[r] ? q.gsu[r] * b : -1.0;
     }
     team.sync();
-    if (team.rank == 0) {
-        const double sd = clamp_min(arr_sum(t_sum, nk) / (double)(m + 2 * n + 2 * m), 100.0) / 100.0;
-        const double dual = arr_nanmax(t_res, nk, 0.0) / sd, prim = arr_nanmax(t_prim, m, 0.0);
+    if (team.rank < team.lanes()) {  // the first warp folds; its lane 0 decides
+        const double sd = clamp_min(arr_sum(team, t_sum, nk) / (double)(m + 2 * n + 2 * m), 100.0) / 100.0;
+        const double dual = arr_nanmax(team, t_res, nk, 0.0) / sd, prim = arr_nanmax(team, t_prim, m, 0.0);
         auto comp = [&](double mu) {  // max |gap x multiplier - mu| over the bounded components, / sd
             double e = 0.0;
-            for (int j = 0; j < n; j++) {
+            for (int j = team.rank; j < n; j += team.lanes()) {
                 if (p_xl[j] != -1.0) e = nanmax(e, dabs(p_xl[j] - mu));
                 if (p_xu[j] != -1.0) e = nanmax(e, dabs(p_xu[j] - mu));
             }
-            for (int r = 0; r < m; r++) {
+            for (int r = team.rank; r < m; r += team.lanes()) {
                 if (p_sl[r] != -1.0) e = nanmax(e, dabs(p_sl[r] - mu));
                 if (p_su[r] != -1.0) e = nanmax(e, dabs(p_su[r] - mu));
             }
-            return e / sd;
+            return team.lane_nanmax(e) / sd;
         };
         const double E0 = nanmax(nanmax(dual, prim), comp(0.0));
-        const double vmax = arr_nanmax(t_viol, m, 0.0);
+        const double vmax = arr_nanmax(team, t_viol, m, 0.0);
+        // barrier update candidates need comp(mu) from every lane: evaluate the (uniform) recursion on all lanes
+        double mu_next = mu_old;
+        {
+            const double dp0 = nanmax(dual, prim);
+            for (int rep = 0; rep < 4; rep++) {
+                const double Emu = nanmax(dp0, comp(mu_next));
+                if (Emu <= 10.0 * mu_next && mu_next > O.tol / 10.0) mu_next = dmax(dmin(0.2 * mu_next, pow(mu_next, 1.5)), O.tol / 10.0);
+            }
+        }
+      if (team.rank == 0) {
         // IPOPT's test (scaled error <= tol, unscaled violation <= constr_viol_tol) switches the instance to the feasibility
         // polish; it is done when the constraints hold to polish_viol_tol as well
         if (E0 <= O.tol && vmax <= O.constr_viol_tol) T.polish[i] = 1;
@@ -495,13 +517,8 @@ CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T,
         }
         if (active) {
             T.iters[i] += 1;
-            // monotone barrier update (Waechter & Biegler eq. 7)
-            double mu = mu_old;
-            const double dp0 = nanmax(dual, prim);
-            for (int rep = 0; rep < 4; rep++) {
-                const double Emu = nanmax(dp0, comp(mu));
-                if (Emu <= 10.0 * mu && mu > O.tol / 10.0) mu = dmax(dmin(0.2 * mu, pow(mu, 1.5)), O.tol / 10.0);
-            }
+            // monotone barrier update (Waechter & Biegler eq. 7): computed above by the whole warp
+            const double mu = mu_next;
             T.mu[i] = mu;
             T.tau[i] = dmax(1.0 - mu, 0.99);
             // slot in the working set of this round (the tail kernel keeps an instance in its slot: nobody else is waiting)
@@ -518,6 +535,7 @@ CPLB_HD void phase_round_begin(const Team& team, const Shape& S, const State& T,
         }
         T.active[i] = active;
         q.red[0] = (double)active;
+      }
     }
     team.sync();
     // forward-difference points of the Lagrangian Hessian: point a < nf perturbs free variable a, point nf is x itself
@@ -742,16 +760,19 @@ CPLB_HD void phase_kkt(const Team& team, const Shape& S, const State& T, const O
     }
     team.sync();
     const bool pol = T.polish[i] != 0;
-    if (team.rank == 0) {
-        const double h1 = arr_sum(t_h1, m), dphi = arr_sum(t_dphi, nk), lb = arr_sum(t_lb, nk), lmax = arr_nanmax(t_lmax, m, 0.0);
+    if (team.rank < team.lanes()) {
+        const double h1 = arr_sum(team, t_h1, m), dphi = arr_sum(team, t_dphi, nk), lb = arr_sum(team, t_lb, nk), lmax = arr_nanmax(team, t_lmax, m, 0.0);
+        const double a_d_min = arr_nanmin(team, t_ad, nk, INFINITY);
+      if (team.rank == 0) {
         const double phi0 = dobj * T.f[i] - mu * lb;
         const double nu_need = (dphi + 0.5 * clamp_min(quad, 0.0)) / (0.9 * clamp_min(h1, 1e-300));
         const double nu = nanmax(clamp_min(nu_need, 0.0), lmax) * 1.1 + 1e-3;
         T.nu[i] = nu;
         T.Dm[i] = dphi - nu * h1;
         T.merit0[i] = phi0 + nu * h1;
-        T.a_d[i] = pol ? 0.0 : clamp_max(arr_nanmin(t_ad, nk, INFINITY), 1.0);
+        T.a_d[i] = pol ? 0.0 : clamp_max(a_d_min, 1.0);
         T.pol[i] = pol ? 1 : 0;
+      }
     }
     team.sync();
 
@@ -824,12 +845,15 @@ CPLB_HD void phase_kkt(const Team& team, const Shape& S, const State& T, const O
         t_R0[r] = S.is_eq[r] ? dabs(cs - sl[r]) : ((S.s_hi[r] ? clamp_min(cs - cu_s[r], 0.0) : 0.0) + (S.s_lo[r] ? clamp_min(cl_s[r] - cs, 0.0) : 0.0));
     }
     team.sync();
-    if (team.rank == 0) {
-        const double a_p = clamp_max(arr_nanmin(t_ap, nk, INFINITY), 1.0);
-        T.a_p[i] = a_p;
-        T.tiny[i] = arr_nanmax(t_tiny, n, 0.0) < 1e-13 ? 1 : 0;
-        T.R0[i] = arr_nanmax(t_R0, m, 0.0);
-        q.red[6] = a_p;
+    if (team.rank < team.lanes()) {
+        const double a_p = clamp_max(arr_nanmin(team, t_ap, nk, INFINITY), 1.0);
+        const double tiny_max = arr_nanmax(team, t_tiny, n, 0.0), R0 = arr_nanmax(team, t_R0, m, 0.0);
+        if (team.rank == 0) {
+            T.a_p[i] = a_p;
+            T.tiny[i] = tiny_max < 1e-13 ? 1 : 0;
+            T.R0[i] = R0;
+            q.red[6] = a_p;
+        }
     }
     team.sync();
     // line-search candidates x + alpha0 2^-k dx, k = 0 .. kCandidates - 1
@@ -879,18 +903,20 @@ CPLB_HD Trial merit_test(const Team& team, const Inst& I, Scratch& q, const doub
         st_out[r] = st;
     }
     team.sync();
-    if (team.rank == 0) {
-        const bool ct_fin = arr_sum(t_bad, m) == 0.0;
+    if (team.rank < team.lanes()) {
+        const bool ct_fin = arr_sum(team, t_bad, m) == 0.0;
         bool ok;
         if (pol) {
-            ok = ct_fin && arr_nanmax(t_viol, m, 0.0) < T.R0[i];
+            ok = ct_fin && arr_nanmax(team, t_viol, m, 0.0) < T.R0[i];
         } else {
-            const double mt = (T.dobj[i] * cost_raw - mu * arr_sum(t_lb, nk)) + nu * arr_sum(t_viol, m);
+            const double mt = (T.dobj[i] * cost_raw - mu * arr_sum(team, t_lb, nk)) + nu * arr_sum(team, t_viol, m);
             const double m0 = T.merit0[i];
             ok = finite_d(mt) && mt <= (m0 + 10.0 * 2.2e-16 * dabs(m0)) + 1e-4 * AL * T.Dm[i];
         }
-        q.red[90] = ok ? 1.0 : 0.0;
-        q.red[91] = ct_fin ? 1.0 : 0.0;
+        if (team.rank == 0) {
+            q.red[90] = ok ? 1.0 : 0.0;
+            q.red[91] = ct_fin ? 1.0 : 0.0;
+        }
     }
     team.sync();
     Trial t;
@@ -978,13 +1004,15 @@ CPLB_HD void phase_ls_first(const Team& team, const Shape& S, const State& T, co
         t_bad[n + r] = finite_d(dl) ? 0.0 : 1.0;
     }
     team.sync();
-    if (team.rank == 0) {
-        const double a_c = clamp_max(arr_nanmin(t_ac, nk, INFINITY), 1.0);
-        const bool fin = arr_sum(t_bad, nk) == 0.0;
+    if (team.rank < team.lanes()) {
+        const double a_c = clamp_max(arr_nanmin(team, t_ac, nk, INFINITY), 1.0);
+        const bool fin = arr_sum(team, t_bad, nk) == 0.0;
+      if (team.rank == 0) {
         T.a_soc[i] = a_c;
         T.soc_valid[i] = fin ? 1 : 0;
         q.red[1] = a_c;
         q.red[2] = fin ? 1.0 : 0.0;
+      }
     }
     team.sync();
     for (int j = team.rank; j < n; j += team.size) Xsoc[j] = q.red[2] != 0.0 ? x[j] + q.red[1] * q.dx[j] : x[j];
