@@ -128,7 +128,6 @@ __global__ void __launch_bounds__(kThreadsLU, 3) k_tail(const __grid_constant__ 
     Scratch q;
     q.carve(smem, A.S.n, A.S.m, A.S.nnz, true);
     const long long b = (long long)blockIdx.x;
-    const int n = A.S.n;
     const long long inst = A.T.list_cur[b];
     auto eval = [&](const double* x, int count, unsigned flags, double* g, double* jac, double* cost, double* grad) {
         eval_points(team.rank, team.size, P, per_instance ? &Q : nullptr, inst, x, count, g, jac, cost, grad, flags);
