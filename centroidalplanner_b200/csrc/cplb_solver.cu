@@ -65,7 +65,15 @@ struct KernelArgs {
     Shape S;
     State T;
     Options O;
+    int mats_in_global;  // dense Jacobian and Hessian of a slot in global memory (State::jd_slot / h0_slot) instead of the team's block
 };
+
+// Scratch::carve with the slot's external matrices where the launch uses them
+__device__ __forceinline__ void carve_full(Scratch& q, double* smem, const KernelArgs& A, long long b)
+{
+    q.carve(smem, A.S.n, A.S.m, A.S.nnz, true, A.mats_in_global ? A.T.jd_slot + b * A.S.m * A.S.n : nullptr,
+            A.mats_in_global ? A.T.h0_slot + b * A.S.n * A.S.n : nullptr);
+}
 
 __global__ void __launch_bounds__(kThreads) k_init_x(const __grid_constant__ KernelArgs A, const double* x0)
 {
@@ -93,8 +101,9 @@ __global__ void __launch_bounds__(kThreadsLU) k_kkt(const __grid_constant__ Kern
     extern __shared__ __align__(16) double smem[];
     DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
     Scratch q;
-    q.carve(smem, A.S.n, A.S.m, A.S.nnz, true);
-    phase_kkt(team, A.S, A.T, A.O, (long long)blockIdx.x, q);
+    const long long b = (long long)blockIdx.x;
+    carve_full(q, smem, A, b);
+    phase_kkt(team, A.S, A.T, A.O, b, q);
 }
 
 __global__ void __launch_bounds__(kThreads) k_ls_first(const __grid_constant__ KernelArgs A)
@@ -102,8 +111,9 @@ __global__ void __launch_bounds__(kThreads) k_ls_first(const __grid_constant__ K
     extern __shared__ __align__(16) double smem[];
     DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
     Scratch q;
-    q.carve(smem, A.S.n, A.S.m, A.S.nnz, true);
-    phase_ls_first(team, A.S, A.T, A.O, (long long)blockIdx.x, q);
+    const long long b = (long long)blockIdx.x;
+    carve_full(q, smem, A, b);
+    phase_ls_first(team, A.S, A.T, A.O, b, q);
 }
 
 __global__ void __launch_bounds__(kThreads) k_ls_select(const __grid_constant__ KernelArgs A)
@@ -126,8 +136,8 @@ __global__ void __launch_bounds__(kThreadsLU, 3) k_tail(const __grid_constant__ 
     extern __shared__ __align__(16) double smem[];
     DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
     Scratch q;
-    q.carve(smem, A.S.n, A.S.m, A.S.nnz, true);
     const long long b = (long long)blockIdx.x;
+    carve_full(q, smem, A, b);
     const long long inst = A.T.list_cur[b];
     auto eval = [&](const double* x, int count, unsigned flags, double* g, double* jac, double* cost, double* grad) {
         eval_points(team.rank, team.size, P, per_instance ? &Q : nullptr, inst, x, count, g, jac, cost, grad, flags);
@@ -369,7 +379,13 @@ cudaError_t solve_device(const CplbParams& P, int im_kernel, const CplbInstParam
     A.T.out_dual = dual;
 
     Scratch probe;
-    const size_t smem = probe.carve(nullptr, S.n, S.m, S.nnz, true) * sizeof(double);
+    // Four teams per SM are what the registers allow (256 threads x 64): where the full block is too large for that, the dense
+    // Jacobian and the Hessian move to global memory (4 contacts: 71 KB -> 49 KB; 4,096 ground solves 0.0891 -> 0.0868 s); smaller
+    // problems keep them in shared memory (CoMPlanner: 35 KB, and the global round trips would cost 10 %)
+    double dummy = 0.0;
+    size_t smem = probe.carve(nullptr, S.n, S.m, S.nnz, true) * sizeof(double);
+    A.mats_in_global = smem > (227 * 1024) / 4 - 1024 ? 1 : 0;
+    if (A.mats_in_global) smem = probe.carve(nullptr, S.n, S.m, S.nnz, true, &dummy, &dummy) * sizeof(double);
     const size_t smem_small = probe.carve(nullptr, S.n, S.m, S.nnz, false) * sizeof(double);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     for (const void* k : {(const void*)k_round_begin, (const void*)k_kkt, (const void*)k_ls_first, (const void*)k_ls_select, (const void*)k_tail})

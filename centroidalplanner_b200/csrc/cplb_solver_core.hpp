@@ -70,6 +70,7 @@ struct State {
     double *a_p, *a_d, *merit0, *Dm, *nu, *R0, *quad;
     int32_t *tiny, *pol, *okK, *accepted0;
     double *lu, *lu_dinv;                                      // [N nk nk], [N nk]: factors kept for the second-order correction
+    double *jd_slot, *h0_slot;                                 // [N m n], [N n n]: dense Jacobian / Hessian of a slot (GPU: Scratch::carve)
     int32_t* piv;                                              // [N nk]
     // widened evaluation buffers
     double *x_fd, *grad_fd, *jac_fd;                           // [N (nf+1) n], [N (nf+1) n], [N (nf+1) nnz]
@@ -225,7 +226,10 @@ struct Scratch {
     int ld;
     static constexpr int kTerms = 8;  // per-element term arrays in `e` (kTerms x nk)
     // returns the number of doubles used; base may be nullptr (size query)
-    CPLB_HD size_t carve(double* base, int n, int m, int nnz, bool full)
+    // jd_ext / h0_ext: where the dense Jacobian and the Hessian live when not in the team's own block (the GPU keeps them in
+    // global memory, per slot: they are written once per iteration and only re-read to rebuild K, and without them a team's
+    // shared memory drops from 71 KB to 49 KB at four contacts -- four teams per SM instead of three)
+    CPLB_HD size_t carve(double* base, int n, int m, int nnz, bool full, double* jd_ext = nullptr, double* h0_ext = nullptr)
     {
         const int nk = n + m;
         ld = nk | 1;
@@ -253,8 +257,8 @@ struct Scratch {
             K = take((size_t)nk * ld);
             rhs = take(nk);
             sol = take(nk);
-            Jd = take((size_t)m * n);
-            H0 = take((size_t)n * n);
+            Jd = jd_ext ? jd_ext : take((size_t)m * n);
+            H0 = h0_ext ? h0_ext : take((size_t)n * n);
             w = take(nnz);
             glb = take(n);
         }
@@ -1189,6 +1193,7 @@ inline std::vector<StateField> state_fields(State& T, const ShapeHost& S)
     D(T.a_p, 1); D(T.a_d, 1); D(T.merit0, 1); D(T.Dm, 1); D(T.nu, 1); D(T.R0, 1); D(T.quad, 1);
     I(T.tiny, 1); I(T.pol, 1); I(T.okK, 1); I(T.accepted0, 1);
     D(T.lu, nk * nk); D(T.lu_dinv, nk); I(T.piv, nk);
+    D(T.jd_slot, m * n); D(T.h0_slot, n * n);
     D(T.x_fd, P * n); D(T.grad_fd, P * n); D(T.jac_fd, P * nnz);
     D(T.x_ls, KC * n); D(T.g_ls, KC * m); D(T.cost_ls, KC);
     D(T.x_soc, n); D(T.g_soc, m); D(T.cost_soc, 1); D(T.dx_soc, n); D(T.ds_soc, m); D(T.dlam_soc, m); D(T.a_soc, 1);

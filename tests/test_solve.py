@@ -385,6 +385,39 @@ def test_testbasic_through_the_native_solve_round(case, cuda_device):
 
 
 @pytest.mark.gpu
+def test_native_round_on_an_eight_contact_problem(cuda_device):
+    """Config 4's shape through cplb_solve_device: 8 contacts (n = 75, m = 54: a 129 x 129 KKT matrix, 133 KB of shared memory; the
+    dense Jacobian and the Hessian live in global memory).  TestBasic's ground set-up on eight contacts; every solved instance must
+    be in static equilibrium on the ground with every force inside its cone."""
+    names = ["l_foot_a", "l_foot_b", "r_foot_a", "r_foot_b", "l_hand_a", "l_hand_b", "r_hand_a", "r_hand_b"][::-1]
+    env = cpl.Ground()
+    env.SetGroundZ(0.1)
+    env.SetMu(0.5)
+    prob = cpl.BatchedCplProblem(names, MASS, env)
+    prob.SetCoMWeight(2.0)
+    prob.SetForceWeight(0.0)
+    for nm in names:
+        prob.SetPosBounds(nm, [-0.3, -0.3, 0.0], [0.3, 0.3, 1.0])
+    wrench = np.array([100.0, 0, 0, 0, 0, 100.0])
+    prob.SetManipulationWrench(list(wrench))
+    x0 = starts(prob, 40, seed=11, device=cuda_device)
+    res = cpl.NativeInteriorPoint().Solve(prob, x0)
+    ok = (res.status == SUCCESS).cpu().numpy()
+    assert ok[0] and ok.mean() >= 0.9, (res.status.tolist(), res.iterations.tolist())
+    for com, cmap in np.asarray(solution_maps(names, res.x.cpu().numpy()[ok]), dtype=object):
+        F_sum, T_sum = np.zeros(3), np.zeros(3)
+        for F, p, n in cmap.values():
+            F_sum += F
+            T_sum += np.cross(p - com, F)
+            assert abs(p[2] - 0.1) < 1e-6 and abs(n[2] - 1.0) < 1e-6
+            assert -F.dot(n) <= RELAX and np.linalg.norm(F - n.dot(F) * n) - 0.5 * F.dot(n) <= RELAX
+        assert np.abs(F_sum - (wrench[:3] - MASS * np.array([0.0, 0.0, G]))).max() < 1e-6
+        assert np.abs(T_sum - wrench[3:]).max() < 1e-4
+    lock = cpl.NativeInteriorPoint(tail_instances=0).Solve(prob, x0)
+    assert torch.equal(lock.x.view(torch.int64), res.x.view(torch.int64)) and torch.equal(lock.iterations, res.iterations)
+
+
+@pytest.mark.gpu
 def test_native_round_with_per_instance_parameters(cuda_device):
     """A sweep: every instance solves ITS planning problem (own manipulation wrench and mass) through cplb_solve_device, and must
     balance its own wrench and weight (the equilibrium lines of TEST_F testGroundEnv, tests/TestBasic.cpp:131-136).  Lock-step
