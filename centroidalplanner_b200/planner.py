@@ -5,8 +5,8 @@ src/CentroidalPlanner.cpp) and `BatchedCoMPlanner` ~ cpl::CoMPlanner (CoMPlanner
 setters/getters with the same checks and exception types, on top of a `BatchedCplProblem` that evaluates N instances.
 `Solve()` runs a batch of instances through a lock-step solver over the batched evaluator: IPOPT stays the production
 host solver but is not part of this repository nor installed in its image, so the default is the
-interior-point stand-in of `lockstep_solver`; the facades also hand out the batched problem (`GetCplProblem`) whose
-evaluation entry points any other solver drives.
+native lock-step solve round (`NativeInteriorPoint`: cplb_solve_device); the facades also hand out the batched problem
+(`GetCplProblem`) whose evaluation entry points any other solver drives.
 """
 from __future__ import annotations
 
@@ -29,19 +29,20 @@ class BatchedCentroidalPlanner:
         instance's starting point (default: one instance at `lockstep_solver.default_start` on the problem's device);
         returns one `Solution` dict per instance (CplProblem::GetSolution, sorted-name order) and keeps the solver's
         report in `last_solve`.  The reference runs ifopt::IpoptSolver here; IPOPT is not part of this repository, so the
-        default `solver` is the lock-step interior-point driver of `lockstep_solver` (same NLP, same callbacks, batched) --
-        anything with `Solve(problem, x0, per_instance)` can take its place.  Like the reference, a failed solve is not
+        default `solver` is the native lock-step solve round (`NativeInteriorPoint`: same NLP, batched, on the GPU) --
+        anything with `Solve(problem, x0, per_instance)` can take its place (e.g. `LockStepInteriorPoint`, the torch driver).  Like the reference, a failed solve is not
         raised (`:29-32`): inspect `last_solve.status`."""
         import torch
 
-        from .lockstep_solver import LockStepInteriorPoint, default_start
+        from .lockstep_solver import default_start
+        from .native_solver import NativeInteriorPoint
 
         prob = self._cpl_problem
         if x0 is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("Solve() evaluates on a CUDA device and none is available (there is no CPU evaluation path)")
             x0 = default_start(prob, 1, device=torch.device("cuda", torch.cuda.current_device()))
-        self.last_solve = (solver or LockStepInteriorPoint()).Solve(prob, x0, per_instance)
+        self.last_solve = (solver or NativeInteriorPoint()).Solve(prob, x0, per_instance)
         return [prob.GetSolution(xi) for xi in self.last_solve.x.detach().cpu().numpy()]
 
     # ---- helpers ------------------------------------------------------------------------------------

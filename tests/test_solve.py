@@ -264,8 +264,10 @@ def test_gpu_solve_trajectory_is_the_oracle_s(case, cuda_device):
 
 
 @pytest.mark.gpu
-def test_com_planner_facade_solve(cuda_device):
-    """TEST_F(TestBasic, testCoMPlanner) (tests/TestBasic.cpp:225-292) call for call through the facade mirror."""
+@pytest.mark.parametrize("driver", ["native", "torch"])
+def test_com_planner_facade_solve(driver, cuda_device):
+    """TEST_F(TestBasic, testCoMPlanner) (tests/TestBasic.cpp:225-292) call for call through the facade mirror; Solve() runs the
+    native solve round by default, any other driver on request."""
     planner = cpl.BatchedCoMPlanner(NAMES, MASS)
     planner.SetMu(0.5)
     assert planner.GetMu() == 0.5
@@ -277,8 +279,9 @@ def test_com_planner_facade_solve(cuda_device):
     assert planner.GetLiftingContacts() == ["contact4"]
     for c in NAMES:
         planner.SetForceThreshold(c, 20.0)
-    sols = planner.Solve()
+    sols = planner.Solve() if driver == "native" else planner.Solve(solver=LockStepInteriorPoint())
     assert planner.last_solve.ok()
+    assert (getattr(planner.last_solve, "tail_instances", 0) == 1) == (driver == "native")   # one instance: straight into the tail
     sol = sols[0]
     assert list(sol["contact_values_map"]) == sorted(NAMES)
     F_sum, T_sum = np.zeros(3), np.zeros(3)
