@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) k_round_begin(const __grid_constant_
     phase_round_begin(team, A.S, A.T, A.O, (long long)blockIdx.x, q, first, last, n_active);
 }
 
-__global__ void __launch_bounds__(kThreadsLU) k_kkt(const __grid_constant__ KernelArgs A)
+__global__ void __launch_bounds__(kThreadsLU, 4) k_kkt(const __grid_constant__ KernelArgs A)
 {
     extern __shared__ __align__(16) double smem[];
     DeviceTeam team{(int)threadIdx.x, (int)blockDim.x};
