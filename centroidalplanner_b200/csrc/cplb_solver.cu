@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads) k_ls_select(const __grid_constant__ 
 }
 
 // The tail: one CTA carries one instance through ALL its remaining iterations, the four evaluations of an iteration done in
-// place by eval_one_instance (one thread per evaluation point: the batched kernels' arithmetic as a device function).  Entered
+// place by eval_points (cplb_eval_inline.cuh: the batched kernels' arithmetic as a device function, spread over the team).  Entered
 // once the working set no longer fills the GPU: from there a lock-step round costs its latency floor whatever the count, and
 // every round would be paid by the slowest instance; here each instance pays only its own iterations and the host waits once.
 __global__ void __launch_bounds__(kThreadsLU, 2) k_tail(const __grid_constant__ KernelArgs A, const __grid_constant__ CplbParams P,
