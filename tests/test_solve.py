@@ -388,6 +388,19 @@ def test_testbasic_through_the_native_solve_round(case, cuda_device):
 
 
 @pytest.mark.gpu
+def test_native_round_is_deterministic(cuda_device):
+    """Finished instances leave the working set in the order their CTAs get there (an atomic counter), so the slot an instance
+    occupies differs from run to run; what is computed for it must not: two solves of the same 3,000 starts end at the same bits."""
+    prob, names, par = product_problem("ground")
+    x0 = starts(prob, 3000, seed=17, device=cuda_device)
+    a = cpl.NativeInteriorPoint().Solve(prob, x0)
+    b = cpl.NativeInteriorPoint().Solve(prob, x0)
+    assert a.rounds > 0 and a.tail_instances > 0 and a.ok()
+    assert torch.equal(a.iterations, b.iterations) and torch.equal(a.status, b.status)
+    assert torch.equal(a.x.view(torch.int64), b.x.view(torch.int64)) and torch.equal(a.lam.view(torch.int64), b.lam.view(torch.int64))
+
+
+@pytest.mark.gpu
 def test_native_round_on_an_eight_contact_problem(cuda_device):
     """Config 4's shape through cplb_solve_device: 8 contacts (n = 75, m = 54: a 129 x 129 KKT matrix, 133 KB of shared memory; the
     dense Jacobian and the Hessian live in global memory).  TestBasic's ground set-up on eight contacts; every solved instance must
