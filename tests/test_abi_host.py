@@ -364,6 +364,30 @@ def test_jacobian_slot_sources_against_the_oracle(case):
         prob._jac_flag("dense")
 
 
+def test_slice_helpers_check_their_arguments():
+    """cplb_get_jacobian_slot_sources / cplb_expand_jacobian / cplb_unpack_jacobian straight through the C ABI: NULL outputs are a
+    size query, NULL inputs and negative counts are errors with a message, zero instances is a no-op."""
+    lib = _cabi.load()
+    prob, o, gen = make_pair("ground4")
+    nv = C.c_int32(-1)
+    assert lib.cplb_get_jacobian_slot_sources(prob._h, C.byref(nv), None, None) == _cabi.OK and nv.value == 54
+    assert lib.cplb_get_jacobian_slot_sources(None, C.byref(nv), None, None) == _cabi.NULL_POINTER
+    x = gen(3)
+    comp = np.zeros((3, 54))
+    full = np.zeros((3, o.nnz))
+    dp = _cabi.dp
+    assert lib.cplb_expand_jacobian(prob._h, 0, None, None, None) == _cabi.OK
+    assert lib.cplb_expand_jacobian(prob._h, -1, x.ctypes.data_as(dp), comp.ctypes.data_as(dp), full.ctypes.data_as(dp)) == _cabi.INVALID_ARGUMENT
+    assert b"negative" in lib.cplb_last_error()
+    assert lib.cplb_expand_jacobian(prob._h, 3, None, comp.ctypes.data_as(dp), full.ctypes.data_as(dp)) == _cabi.NULL_POINTER
+    assert lib.cplb_expand_jacobian(prob._h, 3, x.ctypes.data_as(dp), comp.ctypes.data_as(dp), None) == _cabi.NULL_POINTER
+    assert lib.cplb_unpack_jacobian(prob._h, 3, None, full.ctypes.data_as(dp)) == _cabi.NULL_POINTER
+    # solver options: defaults as documented in the header
+    opt = _cabi.SolverOptions()
+    lib.cplb_solver_default_options(C.byref(opt))
+    assert (opt.tol, opt.max_iter, opt.max_backtracks, opt.tail_instances) == (1e-3, 500, 30, -1)
+
+
 def same_bits_host(a, b):
     na, nb = np.isnan(a), np.isnan(b)
     return bool((na == nb).all() and (a[~na] == b[~nb]).all())
