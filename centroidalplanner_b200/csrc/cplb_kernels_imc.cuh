@@ -310,7 +310,13 @@ cudaError_t launch_imc_roles(const CplbParams& P, const CplbIo& io, unsigned fla
     cudaError_t e = resident_grid(reinterpret_cast<const void*>(kern), threads, smem, &resident);
     if (e != cudaSuccess) return e;
     const long long tiles = (io.N + TI - 1) / TI;
-    const unsigned blocks = (unsigned)(tiles < resident ? tiles : resident);
+    // Full rows with shared parameters on Ground / no environment: a grid of 2x (4x for long launches) the CTAs that fit at once.
+    // The CTAs of the first wave finish at different times and the waiting ones take their places, which keeps the co-resident
+    // CTAs of an SM out of lock step (all computing, nobody storing) -- measured, profiles/r02_instance_major.md: 65,536 ground4
+    // instances 85.8 -> 88.1 % of the roofline, 1,048,576: 89.1 -> 92 %.  The other variants lose with it and stay at 1x.
+    const bool oversubscribe = PACKED == 0 && !PERINST && ENV != CPLB_ENV_SUPERQUADRIC_K && P.nc <= 4;
+    const long long want = !oversubscribe ? resident : (long long)resident * (tiles >= 16LL * resident ? 4 : 2);
+    const unsigned blocks = (unsigned)(tiles < want ? tiles : want);
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     // complete tiles hold TI (even) instances: TI*n*8, TI*m*8, TI*nnz*8 bytes are multiples of 16
     const int aligned16 = al16(io.x) && al16(io.g) && al16(io.jac) && al16(io.grad) && (TI % 2 == 0);
@@ -353,7 +359,10 @@ cudaError_t launch_imc_ti(const CplbParams& P, const CplbIo& io, unsigned flags,
 template <int ENV>
 cudaError_t launch_imc_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, cudaStream_t st)
 {
-    switch (cta_tile_instances(P.nc)) {
+    int ti = cta_tile_instances(P.nc);
+    // (same measurement: with the oversubscribed grid, half-size tiles are the better granularity up to 4 contacts)
+    if (!(flags & (CPLB_JAC_PACKED_K | CPLB_JAC_COMPUTED_K)) && Q == nullptr && ENV != CPLB_ENV_SUPERQUADRIC_K && P.nc <= 4) ti = 16;
+    switch (ti) {
     case 32: return launch_imc_ti<ENV, 32>(P, io, flags, Q, st);
     case 16: return launch_imc_ti<ENV, 16>(P, io, flags, Q, st);
     case 8: return launch_imc_ti<ENV, 8>(P, io, flags, Q, st);
