@@ -423,7 +423,10 @@ namespace cplb {
 template <int ENV>
 cudaError_t launch_im_env(const CplbParams& P, const CplbIo& io, unsigned flags, const CplbInstParams* Q, int im_kernel, cudaStream_t st)
 {
-    const bool cta_tile = im_kernel == CPLB_IM_CTA_TILE || (im_kernel == CPLB_IM_AUTO && instance_major_auto_is_cta_tile(P.nc)) ||
+    // (measured, profiles/r02_variants.md: a Superquadric evaluation with any other output set than g + Jacobian -- the variant with
+    // run-time output flags -- runs at 64-76 % of the roofline on the warp-tile kernel and at 47-53 % on the CTA-tile one)
+    const bool sq_other_outputs = ENV == CPLB_ENV_SUPERQUADRIC_K && (flags & 15u) != (CPLB_WANT_G | CPLB_WANT_J);
+    const bool cta_tile = im_kernel == CPLB_IM_CTA_TILE || (im_kernel == CPLB_IM_AUTO && instance_major_auto_is_cta_tile(P.nc) && !sq_other_outputs) ||
                           (flags & (CPLB_JAC_PACKED_K | CPLB_JAC_COMPUTED_K));  // packed Jacobian slices exist in the CTA-tile kernel only
     if (cta_tile) return launch_imc_env<ENV>(P, io, flags, Q, st);
     // lanes per instance: the smallest power of two >= nc (capped at 8; more contacts loop)
