@@ -426,7 +426,11 @@ cudaError_t launch_im_env(const CplbParams& P, const CplbIo& io, unsigned flags,
     // (measured, profiles/r02_variants.md: a Superquadric evaluation with any other output set than g + Jacobian -- the variant with
     // run-time output flags -- runs at 64-76 % of the roofline on the warp-tile kernel and at 47-53 % on the CTA-tile one)
     const bool sq_other_outputs = ENV == CPLB_ENV_SUPERQUADRIC_K && (flags & 15u) != (CPLB_WANT_G | CPLB_WANT_J);
-    const bool cta_tile = im_kernel == CPLB_IM_CTA_TILE || (im_kernel == CPLB_IM_AUTO && instance_major_auto_is_cta_tile(P.nc) && !sq_other_outputs) ||
+    // (same table: with more than 8 contacts the CTA-tile kernel wins at 65,536 instances, 81 -> 85 %, and loses in long launches,
+    // 96 -> 89 % at 1,048,576; warp-tile ahead from 131,072 on: 89.7 vs 87.6 %)
+    const bool many_contacts_long = P.nc > 8 && io.N >= (1LL << 17);
+    const bool cta_tile = im_kernel == CPLB_IM_CTA_TILE ||
+                          (im_kernel == CPLB_IM_AUTO && instance_major_auto_is_cta_tile(P.nc) && !sq_other_outputs && !many_contacts_long) ||
                           (flags & (CPLB_JAC_PACKED_K | CPLB_JAC_COMPUTED_K));  // packed Jacobian slices exist in the CTA-tile kernel only
     if (cta_tile) return launch_imc_env<ENV>(P, io, flags, Q, st);
     // lanes per instance: the smallest power of two >= nc (capped at 8; more contacts loop)
