@@ -400,7 +400,8 @@ cplb_status cplb_host_free(void *ptr);
 #define CPLB_KERNEL_PER_INSTANCE 2
 cplb_status cplb_set_component_major_kernel(cplb_problem *p, int32_t kernel);
 /* The same for the two INSTANCE_MAJOR kernels: a warp per tile of 32/LPI instances (lanes = an (instance, contact) grid) or a
- * CTA per tile (one warp per contact, lanes = consecutive instances).  Same arithmetic, same bits; AUTO picks by shape. */
+ * CTA per tile (one warp per contact, lanes = consecutive instances).  Same arithmetic, same bits; AUTO picks by shape and, for
+ * a few shapes, by the requested outputs and the batch size (measured crossovers: DESIGN.md 4.2b). */
 #define CPLB_KERNEL_WARP_TILE 1
 #define CPLB_KERNEL_CTA_TILE 2
 cplb_status cplb_set_instance_major_kernel(cplb_problem *p, int32_t kernel);
