@@ -158,16 +158,19 @@ int main(int argc, char** argv)
 {
     const std::string which = argc > 1 ? argv[1] : "ground";
     const long long N = argc > 2 ? atoll(argv[2]) : 16;
-    const char* names[4] = {"contact1", "contact2", "contact3", "contact4"};
-    const int nc = which == "simple" ? 1 : 4;
+    // (ground8: config 4's shape -- 8 contacts, names given r_* first so that vector order != sorted order; a 129 x 129 KKT matrix)
+    const char* names4[4] = {"contact1", "contact2", "contact3", "contact4"};
+    const char* names8[8] = {"r_hand_b", "r_hand_a", "l_hand_b", "l_hand_a", "r_foot_b", "r_foot_a", "l_foot_b", "l_foot_a"};
+    const int nc = which == "simple" ? 1 : (which == "ground8" ? 8 : 4);
+    const char** names = nc == 8 ? names8 : names4;
     const int env = which == "superquadric" ? CPL_ORACLE_ENV_SUPERQUADRIC : (which == "complanner" ? CPL_ORACLE_ENV_NONE : CPL_ORACLE_ENV_GROUND);
     cpl_oracle* o = cpl_oracle_new(nc, names, env, 100.0);
     const double wrench[6] = {100, 0, 0, 0, 0, 100};
-    if (which == "ground") {
+    if (which == "ground" || which == "ground8") {
         cpl_oracle_set_ground_z(o, 0.1);
         cpl_oracle_set_mu(o, 0.5);
         cpl_oracle_set_com_weight(o, 2.0);
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < nc; k++) {
             cpl_oracle_set_force_weight(o, k, 0.0);
             const double lb[3] = {-0.3, -0.3, 0.0}, ub[3] = {0.3, 0.3, 1.0};
             cpl_oracle_set_var_bounds(o, 2, k, lb, ub);

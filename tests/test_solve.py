@@ -337,7 +337,7 @@ def test_native_solve_round_on_the_cpu_with_the_oracle(tmp_path):
                            "-I", os.path.join(root, "centroidalplanner_b200", "csrc"), os.path.join(root, "tests", "native", "solver_host_check.cpp"),
                            "-o", exe, "-L", os.path.join(root, "oracle"), "-lcpl_oracle", f"-Wl,-rpath,{os.path.join(root, 'oracle')}", "-lpthread"])
     summary = {}
-    for which, n in (("ground", 64), ("complanner", 64), ("simple", 64)):
+    for which, n in (("ground", 64), ("complanner", 64), ("simple", 64), ("ground8", 12)):   # ground8: 8 contacts, a 129 x 129 KKT matrix
         r = subprocess.run([exe, which, str(n)], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "-> 0 failures" in r.stdout, r.stdout + r.stderr
         summary[which] = r.stdout.strip().splitlines()[-1]
