@@ -13,6 +13,10 @@
 //   * the x-independent Jacobian slots (cplb_get_jacobian_constants: 72 of 174 for a 4-contact Ground problem) are
 //     written into the CTA's output tile ONCE, before the first tile: the tile buffer persists across the CTA's tiles
 //     and nothing else ever writes those slots.
+// Two launch-level choices on top, both by measurement (profiles/r02_instance_major.md): full rows with shared parameters give
+// every (instance, contact) pair TWO threads with complementary shares of the contact's rows (ROLES = 2, contact_rows<..., PARTS>),
+// and on Ground / no environment up to 4 contacts they use 16-instance tiles on a grid of 2x (4x for long launches) the CTAs that
+// fit at once instead of a strictly persistent grid (launch_imc_roles).
 // Data movement is unchanged: one cp.async.bulk (TMA) load of the tile's T*n contiguous doubles of x into one of two
 // buffers (the next tile's load is issued before the current one is consumed), outputs leave with cp.async.bulk stores and
 // the CTA waits for the engine to have READ the tile only right before the next tile's first write to it.
